@@ -1,0 +1,446 @@
+// micloc_api.cu -- C-ABI of the float SNN chain (include/micloc_b200.h).
+// Host-side only: validates arguments the way the reference raises, owns device
+// constants and scratch, and launches the kernels in micloc_staged.cuh /
+// micloc_fused.cuh on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/micloc_b200.h"
+#include "micloc_common.h"
+#include "micloc_staged.cuh"
+
+using namespace micloc;
+
+// ---------------------------------------------------------------------------
+// error handling / bookkeeping
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+int micloc::set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+void micloc::count_launch(int n) { g_launches.fetch_add(n); }
+
+extern "C" const char *micloc_last_error(void) { return g_err.c_str(); }
+extern "C" int micloc_version(void) { return MICLOC_VERSION; }
+extern "C" int64_t micloc_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct micloc_snn {
+    int device = 0;
+    ChainParams p{};
+    float *d_taps = nullptr;       // [n_taps]
+    float *d_sos = nullptr;        // [1][kMaxSections][5]
+    float *d_W = nullptr;          // [C2][G] f32
+    double *d_Wd = nullptr;        // [C2][G] f64
+    DevBuf q, spikes, vmem, gram, flags, part;
+    // host staging for run_host
+    DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_kernels = 0;
+    int sm_count = 148;
+};
+
+static int upload_bf(micloc_snn *c, const double *bf, int G) {
+    const int C2 = c->p.C2;
+    std::vector<float> wf((size_t)C2 * G);
+    for (size_t i = 0; i < wf.size(); ++i) wf[i] = (float)bf[i];
+    if (c->d_W) cudaFree(c->d_W);
+    if (c->d_Wd) cudaFree(c->d_Wd);
+    c->d_W = nullptr; c->d_Wd = nullptr;
+    MICLOC_CUDA(cudaMalloc(&c->d_W, wf.size() * sizeof(float)));
+    MICLOC_CUDA(cudaMalloc(&c->d_Wd, wf.size() * sizeof(double)));
+    MICLOC_CUDA(cudaMemcpy(c->d_W, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    MICLOC_CUDA(cudaMemcpy(c->d_Wd, bf, wf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->p.G = G;
+    return MICLOC_OK;
+}
+
+// Shared by the SNN and the Xylo front end: fills the STHT part of ChainParams and
+// uploads the compacted taps.  Taps below 1e-12 * max|h| are treated as zero (the
+// Hilbert kernel's even taps are exact zeros or ~1e-19 FFT residue).
+int micloc::setup_stht(ChainParams &p, const double *h, int K, float **d_taps) {
+    if (K < 1 || K > 8192) return set_error(MICLOC_ERR_CONFIG, "kernel_len %d out of range [1, 8192]", K);
+    double mx = 0.0;
+    for (int k = 0; k < K; ++k) mx = std::fmax(mx, std::fabs(h[k]));
+    const double thr = mx * 1e-12;
+    int first = -1, last = -1;
+    bool same_parity = true;
+    for (int k = 0; k < K; ++k)
+        if (std::fabs(h[k]) > thr) {
+            if (first < 0) first = k;
+            else if (((k - first) & 1) != 0) same_parity = false;
+            last = k;
+        }
+    if (first < 0) { first = 0; last = 0; }
+    const int stride = (same_parity && last > first) ? 2 : 1;
+    int n = (last - first) / stride + 1;
+    const int npad = (n + kFirJB - 1) / kFirJB * kFirJB;
+    std::vector<float> taps(npad, 0.f);
+    for (int j = 0; j < n; ++j) taps[j] = (float)h[first + stride * j];
+    p.K = K; p.half = K / 2;
+    p.tap_stride = stride; p.tap_first = first; p.n_taps = npad;
+    p.span = first + stride * (npad - 1);
+    MICLOC_CUDA(cudaMalloc(d_taps, npad * sizeof(float)));
+    MICLOC_CUDA(cudaMemcpy(*d_taps, taps.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
+    return MICLOC_OK;
+}
+
+int micloc::sos_to_f32(const double *sos, int nsec, float *out /* [kMaxSections][5] */) {
+    if (nsec < 1 || nsec > kMaxSections)
+        return set_error(MICLOC_ERR_CONFIG, "n_sections %d out of range [1, %d]", nsec, kMaxSections);
+    for (int k = 0; k < kMaxSections * 5; ++k) out[k] = 0.f;
+    for (int k = 0; k < nsec; ++k) {
+        const double a0 = sos[k * 6 + 3];
+        if (a0 == 0.0) return set_error(MICLOC_ERR_CONFIG, "sos section %d has a0 == 0", k);
+        out[k * 5 + 0] = (float)(sos[k * 6 + 0] / a0);
+        out[k * 5 + 1] = (float)(sos[k * 6 + 1] / a0);
+        out[k * 5 + 2] = (float)(sos[k * 6 + 2] / a0);
+        out[k * 5 + 3] = (float)(sos[k * 6 + 4] / a0);
+        out[k * 5 + 4] = (float)(sos[k * 6 + 5] / a0);
+    }
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, micloc_snn **out) {
+    if (!cfg || !out) return set_error(MICLOC_ERR_CONFIG, "null config");
+    *out = nullptr;
+    if (cfg->num_mic < 1 || cfg->num_mic > 128)
+        return set_error(MICLOC_ERR_CONFIG, "num_mic %d out of range [1, 128]", cfg->num_mic);
+    if (!cfg->stht_kernel || !cfg->sos || !cfg->bf_mat) return set_error(MICLOC_ERR_CONFIG, "null array in config");
+    if (cfg->robust_width < 1)
+        return set_error(MICLOC_ERR_CONFIG, "`distance` must be greater or equal to 1");  // scipy find_peaks
+    if (cfg->neuron_len < 1 || !(cfg->neuron_decay > 0.0 && cfg->neuron_decay < 1.0))
+        return set_error(MICLOC_ERR_CONFIG, "bad neuron kernel (len %d, decay %g)", cfg->neuron_len, cfg->neuron_decay);
+    if (cfg->num_doa < 1) return set_error(MICLOC_ERR_CONFIG, "num_doa must be >= 1");
+    MICLOC_CUDA(cudaSetDevice(device));
+    micloc_snn *c = new micloc_snn();
+    c->device = device;
+    ChainParams &p = c->p;
+    p.M = cfg->num_mic; p.C2 = 2 * cfg->num_mic;
+    int rc = setup_stht(p, cfg->stht_kernel, cfg->kernel_len, &c->d_taps);
+    if (rc) { micloc_snn_destroy(c); return rc; }
+    p.nsec = cfg->n_sections;
+    rc = sos_to_f32(cfg->sos, cfg->n_sections, &p.sos[0][0]);
+    if (rc) { micloc_snn_destroy(c); return rc; }
+    p.w = cfg->robust_width; p.bipolar = cfg->bipolar ? 1 : 0;
+    p.na = (float)cfg->neuron_decay; p.nc = (float)cfg->neuron_scale; p.nL = cfg->neuron_len;
+    p.ncT = (float)(cfg->neuron_scale * std::pow(cfg->neuron_decay, (double)cfg->neuron_len));
+    p.nLf = (float)cfg->neuron_len;
+    if (cudaMalloc(&c->d_sos, sizeof(float) * kMaxSections * 5) != cudaSuccess ||
+        cudaMemcpy(c->d_sos, &p.sos[0][0], sizeof(float) * kMaxSections * 5, cudaMemcpyHostToDevice) != cudaSuccess) {
+        micloc_snn_destroy(c);
+        return set_error(MICLOC_ERR_CUDA, "cudaMalloc(sos) failed");
+    }
+    rc = upload_bf(c, cfg->bf_mat, cfg->num_doa);
+    if (rc) { micloc_snn_destroy(c); return rc; }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_destroy(micloc_snn *c) {
+    if (!c) return MICLOC_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_taps); cudaFree(c->d_sos); cudaFree(c->d_W); cudaFree(c->d_Wd);
+    c->q.release(); c->spikes.release(); c->vmem.release(); c->gram.release(); c->flags.release(); c->part.release();
+    for (int i = 0; i < 2; ++i) {
+        c->h_audio[i].release(); c->h_spk[i].release(); c->h_pow[i].release(); c->h_doa[i].release(); c->h_flg[i].release();
+        if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
+    }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_set_bf(micloc_snn *c, const double *bf, int32_t G) {
+    if (!c || !bf || G < 1) return set_error(MICLOC_ERR_CONFIG, "bad bf_mat");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    MICLOC_CUDA(cudaDeviceSynchronize());
+    return upload_bf(c, bf, G);
+}
+
+extern "C" int micloc_snn_enable_timing(micloc_snn *c, int enable) {
+    if (!c) return set_error(MICLOC_ERR_CONFIG, "null context");
+    c->timing = enable != 0;
+    if (c->timing && !c->ev0) {
+        MICLOC_CUDA(cudaEventCreate(&c->ev0));
+        MICLOC_CUDA(cudaEventCreate(&c->ev1));
+    }
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_last_kernel_ms(micloc_snn *c, float *ms, int32_t *n_kernels) {
+    if (!c || !c->ev0) return set_error(MICLOC_ERR_CONFIG, "timing not enabled");
+    float v = 0.f;
+    MICLOC_CUDA(cudaEventElapsedTime(&v, c->ev0, c->ev1));
+    if (ms) *ms = v;
+    if (n_kernels) *n_kernels = c->last_kernels;
+    return MICLOC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+template <typename IN_T>
+static int launch_stht(const ChainParams &p, const float *d_taps, const IN_T *audio, float *q,
+                       long long B, long long T, cudaStream_t st) {
+    const int TT = 512;
+    const int MG = p.M < 8 ? p.M : 8;
+    const int ntiles = (int)((T + TT - 1) / TT);
+    const size_t smem = (size_t)(((p.n_taps + 3) & ~3) + MG * fir_row_pitch(TT, p.span)) * sizeof(float);
+    if (smem > 227 * 1024) return set_error(MICLOC_ERR_UNSUPPORTED, "STHT tile needs %zu B of shared memory", smem);
+    dim3 grid((unsigned)(B * ntiles), (unsigned)((p.M + MG - 1) / MG));
+    if (p.tap_stride == 2) {
+        MICLOC_CUDA(cudaFuncSetAttribute(k_stht<IN_T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stht<IN_T, 2><<<grid, 256, smem, st>>>(audio, q, d_taps, p, T, TT, ntiles, MG);
+    } else {
+        MICLOC_CUDA(cudaFuncSetAttribute(k_stht<IN_T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stht<IN_T, 1><<<grid, 256, smem, st>>>(audio, q, d_taps, p, T, TT, ntiles, MG);
+    }
+    count_launch(1);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+int micloc::launch_stht_any(const ChainParams &p, const float *d_taps, const void *audio, int dtype, float *q,
+                            long long B, long long T, cudaStream_t st) {
+    return dtype == MICLOC_I16 ? launch_stht<int16_t>(p, d_taps, (const int16_t *)audio, q, B, T, st)
+                               : launch_stht<float>(p, d_taps, (const float *)audio, q, B, T, st);
+}
+
+int micloc::launch_chain_any(const ChainParams &p, const void *audio, int dtype, const float *q,
+                             const float *band_sos, int nb, float *z, int8_t *spikes, int32_t *flags,
+                             long long B, long long T, cudaStream_t st) {
+    const long long n = B * p.C2 * nb;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (dtype == MICLOC_I16)
+        k_chain<int16_t><<<grid, 128, 0, st>>>((const int16_t *)audio, q, band_sos, z, spikes, flags, p, B, T, nb);
+    else
+        k_chain<float><<<grid, 128, 0, st>>>((const float *)audio, q, band_sos, z, spikes, flags, p, B, T, nb);
+    count_launch(1);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+static int check_run_args(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T) {
+    if (!c) return set_error(MICLOC_ERR_CONFIG, "null context");
+    if (!audio) return set_error(MICLOC_ERR_SHAPE, "null audio pointer");
+    if (dtype != MICLOC_F32 && dtype != MICLOC_I16) return set_error(MICLOC_ERR_SHAPE, "dtype must be MICLOC_F32 or MICLOC_I16");
+    if (B < 1 || T < 1) return set_error(MICLOC_ERR_SHAPE, "empty batch (B=%lld, T=%lld)", (long long)B, (long long)T);
+    if (T > (1ll << 30)) return set_error(MICLOC_ERR_SHAPE, "T too large");
+    return MICLOC_OK;
+}
+
+static int run_power(micloc_snn *c, const float *vmem, long long B, long long T, float *power, int32_t *doa,
+                     cudaStream_t st) {
+    const ChainParams &p = c->p;
+    MICLOC_TRY(c->gram.reserve((size_t)B * p.C2 * p.C2 * sizeof(double)));
+    dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
+    k_gram<<<gg, 256, 0, st>>>(vmem, (double *)c->gram.ptr, p.C2, T, 0);
+    const size_t smem = (size_t)p.C2 * p.C2 * sizeof(double);
+    MICLOC_CUDA(cudaFuncSetAttribute(k_power_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_power_argmax<<<(unsigned)B, 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
+                                                   1.0 / (double)T);
+    count_launch(2);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                                   float *q_dev, float *z_dev, int8_t *spikes_dev, float *vmem_dev,
+                                   float *y_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                                   void *stream) {
+    MICLOC_TRY(check_run_args(c, audio, dtype, B, T));
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ChainParams &p = c->p;
+    const size_t n_q = (size_t)B * T * p.M, n_c = (size_t)B * T * p.C2;
+    float *q = q_dev; int8_t *spk = spikes_dev; float *vm = vmem_dev; int32_t *flg = flags_dev;
+    if (!q) { MICLOC_TRY(c->q.reserve(n_q * sizeof(float))); q = (float *)c->q.ptr; }
+    if (!spk) { MICLOC_TRY(c->spikes.reserve(n_c)); spk = (int8_t *)c->spikes.ptr; }
+    if (!vm) { MICLOC_TRY(c->vmem.reserve(n_c * sizeof(float))); vm = (float *)c->vmem.ptr; }
+    if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
+    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev0, st));
+    const long long l0 = g_launches.load();
+    MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
+    MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, q, B, T, st));
+    MICLOC_TRY(launch_chain_any(p, audio, dtype, q, c->d_sos, 1, z_dev, spk, flg, B, T, st));
+    const bool need_vmem = vmem_dev || y_dev || power_dev || doa_dev;
+    if (need_vmem) {
+        const long long n = B * p.C2;
+        k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+    }
+    if (power_dev || doa_dev) MICLOC_TRY(run_power(c, vm, B, T, power_dev, doa_dev, st));
+    if (y_dev) {
+        const int slab = 256;
+        dim3 grid((unsigned)((p.G + 127) / 128), (unsigned)((T + slab - 1) / slab), (unsigned)B);
+        if (B > 65535) return set_error(MICLOC_ERR_UNSUPPORTED, "dense output supports B <= 65535");
+        if (p.C2 <= 16) k_dense<16><<<grid, 128, 0, st>>>(vm, c->d_W, y_dev, p.C2, p.G, T, slab);
+        else k_dense<0><<<grid, 128, 0, st>>>(vm, c->d_W, y_dev, p.C2, p.G, T, slab);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+    }
+    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev1, st));
+    c->last_kernels = (int)(g_launches.load() - l0);
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_gram(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                               int64_t t_start, double *gram_dev, void *stream) {
+    MICLOC_TRY(check_run_args(c, audio, dtype, B, T));
+    if (!gram_dev || t_start < 0 || t_start >= T) return set_error(MICLOC_ERR_SHAPE, "bad gram output / t_start");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ChainParams &p = c->p;
+    const size_t n_q = (size_t)B * T * p.M, n_c = (size_t)B * T * p.C2;
+    MICLOC_TRY(c->q.reserve(n_q * sizeof(float)));
+    MICLOC_TRY(c->spikes.reserve(n_c));
+    MICLOC_TRY(c->vmem.reserve(n_c * sizeof(float)));
+    MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t)));
+    MICLOC_CUDA(cudaMemsetAsync(c->flags.ptr, 0, (size_t)B * sizeof(int32_t), st));
+    MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, (float *)c->q.ptr, B, T, st));
+    MICLOC_TRY(launch_chain_any(p, audio, dtype, (float *)c->q.ptr, c->d_sos, 1, nullptr, (int8_t *)c->spikes.ptr,
+                                (int32_t *)c->flags.ptr, B, T, st));
+    const long long n = B * p.C2;
+    k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const int8_t *)c->spikes.ptr, (float *)c->vmem.ptr, p, B, T);
+    dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
+    k_gram<<<gg, 256, 0, st>>>((const float *)c->vmem.ptr, gram_dev, p.C2, T, t_start);
+    count_launch(2);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                              int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                              int fused, void *stream) {
+    if (!fused)
+        return micloc_snn_run_taps(c, audio, dtype, B, T, nullptr, nullptr, spikes_dev, nullptr, nullptr,
+                                   power_dev, doa_dev, flags_dev, stream);
+    MICLOC_TRY(check_run_args(c, audio, dtype, B, T));
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *flg = flags_dev;
+    if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
+    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev0, st));
+    const long long l0 = g_launches.load();
+    MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
+    MICLOC_TRY(launch_fused(c->p, c->d_taps, c->d_Wd, audio, dtype, B, T, spikes_dev, power_dev, doa_dev, flg,
+                            c->sm_count, st));
+    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev1, st));
+    c->last_kernels = (int)(g_launches.load() - l0);
+    return MICLOC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// end-to-end with host buffers: two chunks in flight on two private streams
+// ---------------------------------------------------------------------------
+extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dtype, int64_t B, int64_t T,
+                                   int8_t *spikes_host, float *power_host, int32_t *doa_host,
+                                   int32_t *flags_host, int fused) {
+    MICLOC_TRY(check_run_args(c, audio_host, dtype, B, T));
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    const ChainParams &p = c->p;
+    const size_t esz = dtype == MICLOC_I16 ? 2 : 4;
+    const size_t clip_in = (size_t)T * p.M * esz, clip_spk = (size_t)T * p.C2;
+    // chunk so that two chunks of input stay under ~1 GiB and every chunk fills the GPU
+    long long chunk = (long long)((512ull << 20) / clip_in);
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    for (int i = 0; i < 2; ++i) {
+        if (!c->hs[i]) MICLOC_CUDA(cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking));
+        MICLOC_TRY(c->h_audio[i].reserve((size_t)chunk * clip_in));
+        if (spikes_host) MICLOC_TRY(c->h_spk[i].reserve((size_t)chunk * clip_spk));
+        MICLOC_TRY(c->h_pow[i].reserve((size_t)chunk * p.G * sizeof(float)));
+        MICLOC_TRY(c->h_doa[i].reserve((size_t)chunk * sizeof(int32_t)));
+        MICLOC_TRY(c->h_flg[i].reserve((size_t)chunk * sizeof(int32_t)));
+    }
+    // the staged path shares one scratch set, so its chunks are serialised on stream 0
+    int slot = 0;
+    for (long long b0 = 0; b0 < B; b0 += chunk, slot ^= fused ? 1 : 0) {
+        const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        cudaStream_t st = c->hs[slot];
+        MICLOC_CUDA(cudaMemcpyAsync(c->h_audio[slot].ptr, (const char *)audio_host + (size_t)b0 * clip_in,
+                                    (size_t)nb * clip_in, cudaMemcpyHostToDevice, st));
+        int8_t *d_spk = spikes_host ? (int8_t *)c->h_spk[slot].ptr : nullptr;
+        float *d_pow = power_host ? (float *)c->h_pow[slot].ptr : nullptr;
+        int rc = micloc_snn_run(c, c->h_audio[slot].ptr, dtype, nb, T, d_spk, d_pow, (int32_t *)c->h_doa[slot].ptr,
+                                (int32_t *)c->h_flg[slot].ptr, fused, st);
+        if (rc) return rc;
+        if (spikes_host)
+            MICLOC_CUDA(cudaMemcpyAsync(spikes_host + (size_t)b0 * clip_spk, d_spk, (size_t)nb * clip_spk,
+                                        cudaMemcpyDeviceToHost, st));
+        if (power_host)
+            MICLOC_CUDA(cudaMemcpyAsync(power_host + (size_t)b0 * p.G, d_pow, (size_t)nb * p.G * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+        if (doa_host)
+            MICLOC_CUDA(cudaMemcpyAsync(doa_host + b0, c->h_doa[slot].ptr, (size_t)nb * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, st));
+        if (flags_host)
+            MICLOC_CUDA(cudaMemcpyAsync(flags_host + b0, c->h_flg[slot].ptr, (size_t)nb * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    MICLOC_CUDA(cudaStreamSynchronize(c->hs[0]));
+    MICLOC_CUDA(cudaStreamSynchronize(c->hs[1]));
+    return MICLOC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Beamformer.apply_to_signal (micloc/beamformer.py:260-292)
+// ---------------------------------------------------------------------------
+extern "C" int micloc_hilbert_beamform(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                                       const double *bf_re, const double *bf_im, int32_t G, float *y_dev,
+                                       float *power_dev, int32_t *doa_dev, void *stream) {
+    MICLOC_TRY(check_run_args(c, audio, dtype, B, T));
+    if (!bf_re || !bf_im || G < 1 || !y_dev) return set_error(MICLOC_ERR_SHAPE, "bad beamforming matrix / output");
+    if (B > 65535) return set_error(MICLOC_ERR_UNSUPPORTED, "hilbert_beamform supports B <= 65535");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ChainParams &p = c->p;
+    const size_t n_q = (size_t)B * T * p.M, n_c = (size_t)B * T * p.C2;
+    MICLOC_TRY(c->q.reserve(n_q * sizeof(float)));
+    MICLOC_TRY(c->vmem.reserve(n_c * sizeof(float)));   // holds z
+    MICLOC_TRY(c->spikes.reserve(n_c));
+    MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t)));
+    MICLOC_TRY(c->part.reserve((size_t)2 * p.M * G * sizeof(float)));
+    std::vector<float> w((size_t)2 * p.M * G);
+    for (size_t i = 0; i < (size_t)p.M * G; ++i) { w[i] = (float)bf_re[i]; w[(size_t)p.M * G + i] = (float)bf_im[i]; }
+    MICLOC_CUDA(cudaMemcpyAsync(c->part.ptr, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    MICLOC_CUDA(cudaStreamSynchronize(st));  // w is a stack-owned vector
+    float *z = (float *)c->vmem.ptr;
+    MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, (float *)c->q.ptr, B, T, st));
+    MICLOC_TRY(launch_chain_any(p, audio, dtype, (float *)c->q.ptr, c->d_sos, 1, z, (int8_t *)c->spikes.ptr,
+                                (int32_t *)c->flags.ptr, B, T, st));
+    const int slab = 256;
+    dim3 grid((unsigned)((G + 127) / 128), (unsigned)((T + slab - 1) / slab), (unsigned)B);
+    const float *bfr = (const float *)c->part.ptr, *bfi = bfr + (size_t)p.M * G;
+    k_cproject<<<grid, 128, 0, st>>>(z, bfr, bfi, (float2 *)y_dev, p.M, G, T, slab);
+    count_launch(1);
+    if (power_dev || doa_dev) {
+        k_cpower_argmax<<<(unsigned)B, 256, 0, st>>>((const float2 *)y_dev, power_dev, doa_dev, G, T);
+        count_launch(1);
+    }
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}

@@ -1,0 +1,56 @@
+// micloc_common.h -- host-side helpers shared by the API translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/micloc_b200.h"
+#include "micloc_device.cuh"
+
+namespace micloc {
+
+int set_error(int code, const char *fmt, ...);
+void count_launch(int n);
+
+#define MICLOC_CUDA(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return ::micloc::set_error(MICLOC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                       cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define MICLOC_TRY(expr)          \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+// device scratch that only grows
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess)
+            return set_error(MICLOC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+int setup_stht(ChainParams &p, const double *h, int K, float **d_taps);
+int sos_to_f32(const double *sos, int nsec, float *out);
+int launch_stht_any(const ChainParams &p, const float *d_taps, const void *audio, int dtype, float *q,
+                    long long B, long long T, cudaStream_t st);
+int launch_chain_any(const ChainParams &p, const void *audio, int dtype, const float *q, const float *band_sos,
+                     int nb, float *z, int8_t *spikes, int32_t *flags, long long B, long long T, cudaStream_t st);
+int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
+                 long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
+                 int sm_count, cudaStream_t st);
+
+}  // namespace micloc

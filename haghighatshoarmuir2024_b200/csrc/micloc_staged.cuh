@@ -1,0 +1,274 @@
+// micloc_staged.cuh -- one kernel per stage of the float SNN chain, with every
+// intermediate in global memory.  These are the debug-tap path of the C-ABI
+// (micloc_snn_run_taps), the building blocks of Beamformer.apply_to_signal and of
+// the Xylo front end, and the cross-check of the fused kernel.
+#pragma once
+#include "micloc_device.cuh"
+
+namespace micloc {
+
+// ---------------------------------------------------------------------------
+// S1: STHT quadrature FIR   q[b][t][m] = sum_k h[k] * x[b][t-k][m]
+//     (micloc/snn_beamformer.py:327, zero initial state)
+// grid.x = B * ntiles, grid.y = mic groups of <= MG mics; dynamic smem:
+//   taps[n_taps] | rows[MG][pitch]
+// Each thread owns kFirR consecutive outputs of one mic and walks the kept taps
+// in blocks of kFirJB with a register window: 128 FFMA per 8+2 LDS.128.
+// ---------------------------------------------------------------------------
+template <typename IN_T, int STRIDE>
+__global__ void __launch_bounds__(256)
+k_stht(const IN_T *__restrict__ audio, float *__restrict__ q, const float *__restrict__ taps,
+       const __grid_constant__ ChainParams p, long long T, int TT, int ntiles, int MG) {
+    extern __shared__ __align__(16) float smem[];
+    float *taps_s = smem;
+    const int pitch = fir_row_pitch(TT, p.span);
+    float *rows = smem + ((p.n_taps + 3) & ~3);
+
+    const long long b = blockIdx.x / ntiles;
+    const long long t0 = (long long)(blockIdx.x % ntiles) * TT;
+    const int m0 = blockIdx.y * MG;
+    const int mg = min(MG, p.M - m0);
+    const IN_T *clip = audio + b * T * p.M;
+
+    for (int i = threadIdx.x; i < p.n_taps; i += blockDim.x) taps_s[i] = taps[i];
+    fir_fill_rows<IN_T>(rows, pitch, clip, T, p.M, m0, mg, t0, p.span, TT + p.span + 8);
+    __syncthreads();
+
+    const int chunks = TT / kFirR;
+    for (int item = threadIdx.x; item < mg * chunks; item += blockDim.x) {
+        const int mm = item / chunks, chunk = item % chunks;
+        float acc[kFirR];
+        fir_accumulate<STRIDE>(rows + mm * pitch, taps_s, p.n_taps, p.span, p.tap_first, chunk, acc);
+        float *dst = q + (b * T + t0 + (long long)chunk * kFirR) * p.M + m0 + mm;
+#pragma unroll
+        for (int i = 0; i < kFirR; ++i)
+            if (t0 + chunk * kFirR + i < T) dst[(long long)i * p.M] = acc[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// S2: band-pass + RZCC, one thread per (clip, band, channel), sequential in time.
+//   channel c < M : in-phase  = x[(t - K/2) mod T]   (np.roll, snn_beamformer.py:325)
+//   channel c >= M: quadrature = q[t]
+//   z = SOS cascade (snn_beamformer.py:330-335 / filterbank.py:40-44)
+//   spikes = RZCC(z)          (spike_encoder.py:115-137)
+// Output channel index is band*C2 + c (Demo.spike_encoding's hstack over bands,
+// xylo_snn_localization.py:341-342); nb == 1 for the float SNN chain.
+// `band_sos` [nb][kMaxSections][5]; sos of band 0 also sits in p.sos.
+// ---------------------------------------------------------------------------
+template <typename IN_T>
+__global__ void __launch_bounds__(128)
+k_chain(const IN_T *__restrict__ audio, const float *__restrict__ q, const float *__restrict__ band_sos,
+        float *__restrict__ z_out, int8_t *__restrict__ spikes, int32_t *__restrict__ flags,
+        const __grid_constant__ ChainParams p, long long B, long long T, int nb) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CT = p.C2 * nb;
+    if (idx >= B * CT) return;
+    const long long b = idx / CT;
+    const int cc = (int)(idx % CT);
+    const int band = cc / p.C2, c = cc % p.C2;
+
+    float sos[kMaxSections][5];
+#pragma unroll
+    for (int k = 0; k < kMaxSections; ++k)
+#pragma unroll
+        for (int e = 0; e < 5; ++e) sos[k][e] = band_sos[(band * kMaxSections + k) * 5 + e];
+
+    BiquadState bq; biquad_reset(bq);
+    RzccState rz; rzcc_reset(rz);
+    int8_t *sp = spikes + b * T * CT + cc;
+    auto emit = [&](int pos, int sign) { sp[(long long)pos * CT] = (int8_t)sign; };
+
+    const bool inphase = c < p.M;
+    const IN_T *xa = audio + b * T * p.M + (inphase ? c : 0);
+    const float *xq = q + b * T * p.M + (inphase ? 0 : c - p.M);
+    long long src = ((-(long long)p.half) % T + T) % T;  // (t - K/2) mod T at t = 0
+    for (long long t = 0; t < T; ++t) {
+        float x;
+        if (inphase) { x = to_f32<IN_T>(xa[src * p.M]); if (++src == T) src = 0; }
+        else x = xq[t * p.M];
+        const float z = biquad_step(sos, p.nsec, bq, x);
+        if (z_out) z_out[(b * T + t) * CT + cc] = z;
+        sp[t * CT] = 0;
+        rzcc_step(rz, p.w, p.bipolar, (int)t, z, emit);
+    }
+    rzcc_finish(rz, p.w, p.bipolar, emit);
+    if (rz.overflow && flags) atomicOr(flags + b, 1);
+}
+
+// ---------------------------------------------------------------------------
+// S3: neuron filter   vmem[b][t][c] = sum_{n<L} h[n] * spikes[b][t-n][c]
+//     (snn_beamformer.py:364)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
+         const __grid_constant__ ChainParams p, long long B, long long T) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * p.C2) return;
+    const long long b = idx / p.C2;
+    const int c = (int)(idx % p.C2);
+    const int8_t *sp = spikes + b * T * p.C2 + c;
+    float *vm = vmem + b * T * p.C2 + c;
+    NeuronState n; neuron_reset(n);
+    for (long long t = 0; t < T; ++t) {
+        const float s = (float)sp[t * p.C2];
+        const float sd = t >= p.nL ? (float)sp[(t - p.nL) * p.C2] : 0.f;
+        vm[t * p.C2] = neuron_step(p, n, s, sd);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// S4a: Gram matrix of the membrane signals   C[b][i][j] = sum_t v[t][i] v[t][j]
+//      mean_t (v[t] . w_g)^2 == w_g^T (C/T) w_g, so the per-DoA power of
+//      snn_beamformer.py:368 + target_snn_localization.py:462 needs no T x G pass.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gram(const float *__restrict__ vmem, double *__restrict__ gram, int C2, long long T, long long t_start) {
+    const long long b = blockIdx.x;
+    const int pair = blockIdx.y * blockDim.x + threadIdx.x;
+    if (pair >= C2 * C2) return;
+    const int i = pair / C2, j = pair % C2;
+    if (j < i) return;  // symmetric: upper triangle only
+    const float *v = vmem + b * T * C2;
+    double acc = 0.0;
+    for (long long t = t_start; t < T; ++t) acc = fma((double)v[t * C2 + i], (double)v[t * C2 + j], acc);
+    gram[(b * C2 + i) * C2 + j] = acc;
+    gram[(b * C2 + j) * C2 + i] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// S4b: power[b][g] = w_g^T C_b w_g / T (float64), doa[b] = first argmax.
+// One block per clip; dynamic smem: C2*C2 doubles + reduction scratch.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_power_argmax(const double *__restrict__ gram, const double *__restrict__ Wd, float *__restrict__ power,
+               int32_t *__restrict__ doa, int C2, int G, double inv_T) {
+    extern __shared__ __align__(16) double sm_d[];
+    double *Cs = sm_d;
+    __shared__ double red_v[256];
+    __shared__ int red_i[256];
+    const long long b = blockIdx.x;
+    for (int e = threadIdx.x; e < C2 * C2; e += blockDim.x) Cs[e] = gram[b * C2 * C2 + e];
+    __syncthreads();
+    double best = -1.0; int besti = 0x7fffffff;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < C2; ++i) {
+            double r = 0.0;
+            for (int j = 0; j < C2; ++j) r = fma(Cs[i * C2 + j], Wd[(long long)j * G + g], r);
+            acc = fma(Wd[(long long)i * G + g], r, acc);
+        }
+        acc *= inv_T;
+        if (power) power[b * G + g] = (float)acc;
+        if (acc > best) { best = acc; besti = g; }  // ascending g: first maximum kept
+    }
+    red_v[threadIdx.x] = best; red_i[threadIdx.x] = besti;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double ov = red_v[threadIdx.x + s]; const int oi = red_i[threadIdx.x + s];
+            if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
+                red_v[threadIdx.x] = ov; red_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && doa) doa[b] = red_i[0];
+}
+
+// ---------------------------------------------------------------------------
+// S5: dense beamformed signal  y[b][t][g] = sum_c vmem[b][t][c] * W[c][g]
+//     (the value apply_to_signal returns, snn_beamformer.py:368); one thread per
+//     DoA neuron looping over a slab of time steps, weights held in registers
+//     when C2 <= 16.
+// ---------------------------------------------------------------------------
+template <int C2T>
+__global__ void __launch_bounds__(128)
+k_dense(const float *__restrict__ vmem, const float *__restrict__ W, float *__restrict__ y,
+        int C2, int G, long long T, int slab) {
+    const long long b = blockIdx.z;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t0 = (long long)blockIdx.y * slab;
+    const long long t1 = min(T, t0 + slab);
+    const bool live = g < G;
+    const float *v = vmem + b * T * C2;
+    float *yo = y + b * T * G + g;
+    if (C2T > 0) {
+        float wr[C2T > 0 ? C2T : 1];
+#pragma unroll
+        for (int c = 0; c < C2T; ++c) wr[c] = (live && c < C2) ? W[(long long)c * G + g] : 0.f;
+        for (long long t = t0; t < t1; ++t) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < C2T; ++c)
+                if (c < C2) acc = fmaf(__ldg(v + t * C2 + c), wr[c], acc);
+            if (live) yo[t * G] = acc;
+        }
+    } else {
+        for (long long t = t0; t < t1; ++t) {
+            float acc = 0.f;
+            for (int c = 0; c < C2; ++c)
+                acc = fmaf(__ldg(v + t * C2 + c), live ? __ldg(W + (long long)c * G + g) : 0.f, acc);
+            if (live) yo[t * G] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Beamformer.apply_to_signal tail (micloc/beamformer.py:290):
+//   y[b][t][g] = sum_m (zr + i zi)[t][m] * conj(bf[m][g]),  z = [T][2M] (real | imag)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_cproject(const float *__restrict__ z, const float *__restrict__ bfr, const float *__restrict__ bfi,
+           float2 *__restrict__ y, int M, int G, long long T, int slab) {
+    const long long b = blockIdx.z;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const long long t0 = (long long)blockIdx.y * slab;
+    const long long t1 = min(T, t0 + slab);
+    const float *zz = z + b * T * 2 * M;
+    for (long long t = t0; t < t1; ++t) {
+        float ar = 0.f, ai = 0.f;
+        for (int m = 0; m < M; ++m) {
+            const float sr = __ldg(zz + t * 2 * M + m), si = __ldg(zz + t * 2 * M + M + m);
+            const float wr = __ldg(bfr + (long long)m * G + g), wi = -__ldg(bfi + (long long)m * G + g);
+            ar = fmaf(sr, wr, fmaf(-si, wi, ar));
+            ai = fmaf(sr, wi, fmaf(si, wr, ai));
+        }
+        y[(b * T + t) * G + g] = make_float2(ar, ai);
+    }
+}
+
+// power[b][g] = mean_t |y|^2 in float64 + argmax; one block per (clip), thread per g
+__global__ void __launch_bounds__(256)
+k_cpower_argmax(const float2 *__restrict__ y, float *__restrict__ power, int32_t *__restrict__ doa,
+                int G, long long T) {
+    __shared__ double red_v[256];
+    __shared__ int red_i[256];
+    const long long b = blockIdx.x;
+    double best = -1.0; int besti = 0x7fffffff;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double acc = 0.0;
+        for (long long t = 0; t < T; ++t) {
+            const float2 v = y[(b * T + t) * G + g];
+            acc += (double)v.x * v.x + (double)v.y * v.y;
+        }
+        acc /= (double)T;
+        if (power) power[b * G + g] = (float)acc;
+        if (acc > best) { best = acc; besti = g; }
+    }
+    red_v[threadIdx.x] = best; red_i[threadIdx.x] = besti;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double ov = red_v[threadIdx.x + s]; const int oi = red_i[threadIdx.x + s];
+            if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
+                red_v[threadIdx.x] = ov; red_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && doa) doa[b] = red_i[0];
+}
+
+}  // namespace micloc

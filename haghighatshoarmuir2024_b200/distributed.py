@@ -1,0 +1,49 @@
+"""Multi-GPU plumbing: clips are independent, so the batch is sharded by clip across
+ranks (one process per GPU) and the only exchange is a final sum of DoA histograms
+(the Monte-Carlo loop of paper_plots/target_snn_localization.py:447-467).
+
+Works with any torch.distributed backend: NCCL over NVLink for CUDA tensors on the
+GPU box, gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous clip range [lo, hi) of `rank`; sizes differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def doa_histogram(doa: torch.Tensor, num_doa: int, group_id: Optional[torch.Tensor] = None,
+                  num_groups: int = 1) -> torch.Tensor:
+    """int64 [num_groups, num_doa] counts of DoA indices (group = e.g. SNR x band cell)."""
+    doa = doa.to(torch.int64).reshape(-1)
+    if group_id is None:
+        flat = doa
+    else:
+        flat = group_id.to(torch.int64).reshape(-1) * num_doa + doa
+    hist = torch.bincount(flat, minlength=num_groups * num_doa)
+    return hist.reshape(num_groups, num_doa)
+
+
+def reduce_histograms(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum per-rank histograms in place over all ranks (one small all_reduce)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def max_over_ranks(value: float, device: torch.device, group=None) -> float:
+    """Device-timed milliseconds -> max over ranks (the bench's timing rule)."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -1,0 +1,201 @@
+"""Batched device engine over the C-ABI: the call a Monte-Carlo driver makes.
+
+`SnnEngine` owns one `micloc_snn` context on one GPU.  torch is used only for
+device memory and streams; all arithmetic happens in libmicloc_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class ChainSpec:
+    """Host constants of one SNN chain (what SNNBeamformer derives, snn_beamformer.py:45-80,342-361)."""
+    num_mic: int
+    stht_kernel: np.ndarray      # [K] float64
+    sos: np.ndarray              # [n_sections, 6]
+    robust_width: int
+    bipolar: bool
+    neuron_decay: float
+    neuron_scale: float
+    neuron_len: int
+
+
+def neuron_alpha_params(time_vec: np.ndarray, tau_vec: Sequence[float]):
+    """Truncated, normalised alpha kernel of snn_beamformer.py:342-361 as (taps, a, c, L).
+
+    h[n] = (t_n/tau) exp(-t_n/tau) / sum_T(...), cut where the cumulative mass reaches
+    0.999.  Returned closed form: h[n] = c * n * a^n for n < L."""
+    tau_syn, tau_mem = float(tau_vec[0]), float(tau_vec[1])
+    tn = np.asarray(time_vec, dtype=np.float64) - time_vec[0]
+    if tau_mem == tau_syn:
+        h = (tn / tau_syn) * np.exp(-tn / tau_syn)
+    else:
+        h = (np.exp(-tn / tau_syn) - np.exp(tn / tau_mem)) / (1 / tau_mem - 1 / tau_syn)
+        assert np.all(h >= 0)
+    total = np.sum(h)
+    h = h / total
+    L = int(np.sum(np.cumsum(h) < 0.999))
+    dt = float(tn[1] - tn[0]) if len(tn) > 1 else 1.0
+    a = float(np.exp(-dt / tau_syn))
+    c = float((dt / tau_syn) / total)
+    return h[:L], a, c, max(L, 1)
+
+
+class SnnEngine:
+    def __init__(self, spec: ChainSpec, bf_mat: np.ndarray, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SnnEngine needs a CUDA device (B200); there is no CPU fallback")
+        self.spec = spec
+        self.device = torch.device("cuda", device)
+        self._lib = N.lib()
+        bf = np.ascontiguousarray(bf_mat, dtype=np.float64)
+        if bf.ndim != 2 or bf.shape[0] != 2 * spec.num_mic:
+            raise ValueError(f"bf_mat should have shape (2*num_mic, num_DoA); got {bf.shape}")
+        self._kernel = np.ascontiguousarray(spec.stht_kernel, dtype=np.float64)
+        self._sos = np.ascontiguousarray(spec.sos, dtype=np.float64).reshape(-1, 6)
+        cfg = N.SnnConfig()
+        cfg.num_mic = spec.num_mic
+        cfg.kernel_len = len(self._kernel)
+        cfg.stht_kernel = self._kernel.ctypes.data_as(N._dp)
+        cfg.n_sections = self._sos.shape[0]
+        cfg.sos = self._sos.ctypes.data_as(N._dp)
+        cfg.robust_width = int(spec.robust_width)
+        cfg.bipolar = int(bool(spec.bipolar))
+        cfg.neuron_decay = float(spec.neuron_decay)
+        cfg.neuron_scale = float(spec.neuron_scale)
+        cfg.neuron_len = int(spec.neuron_len)
+        cfg.num_doa = bf.shape[1]
+        cfg.bf_mat = bf.ctypes.data_as(N._dp)
+        h = C.c_void_p()
+        N.check(self._lib.micloc_snn_create(C.byref(cfg), device, C.byref(h)))
+        self._h = h
+        self.M, self.C2, self.G = spec.num_mic, 2 * spec.num_mic, bf.shape[1]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.micloc_snn_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_bf(self, bf_mat: np.ndarray):
+        bf = np.ascontiguousarray(bf_mat, dtype=np.float64)
+        if bf.ndim != 2 or bf.shape[0] != self.C2:
+            raise ValueError(f"bf_mat should have shape (2*num_mic, num_DoA); got {bf.shape}")
+        N.check(self._lib.micloc_snn_set_bf(self._h, bf.ctypes.data_as(N._dp), bf.shape[1]))
+        self.G = bf.shape[1]
+
+    # ------------------------------------------------------------------
+    def _check_audio(self, audio: torch.Tensor):
+        if audio.dim() == 2:
+            audio = audio.unsqueeze(0)
+        if audio.dim() != 3 or audio.shape[2] != self.M:
+            raise ValueError(
+                f"number of channels in the input siganl {audio.shape[-1]} should be the same as the number of microphones {self.M}!")
+        if audio.dtype == torch.float32:
+            dt = N.F32
+        elif audio.dtype == torch.int16:
+            dt = N.I16
+        else:
+            raise ValueError(f"audio must be float32 or int16, got {audio.dtype}")
+        return audio.contiguous(), dt
+
+    def run(self, audio: torch.Tensor, want_spikes: bool = False, want_power: bool = True,
+            fused: bool = True) -> Dict[str, torch.Tensor]:
+        """audio [B,T,M] on this engine's GPU -> {'doa','power','spikes','flags'} (device tensors)."""
+        audio, dt = self._check_audio(audio)
+        if audio.device != self.device:
+            raise ValueError(f"audio lives on {audio.device}, engine on {self.device}")
+        B, T, _ = audio.shape
+        dev = self.device
+        doa = torch.empty(B, dtype=torch.int32, device=dev)
+        flags = torch.empty(B, dtype=torch.int32, device=dev)
+        power = torch.empty((B, self.G), dtype=torch.float32, device=dev) if want_power else None
+        spikes = torch.empty((B, T, self.C2), dtype=torch.int8, device=dev) if want_spikes else None
+        N.check(self._lib.micloc_snn_run(self._h, _ptr(audio), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
+                                         _ptr(flags), int(fused), _stream_ptr(dev)))
+        return {"doa": doa, "power": power, "spikes": spikes, "flags": flags}
+
+    def run_taps(self, audio: torch.Tensor, want: Sequence[str] = ("q", "z", "spikes", "vmem", "y", "power", "doa")):
+        """Staged path with per-stage taps (device tensors)."""
+        audio, dt = self._check_audio(audio)
+        B, T, _ = audio.shape
+        dev = self.device
+        mk = lambda name, shape, dtype: torch.empty(shape, dtype=dtype, device=dev) if name in want else None
+        out = {
+            "q": mk("q", (B, T, self.M), torch.float32),
+            "z": mk("z", (B, T, self.C2), torch.float32),
+            "spikes": mk("spikes", (B, T, self.C2), torch.int8),
+            "vmem": mk("vmem", (B, T, self.C2), torch.float32),
+            "y": mk("y", (B, T, self.G), torch.float32),
+            "power": mk("power", (B, self.G), torch.float32),
+            "doa": mk("doa", (B,), torch.int32),
+            "flags": torch.empty(B, dtype=torch.int32, device=dev),
+        }
+        N.check(self._lib.micloc_snn_run_taps(
+            self._h, _ptr(audio), dt, B, T, _ptr(out["q"]), _ptr(out["z"]), _ptr(out["spikes"]), _ptr(out["vmem"]),
+            _ptr(out["y"]), _ptr(out["power"]), _ptr(out["doa"]), _ptr(out["flags"]), _stream_ptr(dev)))
+        return out
+
+    def gram(self, audio: torch.Tensor, t_start: int) -> torch.Tensor:
+        """sum_{t>=t_start} v v^T per clip, float64 [B,2M,2M] (design-time covariance)."""
+        audio, dt = self._check_audio(audio)
+        B, T, _ = audio.shape
+        g = torch.empty((B, self.C2, self.C2), dtype=torch.float64, device=self.device)
+        N.check(self._lib.micloc_snn_gram(self._h, _ptr(audio), dt, B, T, int(t_start), _ptr(g), _stream_ptr(self.device)))
+        return g
+
+    def run_host(self, audio, want_spikes: bool = False, want_power: bool = True, fused: bool = True):
+        """End-to-end with HOST buffers (numpy or CPU torch tensors, ideally pinned):
+        H2D copy, hot path, D2H copy all inside the C call."""
+        t = torch.as_tensor(audio)
+        if t.is_cuda:
+            raise ValueError("run_host takes host memory; use run() for device tensors")
+        t, dt = self._check_audio(t)
+        B, T, _ = t.shape
+        pin = t.is_pinned()
+        mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=pin)
+        doa = mk((B,), torch.int32)
+        flags = mk((B,), torch.int32)
+        power = mk((B, self.G), torch.float32) if want_power else None
+        spikes = mk((B, T, self.C2), torch.int8) if want_spikes else None
+        N.check(self._lib.micloc_snn_run_host(self._h, _ptr(t), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
+                                              _ptr(flags), int(fused)))
+        return {"doa": doa, "power": power, "spikes": spikes, "flags": flags}
+
+    def enable_timing(self, on: bool = True):
+        N.check(self._lib.micloc_snn_enable_timing(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        n = C.c_int32()
+        N.check(self._lib.micloc_snn_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def rzcc_encode(sig: torch.Tensor, robust_width: int, bipolar: bool) -> torch.Tensor:
+    """Exact ZeroCrossingSpikeEncoder.evolve on float64 device input [B,T,C] -> int8 spikes."""
+    if sig.dtype != torch.float64 or not sig.is_cuda or sig.dim() != 3:
+        raise ValueError("sig must be a CUDA float64 tensor of shape [B, T, C]")
+    sig = sig.contiguous()
+    B, T, Cc = sig.shape
+    out = torch.empty((B, T, Cc), dtype=torch.int8, device=sig.device)
+    N.check(N.lib().micloc_rzcc_encode_f64(_ptr(sig), B, T, Cc, int(robust_width), int(bool(bipolar)), _ptr(out),
+                                           sig.device.index or 0, _stream_ptr(sig.device)))
+    return out

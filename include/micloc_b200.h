@@ -1,0 +1,172 @@
+/*
+ * micloc_b200.h -- C-ABI of the B200-native micloc SNN-localisation hot path.
+ *
+ * Drop-in boundary for the reference's Python entry points (all paths under
+ * /root/reference):
+ *   SNNBeamformer.apply_to_signal      micloc/snn_beamformer.py:283-370
+ *   + callers' mean-power / argmax     paper_plots/target_snn_localization.py:462-464
+ *   ZeroCrossingSpikeEncoder.evolve    micloc/spike_encoder.py:115-137
+ *   Beamformer.apply_to_signal         micloc/beamformer.py:260-292
+ *   Demo.spike_encoding / xylo_process micloc/xylo_snn_localization.py:315-377
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures
+ *     (`stream` is a cudaStream_t passed as void*; NULL = default stream).
+ *   - *_dev pointers are device pointers on the context's device; *_host are
+ *     host pointers.  Optional outputs may be NULL.
+ *   - every function returns 0 on success or a negative micloc_status;
+ *     micloc_last_error() gives the message of the calling thread's last failure.
+ *   - launches are stream-ordered; no internal threads; one context per GPU.
+ *   - audio layout is the reference's: [B][T][M] row-major, mics interleaved
+ *     (micloc/snn_beamformer.py:298 `T x num_mic`; micloc/record.py:54-75 wav frames).
+ */
+#ifndef MICLOC_B200_H_
+#define MICLOC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MICLOC_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    MICLOC_OK = 0,
+    MICLOC_ERR_SHAPE = -1,       /* reference raises ValueError (snn_beamformer.py:303-306) */
+    MICLOC_ERR_CONFIG = -2,      /* reference raises ValueError/AssertionError at construction */
+    MICLOC_ERR_CUDA = -3,
+    MICLOC_ERR_UNSUPPORTED = -4,
+    MICLOC_ERR_OVERFLOW = -5     /* RZCC cluster buffer overflow in the fused path: rerun staged */
+} micloc_status;
+
+typedef enum { MICLOC_F32 = 0, MICLOC_I16 = 1 } micloc_dtype;
+
+typedef struct micloc_snn micloc_snn;   /* float SNN chain   */
+typedef struct micloc_xylo micloc_xylo; /* Xylo integer chain */
+
+/* ---- float SNN chain ------------------------------------------------------ */
+typedef struct {
+    int32_t num_mic;            /* M                                   geometry            */
+    int32_t kernel_len;         /* K = int(fs*kernel_duration)         snn_beamformer.py:49 */
+    const double *stht_kernel;  /* [K] fftshift(imag(hilbert(delta)))  snn_beamformer.py:50-53 */
+    int32_t n_sections;         /* biquads of the band-pass (2)        snn_beamformer.py:68-72 */
+    const double *sos;          /* [n_sections][6] b0 b1 b2 1 a1 a2                           */
+    int32_t robust_width;       /* ceil(distance) >= 1                 snn_beamformer.py:75-80 */
+    int32_t bipolar;            /* 0: +1 spikes only, 1: +1/-1         spike_encoder.py:130-135 */
+    double neuron_decay;        /* a = exp(-1/(tau*fs))                snn_beamformer.py:342-361 */
+    double neuron_scale;        /* c: h[n] = c*n*a^n, n < neuron_len                          */
+    int32_t neuron_len;         /* L = effective_length                                       */
+    int32_t num_doa;            /* G                                                          */
+    const double *bf_mat;       /* [2M][G] row-major                   snn_beamformer.py:368  */
+} micloc_snn_config;
+
+/* Build a context on `device`.  Copies every array; the config may be freed. */
+int micloc_snn_create(const micloc_snn_config *cfg, int device, micloc_snn **out);
+int micloc_snn_destroy(micloc_snn *ctx);
+
+/* Replace the beamforming matrix (bf_mat is a per-call argument in the reference). */
+int micloc_snn_set_bf(micloc_snn *ctx, const double *bf_mat, int32_t num_doa);
+
+/* Hot path, device buffers: audio -> spikes, power, DoA index.
+ *   audio_dev  [B][T][M] float32 or int16
+ *   spikes_dev [B][T][2M] int8 in {-1,0,+1}       (nullable)
+ *   power_dev  [B][G] float32 = mean_t y[t,g]^2   (nullable)
+ *   doa_dev    [B] int32 = argmax_g power (first maximum) (nullable)
+ *   flags_dev  [B] int32, bit0 = RZCC cluster overflow (nullable)
+ * `fused` != 0 runs the single fused kernel, 0 the staged kernels (same results). */
+int micloc_snn_run(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                   int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                   int fused, void *stream);
+
+/* Same with per-stage debug taps (all nullable, all device):
+ *   q_dev [B][T][M] f32 (STHT quadrature), z_dev [B][T][2M] f32 (post band-pass,
+ *   hstack(real, imag)), vmem_dev [B][T][2M] f32, y_dev [B][T][G] f32 (dense
+ *   beamformed signal = apply_to_signal's return value). Always staged. */
+int micloc_snn_run_taps(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                        float *q_dev, float *z_dev, int8_t *spikes_dev, float *vmem_dev,
+                        float *y_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                        void *stream);
+
+/* End-to-end with HOST buffers: chunks the batch, copies H2D from pinned staging,
+ * runs the hot path, copies results D2H.  Outputs nullable as above. */
+int micloc_snn_run_host(micloc_snn *ctx, const void *audio_host, int dtype, int64_t B, int64_t T,
+                        int8_t *spikes_host, float *power_host, int32_t *doa_host,
+                        int32_t *flags_host, int fused);
+
+/* Design-time helper (SNNBeamformer.design_from_template, snn_beamformer.py:158-191):
+ * front end + neuron filter, then gram_dev[b][i][j] = sum_{t >= t_start} v[t][i] v[t][j]
+ * (float64, [B][2M][2M]); the caller divides by T - t_start and runs the SVD. */
+int micloc_snn_gram(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                    int64_t t_start, double *gram_dev, void *stream);
+
+/* ---- stand-alone stages ---------------------------------------------------- */
+/* ZeroCrossingSpikeEncoder.evolve on arbitrary float64 input, exact find_peaks
+ * semantics (unbounded clusters).  sig_dev [B][T][C] f64 -> spikes_dev [B][T][C] int8. */
+int micloc_rzcc_encode_f64(const double *sig_dev, int64_t B, int64_t T, int32_t C,
+                           int32_t robust_width, int32_t bipolar, int8_t *spikes_dev,
+                           int device, void *stream);
+
+/* Beamformer.apply_to_signal: STHT + band-pass + complex projection.
+ *   bf_re/bf_im [M][G] (host, float64); y_dev [B][T][G][2] f32 (re, im interleaved),
+ *   power_dev [B][G] = mean_t |y|^2 (nullable), doa_dev [B] (nullable). */
+int micloc_hilbert_beamform(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                            const double *bf_re_host, const double *bf_im_host, int32_t G,
+                            float *y_dev, float *power_dev, int32_t *doa_dev, void *stream);
+
+/* ---- Xylo integer chain ---------------------------------------------------- */
+typedef struct {
+    int32_t num_mic;            /* M                                                      */
+    int32_t kernel_len;         /* K                                                      */
+    const double *stht_kernel;  /* [K]                       xylo_snn_localization.py:327  */
+    int32_t num_bands;          /* F                         xylo_snn_localization.py:148-152 */
+    int32_t n_sections;         /* biquads per band filter (order 1 -> 1, order 2 -> 2)    */
+    const double *sos;          /* [F][n_sections][6]        filterbank.py:79-81           */
+    int32_t robust_width;       /* band-0 width for all bands  xylo_snn_localization.py:346 */
+    int32_t bipolar;            /* 1: inputs = [pos | neg]   xylo_snn_localization.py:350-354 */
+    int32_t num_hidden;         /* N = G*F hidden neurons                                  */
+    int32_t num_doa;            /* G                                                       */
+    const int8_t *w_in;         /* [N_in][N] int8, N_in = 2M*F*(bipolar?2:1)               */
+    const int8_t *w_rec;        /* [N][N] int8 or NULL when all-zero                       */
+    const int16_t *threshold;   /* [N]                                                     */
+    const int8_t *dash_syn;     /* [N] bit-shift decay of I_syn                            */
+    const int8_t *dash_mem;     /* [N] bit-shift decay of V_mem                            */
+    const int16_t *bias;        /* [N] or NULL                                             */
+    int32_t weight_shift;       /* left shift applied to weighted input (XyloSim)          */
+    int32_t max_spikes;         /* spikes per neuron per step cap (hidden: 31)             */
+} micloc_xylo_config;
+
+int micloc_xylo_create(const micloc_xylo_config *cfg, int device, micloc_xylo **out);
+int micloc_xylo_destroy(micloc_xylo *ctx);
+
+/* audio -> input spikes (Demo.spike_encoding) -> hidden spike counts -> DoA.
+ *   spikes_in_dev [B][T][N_in] int8 in {0,1}      (nullable)
+ *   raster_dev    [B][T][N] uint8 hidden spikes per step = rec["Spikes"] (nullable)
+ *   counts_dev    [B][N] int32 = sum_t raster     (nullable)
+ *   doa_dev       [B] int32: argmax over g of band-folded counts (nullable)
+ *   doa_peak_dev  [B] int32: utils.find_peak_location(rate, win) (nullable; win odd) */
+int micloc_xylo_run(micloc_xylo *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                    int8_t *spikes_in_dev, uint8_t *raster_dev, int32_t *counts_dev,
+                    int32_t *doa_dev, int32_t *doa_peak_dev, int32_t peak_win,
+                    int32_t *flags_dev, void *stream);
+
+/* Integer network only (Demo.xylo_process): spikes_in_dev [B][T][N_in] int8 {0,1}. */
+int micloc_xylo_process(micloc_xylo *ctx, const int8_t *spikes_in_dev, int64_t B, int64_t T,
+                        uint8_t *raster_dev, int32_t *counts_dev, void *stream);
+
+/* ---- misc ------------------------------------------------------------------ */
+const char *micloc_last_error(void);
+int micloc_version(void);
+/* kernels launched by this library since load (claim for bench.py's gpu_launches) */
+int64_t micloc_launch_count(void);
+/* duration in ms of the hot-path kernels of the last micloc_snn_run on `ctx`,
+ * measured with CUDA events on the caller's stream (valid after a stream sync);
+ * n_kernels receives how many kernels that was. */
+int micloc_snn_last_kernel_ms(micloc_snn *ctx, float *ms, int32_t *n_kernels);
+int micloc_snn_enable_timing(micloc_snn *ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICLOC_B200_H_ */

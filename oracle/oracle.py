@@ -1,0 +1,188 @@
+"""ctypes front end of the CPU ORACLE (oracle/micloc_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never from the product
+package (haghighatshoarmuir2024_b200/).
+
+Each wrapper cites the reference site it restates; see the C file header.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmicloc_oracle.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (gcc)."""
+    src = os.path.join(_HERE, "micloc_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class _SnnCfg(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("K", C.c_int), ("h", _dp),
+        ("nba", C.c_int), ("b", _dp), ("a", _dp),
+        ("robust_width", C.c_double), ("bipolar", C.c_int),
+        ("L", C.c_int), ("nir", _dp),
+        ("G", C.c_int), ("bf", _dp),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.mo_pairwise_sum.restype = C.c_double
+        _lib.mo_pairwise_sum.argtypes = [_dp, C.c_int]
+        _lib.mo_neuron_kernel.restype = C.c_int
+        _lib.mo_neuron_kernel.argtypes = [_dp, C.c_int, C.c_double, C.c_double, _dp]
+        _lib.mo_rzcc.restype = C.c_int
+        _lib.mo_rzcc.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp]
+        _lib.mo_snn_apply.restype = C.c_int
+        _lib.mo_snn_run_batch.restype = C.c_int
+    return _lib
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def fir(x: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """scipy.signal.lfilter(b, [1], x, axis=0) (micloc/snn_beamformer.py:327,364)."""
+    x = _f64(x); b = _f64(b)
+    x2 = x.reshape(x.shape[0], -1)
+    y = np.empty_like(x2)
+    lib().mo_fir_df2t(_p(x2), _p(y), C.c_int(x2.shape[0]), C.c_int(x2.shape[1]), _p(b), C.c_int(len(b)))
+    return y.reshape(x.shape)
+
+
+def iir(x: np.ndarray, b: np.ndarray, a: np.ndarray) -> np.ndarray:
+    """scipy.signal.lfilter(b, a, x, axis=0), a[0]==1 (micloc/snn_beamformer.py:330-331)."""
+    x = _f64(x); b = _f64(b); a = _f64(a)
+    assert len(a) == len(b) and a[0] == 1.0
+    x2 = x.reshape(x.shape[0], -1)
+    y = np.empty_like(x2)
+    lib().mo_iir_df2t(_p(x2), _p(y), C.c_int(x2.shape[0]), C.c_int(x2.shape[1]), _p(b), _p(a), C.c_int(len(b)))
+    return y.reshape(x.shape)
+
+
+def stht(x: np.ndarray, h: np.ndarray):
+    """(in-phase, quadrature) of micloc/snn_beamformer.py:325-327."""
+    x = _f64(x); h = _f64(h)
+    T, M = x.shape
+    i = np.empty_like(x); q = np.empty_like(x)
+    lib().mo_stht(_p(x), C.c_int(T), C.c_int(M), _p(h), C.c_int(len(h)), _p(i), _p(q))
+    return i, q
+
+
+def rzcc(x: np.ndarray, robust_width: float, bipolar: bool) -> np.ndarray:
+    """ZeroCrossingSpikeEncoder.evolve (micloc/spike_encoder.py:115-137)."""
+    x = _f64(x)
+    T, Cc = x.shape
+    s = np.empty_like(x)
+    rc = lib().mo_rzcc(_p(x), T, Cc, float(robust_width), int(bool(bipolar)), _p(s))
+    if rc != 0:
+        raise ValueError("`distance` must be greater or equal to 1")
+    return s
+
+
+def neuron_kernel(time_vec: np.ndarray, tau_syn: float, tau_mem: float) -> np.ndarray:
+    """Truncated, normalised alpha kernel (micloc/snn_beamformer.py:342-361)."""
+    tv = _f64(time_vec)
+    h = np.empty(len(tv))
+    L = lib().mo_neuron_kernel(_p(tv), len(tv), float(tau_syn), float(tau_mem), _p(h))
+    if L < 0:
+        raise AssertionError("tau_syn != tau_mem is not executable in the reference")
+    return h[:L].copy()
+
+
+@dataclass
+class SnnConfig:
+    """Host-side constants of one SNNBeamformer + bf_mat (float64)."""
+    h: np.ndarray            # STHT kernel [K]
+    b: np.ndarray            # band-pass numerator
+    a: np.ndarray            # band-pass denominator (a[0] == 1)
+    robust_width: float
+    bipolar: bool
+    nir: np.ndarray          # truncated neuron impulse response [L]
+    bf: np.ndarray           # [2M, G]
+
+    def _c(self):
+        self.h = _f64(self.h); self.b = _f64(self.b); self.a = _f64(self.a)
+        self.nir = _f64(self.nir); self.bf = _f64(self.bf)
+        c = _SnnCfg()
+        c.M = self.bf.shape[0] // 2; c.K = len(self.h); c.h = _p(self.h)
+        c.nba = len(self.b); c.b = _p(self.b); c.a = _p(self.a)
+        c.robust_width = float(self.robust_width); c.bipolar = int(bool(self.bipolar))
+        c.L = len(self.nir); c.nir = _p(self.nir)
+        c.G = self.bf.shape[1]; c.bf = _p(self.bf)
+        return c
+
+
+def snn_apply(cfg: SnnConfig, x: np.ndarray, want=("q", "z", "spikes", "vmem", "y", "power")):
+    """Full chain on one clip x[T, M]; returns dict with 'doa' + requested taps.
+
+    Restates SNNBeamformer.apply_to_signal (micloc/snn_beamformer.py:283-370) and
+    the callers' mean-power/argmax (paper_plots/target_snn_localization.py:462-464).
+    """
+    x = _f64(x)
+    T, M = x.shape
+    c = cfg._c()
+    assert M == c.M
+    out = {}
+    shapes = {"q": (T, M), "z": (T, 2 * M), "spikes": (T, 2 * M), "vmem": (T, 2 * M),
+              "y": (T, c.G), "power": (c.G,)}
+    bufs = {k: (np.empty(shapes[k]) if k in want else None) for k in shapes}
+    doa = lib().mo_snn_apply(C.byref(c), _p(x), C.c_int(T), _p(bufs["q"]), _p(bufs["z"]),
+                             _p(bufs["spikes"]), _p(bufs["vmem"]), _p(bufs["y"]), _p(bufs["power"]))
+    out["doa"] = int(doa)
+    out.update({k: v for k, v in bufs.items() if v is not None})
+    return out
+
+
+def snn_run_batch(cfg: SnnConfig, audio: np.ndarray, nthreads: int = 1,
+                  want_power: bool = True, want_spikes: bool = False):
+    """Batched chain over audio[B, T, M] (float32 or int16) on `nthreads` host threads."""
+    assert audio.dtype in (np.float32, np.int16) and audio.flags.c_contiguous
+    B, T, M = audio.shape
+    c = cfg._c()
+    assert M == c.M
+    doa = np.empty(B, dtype=np.int32)
+    power = np.empty((B, c.G)) if want_power else None
+    spikes = np.empty((B, T, 2 * M), dtype=np.int8) if want_spikes else None
+    used = lib().mo_snn_run_batch(
+        C.byref(c), audio.ctypes.data_as(C.c_void_p), int(audio.dtype == np.int16),
+        C.c_int(B), C.c_int(T), doa.ctypes.data_as(C.c_void_p), _p(power),
+        None if spikes is None else spikes.ctypes.data_as(C.c_void_p), C.c_int(nthreads))
+    return {"doa": doa, "power": power, "spikes": spikes, "threads": int(used)}
+
+
+def beamformer_apply(x, h, b, a, bf_mat) -> np.ndarray:
+    """Beamformer.apply_to_signal (micloc/beamformer.py:260-292): complex [T, G]."""
+    x = _f64(x); h = _f64(h); b = _f64(b); a = _f64(a)
+    bf_re = _f64(np.real(bf_mat)); bf_im = _f64(np.imag(bf_mat))
+    T, M = x.shape
+    G = bf_re.shape[1]
+    yr = np.empty((T, G)); yi = np.empty((T, G))
+    lib().mo_beamformer_apply(_p(x), C.c_int(T), C.c_int(M), _p(h), C.c_int(len(h)), _p(b), _p(a),
+                              C.c_int(len(b)), _p(bf_re), _p(bf_im), C.c_int(G), _p(yr), _p(yi))
+    return yr + 1j * yi

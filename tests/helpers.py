@@ -1,0 +1,77 @@
+"""Shared test plumbing: golden fixtures -> oracle config / engine spec, parity metrics."""
+import glob
+import os
+
+import numpy as np
+from scipy.signal import tf2sos
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SNN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "snn_*.npz")))
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def oracle_cfg(g):
+    from oracle import oracle as O
+    return O.SnnConfig(h=g["kernel"], b=g["ba_b"], a=g["ba_a"], robust_width=float(g["robust_width"]),
+                       bipolar=bool(g["bipolar"]), nir=g["nir"], bf=g["bf_mat"])
+
+
+def chain_spec(g, T=None):
+    """Engine spec from a golden case, going through the same host code the drop-in class uses."""
+    from haghighatshoarmuir2024_b200.engine import ChainSpec, neuron_alpha_params
+    from scipy.signal import butter
+    fs = float(g["fs"])
+    T = int(g["x"].shape[0]) if T is None else T
+    t = np.arange(T) / fs
+    tau = float(g["tau"])
+    _, a, c, L = neuron_alpha_params(t, [tau, tau])
+    sos = butter(2, g["band"], btype="bandpass", output="sos", fs=fs)
+    return ChainSpec(num_mic=g["x"].shape[1], stht_kernel=g["kernel"], sos=sos,
+                     robust_width=int(np.ceil(float(g["robust_width"]))), bipolar=bool(g["bipolar"]),
+                     neuron_decay=a, neuron_scale=c, neuron_len=L)
+
+
+def rel_err(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt); b = b.astype(dt)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def spike_agreement(s, ref):
+    """1 - (#positions where the rasters differ) / (#reference spikes)."""
+    s = np.asarray(s).astype(np.int8); ref = np.asarray(ref).astype(np.int8)
+    n_ref = int(np.count_nonzero(ref))
+    return 1.0 - np.count_nonzero(s != ref) / max(n_ref, 1)
+
+
+def synth_clips(g, B, T, seed, snrs_db=(-10.0, 0.0, 10.0, 20.0), int16=False):
+    """Seeded noisy sine clips on the golden case's geometry (restating apply_to_template,
+    micloc/snn_beamformer.py:243-275).  Returns (x [B,T,M], doa_true [B])."""
+    rng = np.random.default_rng(seed)
+    fs = float(g["fs"]); band = g["band"]
+    t = np.arange(T) / fs
+    f0 = float(np.mean(band))
+    r, th = g["r_vec"], g["theta_vec"]
+    xs, doas = [], []
+    for i in range(B):
+        doa = rng.uniform(0, 2 * np.pi)
+        d = -r * np.cos(th - doa) / 340.0
+        d = d - d.min()
+        td = t[None, :] - d[:, None]
+        td[td < 0] = 0
+        x = np.interp(td.ravel(), t, np.sin(2 * np.pi * f0 * t)).reshape(td.shape).T
+        snr_db = snrs_db[i % len(snrs_db)] - 10 * np.log10((fs / 2) / (band[1] - band[0]))
+        x = x + np.sqrt(np.mean(x ** 2)) / np.sqrt(10 ** (snr_db / 10)) * rng.standard_normal(x.shape)
+        xs.append(x); doas.append(doa)
+    x = np.stack(xs)
+    if int16:
+        x = np.round(x / np.abs(x).max() * 16000).astype(np.int16)
+    else:
+        x = x.astype(np.float32)
+    return x, np.asarray(doas)

@@ -1,0 +1,259 @@
+"""Parity of the CUDA hot path (through the C-ABI) with the CPU oracle and with the
+golden vectors of the real reference.  Needs a B200: run with -m gpu.
+
+Tolerances are the ones BASELINE.json's north_star states:
+  STHT output <= 1e-4 relative; spike time+sign agreement >= 99.9 %;
+  identical DoA argmax on >= 99.5 % of frames (a frame = one clip).
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+STHT_TOL = 1e-4
+SPIKE_AGREE = 0.999
+DOA_AGREE = 0.995
+
+
+def engine_for(g, T=None):
+    from haghighatshoarmuir2024_b200.engine import SnnEngine
+    return SnnEngine(H.chain_spec(g, T), g["bf_mat"], device=0)
+
+
+def to_dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ---------------------------------------------------------------------------
+# golden vectors of the reference, stage by stage (staged kernels + taps)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", H.SNN_CASES)
+def test_staged_taps_match_reference_golden(name):
+    g = H.load(name)
+    eng = engine_for(g)
+    out = eng.run_taps(to_dev(g["x"]))
+    torch.cuda.synchronize()
+    rows = g["rows"]
+    q = out["q"][0].cpu().numpy(); z = out["z"][0].cpu().numpy()
+    assert H.rel_err(q[rows], g["q_rows"]) < STHT_TOL
+    assert H.rel_err(z[rows], g["z_rows"]) < STHT_TOL
+    spikes = out["spikes"][0].cpu().numpy()
+    assert H.spike_agreement(spikes, g["spikes"]) >= SPIKE_AGREE
+    assert int(out["flags"][0]) == 0
+    if np.array_equal(spikes, g["spikes"]):
+        assert H.rel_err(out["vmem"][0].cpu().numpy()[rows], g["vmem_rows"]) < 1e-4
+        assert H.rel_err(out["y"][0].cpu().numpy()[rows], g["y_rows"]) < 1e-4
+        assert H.rel_err(out["power"][0].cpu().numpy(), g["power"]) < 1e-4
+    assert int(out["doa"][0]) == int(g["doa"])
+
+
+@pytest.mark.parametrize("name", H.SNN_CASES)
+def test_fused_matches_reference_golden(name):
+    g = H.load(name)
+    eng = engine_for(g)
+    if eng.M > 16:
+        pytest.skip("fused kernel covers up to 16 microphones")
+    out = eng.run(to_dev(g["x"]), want_spikes=True, fused=True)
+    torch.cuda.synchronize()
+    spikes = out["spikes"][0].cpu().numpy()
+    assert H.spike_agreement(spikes, g["spikes"]) >= SPIKE_AGREE
+    assert int(out["flags"][0]) == 0
+    if np.array_equal(spikes, g["spikes"]):
+        assert H.rel_err(out["power"][0].cpu().numpy(), g["power"]) < 1e-4
+    assert int(out["doa"][0]) == int(g["doa"])
+
+
+# ---------------------------------------------------------------------------
+# batches against the oracle: fused == staged bit for bit, both within tolerance
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,T,int16", [("snn_c1_bipolar", 4800, False), ("snn_c1_unipolar", 3000, False),
+                                          ("snn_band2_sine", 4801, True), ("snn_band3_i16", 1000, True),
+                                          ("snn_k20ms", 2500, False)])
+def test_batch_fused_vs_staged_vs_oracle(name, T, int16):
+    g = H.load(name)
+    B = 48
+    x, _ = H.synth_clips(g, B, T, seed=100 + T, int16=int16)
+    eng = engine_for(g, T)
+    xd = to_dev(x)
+    st = eng.run(xd, want_spikes=True, fused=False)
+    fu = eng.run(xd, want_spikes=True, fused=True)
+    torch.cuda.synchronize()
+    # the two device paths run the same arithmetic in the same order for spikes
+    assert torch.equal(st["spikes"], fu["spikes"])
+    assert torch.equal(st["doa"], fu["doa"])
+    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < 1e-5
+    cfg = H.oracle_cfg(g)
+    fs = float(g["fs"]); tau = float(g["tau"])
+    cfg.nir = O.neuron_kernel(np.arange(T) / fs, tau, tau)
+    ref = O.snn_run_batch(cfg, x, nthreads=8, want_spikes=True)
+    sp = fu["spikes"].cpu().numpy()
+    assert H.spike_agreement(sp, ref["spikes"]) >= SPIKE_AGREE
+    same = (fu["doa"].cpu().numpy() == ref["doa"]).mean()
+    assert same >= DOA_AGREE, f"DoA agreement {same}"
+    assert int(fu["flags"].sum()) == 0
+
+
+def test_full_size_clip_config1():
+    """Config 1 size (1 s, 48 kHz, 7 mics, G=64): one clip against the oracle + properties."""
+    g = H.load("snn_c1_bipolar")
+    T = 48000
+    x, _ = H.synth_clips(g, 4, T, seed=7, snrs_db=(20.0,))
+    eng = engine_for(g, T)
+    out = eng.run(to_dev(x), want_spikes=True, fused=True)
+    tap = eng.run_taps(to_dev(x[:1]), want=("q",))
+    torch.cuda.synchronize()
+    cfg = H.oracle_cfg(g)
+    cfg.nir = O.neuron_kernel(np.arange(T) / 48000.0, float(g["tau"]), float(g["tau"]))
+    ref = O.snn_apply(cfg, x[0].astype(np.float64), want=("q", "spikes", "power"))
+    assert H.rel_err(tap["q"][0].cpu().numpy(), ref["q"]) < STHT_TOL
+    assert H.spike_agreement(out["spikes"][0].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
+    assert int(out["doa"][0]) == ref["doa"]
+    # size-independent properties: scale invariance of spikes/DoA, linearity of the STHT
+    out2 = eng.run(to_dev(x * np.float32(4.0)), want_spikes=True, fused=True)
+    assert torch.equal(out2["spikes"], out["spikes"]) and torch.equal(out2["doa"], out["doa"])
+    s = out["spikes"][0].cpu().numpy()
+    assert not s[0].any() and not s[-1].any()          # first / last sample never spike
+    for c in range(s.shape[1]):                        # kept spikes of one sign are >= w apart
+        for sign in (1, -1):
+            pos = np.flatnonzero(s[:, c] == sign)
+            assert pos.size < 2 or np.diff(pos).min() >= int(g["robust_width"])
+
+
+def test_stht_linearity_and_zero_input():
+    g = H.load("snn_c1_bipolar")
+    eng = engine_for(g, 2048)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((1, 2048, 7)).astype(np.float32)
+    b = rng.standard_normal((1, 2048, 7)).astype(np.float32)
+    qa = eng.run_taps(to_dev(a), want=("q",))["q"]; qb = eng.run_taps(to_dev(b), want=("q",))["q"]
+    qab = eng.run_taps(to_dev(a + b), want=("q",))["q"]
+    assert H.rel_err((qa + qb).cpu().numpy(), qab.cpu().numpy()) < 1e-5
+    zero = eng.run(to_dev(np.zeros((2, 2048, 7), np.float32)), want_spikes=True, fused=True)
+    assert int(zero["spikes"].abs().sum()) == 0 and int(zero["doa"][0]) == 0      # all-equal power -> first index
+
+
+def test_ragged_and_tiny_clips():
+    g = H.load("snn_c1_bipolar")
+    cfg = H.oracle_cfg(g)
+    for T in (3, 17, 255, 256, 257, 481, 1023):
+        x, _ = H.synth_clips(g, 3, T, seed=T)
+        eng = engine_for(g, max(T, 64))
+        fu = eng.run(to_dev(x), want_spikes=True, fused=True)
+        st = eng.run(to_dev(x), want_spikes=True, fused=False)
+        torch.cuda.synchronize()
+        assert torch.equal(fu["spikes"], st["spikes"]), T
+        ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
+        assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= 0.99, T
+
+
+def test_shape_errors_raise_valueerror():
+    g = H.load("snn_c1_bipolar")
+    eng = engine_for(g)
+    with pytest.raises(ValueError):
+        eng.run(torch.zeros((1, 100, 6), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.run(torch.zeros((1, 100, 7), device="cuda", dtype=torch.float64))
+
+
+def test_run_host_end_to_end_equals_device_path():
+    g = H.load("snn_band3_i16")
+    x, _ = H.synth_clips(g, 40, 2400, seed=5, int16=True)
+    eng = engine_for(g, 2400)
+    dev = eng.run(to_dev(x), want_spikes=True, fused=True)
+    host = eng.run_host(torch.from_numpy(x).pin_memory(), want_spikes=True, fused=True)
+    assert np.array_equal(host["doa"].numpy(), dev["doa"].cpu().numpy())
+    assert np.array_equal(host["spikes"].numpy(), dev["spikes"].cpu().numpy())
+    np.testing.assert_array_equal(host["power"].numpy(), dev["power"].cpu().numpy())
+
+
+# ---------------------------------------------------------------------------
+# stand-alone stages
+# ---------------------------------------------------------------------------
+def test_rzcc_encoder_bit_exact_on_reference_golden():
+    from haghighatshoarmuir2024_b200.spike_encoder import ZeroCrossingSpikeEncoder
+    g = H.load("rzcc")
+    n = 0
+    for key in g:
+        if not key.startswith("spk_"):
+            continue
+        _, sname, w, b = key.split("_")
+        enc = ZeroCrossingSpikeEncoder(fs=48000, robust_width=int(w[1:]), bipolar=bool(int(b[1:])))
+        got = enc.evolve(g["sig_" + sname])
+        assert got.dtype == np.float64 and np.array_equal(got.astype(np.int8), g[key]), key
+        n += 1
+    assert n == 32
+
+
+def test_rzcc_encoder_white_noise_matches_oracle_and_rejects_bad_width():
+    from haghighatshoarmuir2024_b200.spike_encoder import ZeroCrossingSpikeEncoder
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((20000, 4))
+    for w in (2, 12, 40):
+        got = ZeroCrossingSpikeEncoder(48000, w, True).evolve(x)
+        assert np.array_equal(got, O.rzcc(x, w, True))
+    with pytest.raises(ValueError):
+        ZeroCrossingSpikeEncoder(48000, 0, True).evolve(x)
+
+
+def test_hilbert_beamformer_matches_reference_golden():
+    from haghighatshoarmuir2024_b200.array_geometry import CenterCircularArray
+    from haghighatshoarmuir2024_b200.beamformer import Beamformer
+    g = H.load("beamformer")
+    bf = Beamformer(CenterCircularArray(4.5e-2, 7), 10e-3, list(g["band"]), fs=float(g["fs"]))
+    y = bf.apply_to_signal(g["bf_mat"], g["x"].astype(np.float64))
+    assert y.dtype == np.complex128 and y.shape == (g["x"].shape[0], g["bf_mat"].shape[1])
+    assert H.rel_err(y[g["rows"]], g["y_rows"]) < 1e-4
+    power = np.mean(np.abs(y) ** 2, axis=0)
+    assert int(np.argmax(power)) == int(g["doa"])
+    with pytest.raises(ValueError):
+        bf.apply_to_signal(g["bf_mat"], np.zeros((100, 6)))
+
+
+# ---------------------------------------------------------------------------
+# drop-in classes
+# ---------------------------------------------------------------------------
+def test_snn_beamformer_dropin_apply_and_design():
+    from haghighatshoarmuir2024_b200.array_geometry import CenterCircularArray
+    from haghighatshoarmuir2024_b200.snn_beamformer import SNNBeamformer
+    g = H.load("snn_c1_bipolar")
+    tau = float(g["tau"])
+    beamf = SNNBeamformer(CenterCircularArray(4.5e-2, 7), float(g["kernel_duration"]), list(g["band"]),
+                          np.array([tau, tau]), bipolar_spikes=True, fs=float(g["fs"]))
+    beamf.verbose = False
+    assert beamf.kernel_length == len(g["kernel"]) and beamf.spk_encoder.robust_width == int(g["robust_width"])
+    np.testing.assert_allclose(beamf.kernel, g["kernel"], atol=1e-15)
+    T = g["x"].shape[0]
+    t = np.arange(T) / float(g["fs"])
+    y = beamf.apply_to_signal(g["bf_mat"], (t, g["x"].astype(np.float64)))
+    assert y.dtype == np.float64 and y.shape == (T, g["bf_mat"].shape[1])
+    power = np.mean(np.abs(y) ** 2, axis=0)
+    assert int(np.argmax(power)) == int(g["doa"])
+    with pytest.raises(ValueError):
+        beamf.apply_to_signal(g["bf_mat"], (t, np.zeros((T, 5))))
+    # design_from_template against the reference's matrix (columns up to a global sign)
+    bf = beamf.design_from_template((t, g["template"]), g["doa_list"])
+    assert bf.shape == g["bf_mat"].shape
+    M = 7                                             # columns are complex vectors up to a global phase
+    u = bf[:M] + 1j * bf[M:]; ur = g["bf_mat"][:M] + 1j * g["bf_mat"][M:]
+    d = np.abs(np.sum(u.conj() * ur, axis=0))
+    assert d.min() > 0.999
+    with pytest.raises(ValueError):
+        SNNBeamformer(CenterCircularArray(4.5e-2, 7), 10e-3, [2000, 1000], np.array([tau, tau]))
+
+
+def test_snn_beamformer_unipolar_design_matches_reference():
+    from haghighatshoarmuir2024_b200.array_geometry import CenterCircularArray
+    from haghighatshoarmuir2024_b200.snn_beamformer import SNNBeamformer
+    g = H.load("snn_c1_unipolar")
+    tau = float(g["tau"])
+    beamf = SNNBeamformer(CenterCircularArray(4.5e-2, 7), 10e-3, list(g["band"]), np.array([tau, tau]),
+                          bipolar_spikes=False, fs=48000)
+    beamf.verbose = False
+    t = np.arange(g["x"].shape[0]) / 48000.0
+    bf = beamf.design_from_template((t, g["template"]), g["doa_list"])
+    d = np.abs(np.sum(bf * g["bf_mat"], axis=0))
+    assert d.min() > 0.995
