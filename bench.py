@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native micloc SNN-localisation hot path.
+
+Workload (BASELINE.json configs[1]): the Monte-Carlo SNR sweep of
+paper_plots/target_snn_localization.py on a 7-microphone centre-circular array
+(r = 4.5 cm), fs = 48 kHz, 1 s clips, 10 ms STHT kernel, bipolar RZCC, 449-angle DoA
+grid, the three bands 1600-2000 / 2000-2300 / 2300-2600 Hz, 11 SNRs in [-10, 20] dB.
+One STEP = one batch of `--clips-per-band` clips for each of the three bands through
+the fused STHT -> band-pass -> RZCC -> neuron filter -> beamforming power -> argmax
+kernel (3 launches), plus the DoA histogram (and its NCCL all-reduce when N > 1).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N
+    python bench.py --impl reference ...        # the CPU path on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FS = 48_000
+T_CLIP = 48_000
+NUM_MIC = 7
+SNR_GRID = np.linspace(-10, 20, 11)          # target_snn_localization.py:435
+METRIC = "clips_per_sec"
+UNIT = "clips/s"
+RHO_NOMINAL = 0.076                          # spikes per channel-sample; measured value is reported
+
+
+def load_workload():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bench_c2_bf.npz"))
+    bands = [list(map(float, b)) for b in d["bands"]]
+    return d, bands
+
+
+def flops_per_mic_sample(K, M, G, rho, gram=True):
+    """Algorithmic FLOP per microphone sample (FMA = 2), DESIGN.md 'Roofline'.
+    survey: F = K + 40 + G (2 rho + 6/M)                       (per-neuron time loop)
+    gram  : F = K + 40 + 24 + (2M)(2M+1)/M                      (what the fused kernel has to do:
+            240 FMA STHT, 2 ch x 2 biquads x 9, cumsum/sign, 2 ch x 12 neuron, upper-triangular Gram)"""
+    if gram:
+        return K + 40 + 24 + (2 * M) * (2 * M + 1) / M
+    return K + 40 + G * (2 * rho + 6.0 / M)
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------
+def host_clips(d, band_idx, bands, n, seed):
+    """n clips of band `band_idx` synthesised on the HOST with numpy (same recipe as
+    SnrSweep.synthesize / SNNBeamformer.apply_to_template)."""
+    rng = np.random.default_rng(seed)
+    band = bands[band_idx]
+    t = np.arange(T_CLIP) / FS
+    f0 = band[1]
+    r, th = d["r_vec"], d["theta_vec"]
+    corr = 10 * np.log10((FS / 2) / (band[1] - band[0]))
+    xs = np.empty((n, T_CLIP, NUM_MIC), dtype=np.float32)
+    for i in range(n):
+        doa = rng.uniform(0, 2 * np.pi)
+        dl = -r * np.cos(th - doa) / 340.0
+        dl = dl - dl.min()
+        td = t[None, :] - dl[:, None]
+        td[td < 0] = 0
+        x = np.interp(td.ravel(), t, np.sin(2 * np.pi * f0 * t)).reshape(td.shape).T
+        snr = 10 ** ((SNR_GRID[i % len(SNR_GRID)] - corr) / 10)
+        xs[i] = x + np.sqrt(np.mean(x ** 2)) / np.sqrt(snr) * rng.standard_normal(x.shape)
+    return xs
+
+
+def oracle_cfgs(d, bands):
+    from scipy.signal import butter
+    from oracle import oracle as O
+    cfgs = []
+    t = np.arange(T_CLIP) / FS
+    for i, band in enumerate(bands):
+        b, a = butter(2, band, btype="bandpass", analog=False, output="ba", fs=FS)
+        tau = float(d[f"tau_{i}"])
+        cfgs.append(O.SnnConfig(h=d["kernel"], b=b, a=a, robust_width=float(d[f"robust_width_{i}"]), bipolar=True,
+                                nir=O.neuron_kernel(t, tau, tau), bf=d[f"bf_{i}"]))
+    return cfgs
+
+
+def cpu_pass(cfgs, clips_per_band, nthreads):
+    """One bounded pass of the CPU path: sum over bands of (clips, seconds)."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    n = 0
+    outs = []
+    for cfg, x in zip(cfgs, clips_per_band):
+        outs.append(O.snn_run_batch(cfg, x, nthreads=nthreads, want_power=False, want_spikes=False))
+        n += x.shape[0]
+    return n, time.perf_counter() - t0, outs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, bands = load_workload()
+    cores = os.cpu_count() or 1
+    cfgs = oracle_cfgs(d, bands)
+    n_per_band = cores if args.cpu_clips_per_band <= 0 else args.cpu_clips_per_band
+    clips = [host_clips(d, i, bands, n_per_band, seed=1000 + i) for i in range(len(bands))]
+    for _ in range(args.warmup):
+        cpu_pass(cfgs, [c[:1] for c in clips], cores)
+    tot_n, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        n, s, _ = cpu_pass(cfgs, clips, cores)
+        tot_n += n; tot_s += s
+    v = tot_n / tot_s
+    sample = f"{n_per_band} clips x {len(bands)} bands per step (1 s, 7 mics, G=449), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_per_band, "f32"),
+        "mic_msamples_per_sec": v * T_CLIP * NUM_MIC / 1e6,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle/micloc_oracle.c: C restatement of SNNBeamformer.apply_to_signal + power/argmax, "
+                                 "pinned bit-identical to numpy/scipy on tests/golden; pthreads over clips"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(clips_per_band, dtype):
+    return {"workload": "configs[1]: Monte-Carlo SNR sweep (target_snn_localization.py), 7-mic centre-circular array "
+                        "r=4.5cm, fs=48kHz, 1 s clips, bands 1600-2000/2000-2300/2300-2600 Hz, G=449, bipolar RZCC, "
+                        "11 SNRs -10..20 dB, random DoA",
+            "clips_per_band_per_step": clips_per_band, "bands": 3, "clip_samples": T_CLIP, "num_mic": NUM_MIC,
+            "num_doa": 449, "stht_taps": 480, "input_dtype": dtype,
+            "cache": "per-step input >> 126 MB L2 (no flush needed)", "parallelism": "clips sharded by rank"}
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from haghighatshoarmuir2024_b200 import _native as N
+    from haghighatshoarmuir2024_b200.montecarlo import BandSetup, SnrSweep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = N.lib()
+
+    d, bands = load_workload()
+    nb = len(bands)
+    Bb = args.clips_per_band
+    tdtype = torch.int16 if args.dtype == "i16" else torch.float32
+    setups = [BandSetup(band=bands[i], tau=float(d[f"tau_{i}"]), bf_mat=d[f"bf_{i}"]) for i in range(nb)]
+    sweep = SnrSweep(setups, d["r_vec"], d["theta_vec"], FS, float(d["kernel_duration"]), T_CLIP, device=local)
+    G = sweep.G
+    audio, doa_true = [], []
+    for i in range(nb):
+        a, dt_, _ = sweep.synthesize(i, Bb, seed=10_000 * (rank + 1) + i, snr_db_grid=SNR_GRID, dtype=tdtype)
+        audio.append(a); doa_true.append(dt_)
+    torch.cuda.synchronize()
+    hist = torch.zeros(G, dtype=torch.int64, device=dev)
+    spikes_buf = None
+
+    def step(want_spikes=True):
+        hist.zero_()
+        outs = []
+        for i in range(nb):
+            outs.append(sweep.run_band(i, audio[i], want_spikes=want_spikes, want_power=False, hist=hist))
+        if world > 1:
+            dist.all_reduce(hist)          # the only cross-GPU exchange: DoA histograms
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(args.warmup):
+        outs = step()
+    barrier()
+    for e in sweep.engines:
+        e.enable_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.micloc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        outs = step()
+    ev1.record()
+    barrier()
+    launches = lib.micloc_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    kern_ms, kern_n = 0.0, 0
+    for e in sweep.engines:
+        m_, n_ = e.last_kernel_ms()
+        kern_ms += m_; kern_n += n_
+        e.enable_timing(False)
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_max = float(tm.item())
+    clips_step_all = nb * Bb * world
+    value = clips_step_all * args.steps / (ms_max * 1e-3)
+    spike_density = float(np.mean([float(o["spikes"][:64].ne(0).float().mean()) for o in outs]))
+    flags = int(sum(int(o["flags"].sum()) for o in outs))
+    del outs
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the C-ABI with HOST buffers (`e2e`) ----
+    host = [a.cpu().pin_memory() for a in audio]
+    esz = host[0].element_size()
+    h2d = sum(h.numel() for h in host) * esz
+    d2h = nb * Bb * (4 + 4)                                       # doa + flags per clip
+    def e2e_step():
+        res = []
+        for i in range(nb):
+            res.append(sweep.engines[i].run_host(host[i], want_spikes=False, want_power=False, fused=True))
+        return res
+    for _ in range(max(1, min(args.warmup, 2))):
+        res = e2e_step()
+    barrier()
+    l1 = lib.micloc_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    launches += lib.micloc_launch_count() - l1
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = clips_step_all * args.steps / float(te.item())
+    # the host path and the device path must agree bit for bit
+    dev_doa = [sweep.run_band(i, audio[i], want_power=False)["doa"].cpu().numpy() for i in range(nb)]
+    e2e_same = all(np.array_equal(res[i]["doa"].numpy(), dev_doa[i]) for i in range(nb))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (fused) kernel ----
+    K = len(d["kernel"])
+    mic_samples_per_launch = Bb * T_CLIP * NUM_MIC
+    avg_launch_ms = kern_ms / max(kern_n, 1)
+    F_gram = flops_per_mic_sample(K, NUM_MIC, G, spike_density, gram=True)
+    F_survey = flops_per_mic_sample(K, NUM_MIC, G, spike_density, gram=False)
+    achieved = mic_samples_per_launch * F_gram / (avg_launch_ms * 1e-3) / 1e12
+    peak = {}
+    for name, variant in (("ffma", 0), ("ffma2", 1)):
+        import ctypes
+        v = ctypes.c_double()
+        N.check(lib.micloc_fp32_peak(local, variant, ctypes.byref(v)))
+        peak[name] = v.value
+    fp32_peak = max(peak.values())
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    in_bytes = 2 if args.dtype == "i16" else 4
+    hbm_gbs = mic_samples_per_launch * (in_bytes + 2) / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "fp32", "kernel": "k_fused", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp32_peak, "traffic": traffic,
+        "peak_source": f"measured in this run by micloc_fp32_peak (FFMA {peak['ffma']:.1f}, FFMA2 {peak['ffma2']:.1f} TFLOP/s)",
+        "flop_per_mic_sample": F_gram, "flop_per_mic_sample_survey_formula": F_survey,
+        "achieved_survey_formula": achieved * F_survey / F_gram,
+        "avg_launch_ms": avg_launch_ms, "launches_timed": kern_n, "mic_samples_per_launch": mic_samples_per_launch,
+        "kernel_share_of_step": kern_ms / ms,
+        "hbm_view": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                     "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)" if hbm_src == "measured" else "fallback 6650",
+                     "bytes_per_mic_sample": in_bytes + 2},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N == 1) + DoA match rate of the GPU path against it ----
+    cpu = None
+    match = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        cfgs = oracle_cfgs(d, bands)
+        n_cpu = args.cpu_clips_per_band if args.cpu_clips_per_band > 0 else cores
+        n_cpu = min(n_cpu, Bb)
+        xs = [host[i][:n_cpu].numpy() for i in range(nb)]
+        n, s, ref = cpu_pass(cfgs, xs, cores)
+        cpu = {"value": n / s, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n_cpu} clips of each band of the GPU batch ({n} clips, {s:.1f} s wall)"}
+        same = np.concatenate([dev_doa[i][:n_cpu] == ref[i]["doa"] for i in range(nb)])
+        match = {"doa_match_rate_vs_cpu_path": float(same.mean()), "clips_compared": int(same.size)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(Bb, args.dtype),
+        "mic_msamples_per_sec": value * T_CLIP * NUM_MIC / 1e6,
+        "outputs_in_timed_region": "int8 spikes [B,T,14] + int32 DoA [B] + DoA histogram written to HBM",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "micloc_snn_run_host (pinned host audio in, DoA indices + flags out)",
+                "matches_device_path": bool(e2e_same)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "spike_density": spike_density, "rzcc_overflow_clips": flags,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    if match:
+        line["parity"] = match
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips-per-band", type=int, default=1024)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "i16"])
+    ap.add_argument("--cpu-clips-per-band", type=int, default=0, help="CPU sample size per band (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

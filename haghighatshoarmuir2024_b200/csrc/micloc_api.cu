@@ -54,7 +54,8 @@ struct micloc_snn {
     DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
     cudaStream_t hs[2] = {nullptr, nullptr};
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev;   // [2*i], [2*i+1] bracket the kernels of the i-th timed run
+    size_t ev_used = 0;            // events recorded since the last micloc_snn_last_kernel_ms
     int last_kernels = 0;
     int sm_count = 148;
 };
@@ -166,8 +167,7 @@ extern "C" int micloc_snn_destroy(micloc_snn *c) {
         c->h_audio[i].release(); c->h_spk[i].release(); c->h_pow[i].release(); c->h_doa[i].release(); c->h_flg[i].release();
         if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     }
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     delete c;
     return MICLOC_OK;
 }
@@ -182,19 +182,36 @@ extern "C" int micloc_snn_set_bf(micloc_snn *c, const double *bf, int32_t G) {
 extern "C" int micloc_snn_enable_timing(micloc_snn *c, int enable) {
     if (!c) return set_error(MICLOC_ERR_CONFIG, "null context");
     c->timing = enable != 0;
-    if (c->timing && !c->ev0) {
-        MICLOC_CUDA(cudaEventCreate(&c->ev0));
-        MICLOC_CUDA(cudaEventCreate(&c->ev1));
+    c->ev_used = 0;
+    return MICLOC_OK;
+}
+
+// record one event of a (start, stop) pair on `st`; pairs accumulate until they are read
+static int timing_mark(micloc_snn *c, cudaStream_t st) {
+    if (!c->timing) return MICLOC_OK;
+    if (c->ev_used == c->ev.size()) {
+        if (c->ev.size() >= 16384) return MICLOC_OK;   // stop recording, keep running
+        cudaEvent_t e;
+        MICLOC_CUDA(cudaEventCreate(&e));
+        c->ev.push_back(e);
     }
+    MICLOC_CUDA(cudaEventRecord(c->ev[c->ev_used++], st));
     return MICLOC_OK;
 }
 
 extern "C" int micloc_snn_last_kernel_ms(micloc_snn *c, float *ms, int32_t *n_kernels) {
-    if (!c || !c->ev0) return set_error(MICLOC_ERR_CONFIG, "timing not enabled");
-    float v = 0.f;
-    MICLOC_CUDA(cudaEventElapsedTime(&v, c->ev0, c->ev1));
-    if (ms) *ms = v;
-    if (n_kernels) *n_kernels = c->last_kernels;
+    if (!c || !c->timing) return set_error(MICLOC_ERR_CONFIG, "timing not enabled");
+    double total = 0.0;
+    const size_t pairs = c->ev_used / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+        float v = 0.f;
+        MICLOC_CUDA(cudaEventSynchronize(c->ev[2 * i + 1]));
+        MICLOC_CUDA(cudaEventElapsedTime(&v, c->ev[2 * i], c->ev[2 * i + 1]));
+        total += v;
+    }
+    c->ev_used = 0;
+    if (ms) *ms = (float)total;
+    if (n_kernels) *n_kernels = (int)pairs;
     return MICLOC_OK;
 }
 
@@ -280,7 +297,7 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
     if (!spk) { MICLOC_TRY(c->spikes.reserve(n_c)); spk = (int8_t *)c->spikes.ptr; }
     if (!vm) { MICLOC_TRY(c->vmem.reserve(n_c * sizeof(float))); vm = (float *)c->vmem.ptr; }
     if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
-    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev0, st));
+    MICLOC_TRY(timing_mark(c, st));
     const long long l0 = g_launches.load();
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, q, B, T, st));
@@ -302,7 +319,7 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
         count_launch(1);
         MICLOC_CUDA(cudaGetLastError());
     }
-    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev1, st));
+    MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
     return MICLOC_OK;
 }
@@ -343,12 +360,12 @@ extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *flg = flags_dev;
     if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
-    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev0, st));
+    MICLOC_TRY(timing_mark(c, st));
     const long long l0 = g_launches.load();
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     MICLOC_TRY(launch_fused(c->p, c->d_taps, c->d_Wd, audio, dtype, B, T, spikes_dev, power_dev, doa_dev, flg,
                             c->sm_count, st));
-    if (c->timing) MICLOC_CUDA(cudaEventRecord(c->ev1, st));
+    MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
     return MICLOC_OK;
 }
@@ -441,6 +458,31 @@ extern "C" int micloc_hilbert_beamform(micloc_snn *c, const void *audio, int dty
         k_cpower_argmax<<<(unsigned)B, 256, 0, st>>>((const float2 *)y_dev, power_dev, doa_dev, G, T);
         count_launch(1);
     }
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// DoA histogram of a batch (the only thing that crosses GPUs: SURVEY.md 8e)
+// ---------------------------------------------------------------------------
+namespace micloc {
+__global__ void __launch_bounds__(256)
+k_doa_hist(const int32_t *__restrict__ doa, long long B, int G, unsigned long long *__restrict__ hist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int g = doa[i];
+    if (g >= 0 && g < G) atomicAdd(hist + g, 1ull);
+}
+}  // namespace micloc
+
+extern "C" int micloc_doa_histogram(const int32_t *doa_dev, int64_t B, int32_t G, int64_t *hist_dev, int device,
+                                    void *stream) {
+    if (!doa_dev || !hist_dev || B < 0 || G < 1) return set_error(MICLOC_ERR_SHAPE, "bad histogram arguments");
+    if (B == 0) return MICLOC_OK;
+    MICLOC_CUDA(cudaSetDevice(device));
+    k_doa_hist<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(doa_dev, B, G,
+                                                                             (unsigned long long *)hist_dev);
+    count_launch(1);
     MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
 }

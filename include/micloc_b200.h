@@ -101,6 +101,12 @@ int micloc_snn_run_host(micloc_snn *ctx, const void *audio_host, int dtype, int6
 int micloc_snn_gram(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
                     int64_t t_start, double *gram_dev, void *stream);
 
+/* hist_dev[g] += #{b : doa_dev[b] == g}; hist_dev is int64[G] on `device`, accumulated
+ * (zero it first).  The per-GPU histograms are what the Monte-Carlo driver sums across
+ * GPUs (paper_plots/target_snn_localization.py:447-467 keeps per-trial DoA errors). */
+int micloc_doa_histogram(const int32_t *doa_dev, int64_t B, int32_t G, int64_t *hist_dev, int device,
+                         void *stream);
+
 /* ---- stand-alone stages ---------------------------------------------------- */
 /* ZeroCrossingSpikeEncoder.evolve on arbitrary float64 input, exact find_peaks
  * semantics (unbounded clusters).  sig_dev [B][T][C] f64 -> spikes_dev [B][T][C] int8. */
@@ -160,11 +166,15 @@ const char *micloc_last_error(void);
 int micloc_version(void);
 /* kernels launched by this library since load (claim for bench.py's gpu_launches) */
 int64_t micloc_launch_count(void);
-/* duration in ms of the hot-path kernels of the last micloc_snn_run on `ctx`,
- * measured with CUDA events on the caller's stream (valid after a stream sync);
- * n_kernels receives how many kernels that was. */
-int micloc_snn_last_kernel_ms(micloc_snn *ctx, float *ms, int32_t *n_kernels);
+/* With timing enabled every micloc_snn_run / run_taps brackets its kernels with a pair
+ * of CUDA events on the caller's stream.  micloc_snn_last_kernel_ms waits for them and
+ * returns the SUM of those durations (ms) since the previous read, with the number of
+ * runs summed in n_runs, then forgets them. */
+int micloc_snn_last_kernel_ms(micloc_snn *ctx, float *ms, int32_t *n_runs);
 int micloc_snn_enable_timing(micloc_snn *ctx, int enable);
+/* FP32 FMA-pipe micro-benchmark on `device` (the measured denominator of the
+ * roofline in bench.py): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
+int micloc_fp32_peak(int device, int variant, double *tflops);
 
 #ifdef __cplusplus
 }
