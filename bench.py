@@ -402,7 +402,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips-per-band", type=int, default=1024)
+    ap.add_argument("--clips-per-band", type=int, default=1776,
+                    help="clips per band per step; 1776 = 2 x (148 SMs x 3 CTAs x 2 clips): two full waves of the fused kernel")
     ap.add_argument("--dtype", default="f32", choices=["f32", "i16"])
     ap.add_argument("--cpu-clips-per-band", type=int, default=0, help="CPU sample size per band (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

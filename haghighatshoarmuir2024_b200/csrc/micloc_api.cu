@@ -49,6 +49,7 @@ struct micloc_snn {
     float *d_sos = nullptr;        // [1][kMaxSections][5]
     float *d_W = nullptr;          // [C2][G] f32
     double *d_Wd = nullptr;        // [C2][G] f64
+    unsigned int *d_sm_slots = nullptr;  // [256] per-SM CTA arrival counters (role rotation of the fused kernel)
     DevBuf q, spikes, vmem, gram, flags, part;
     // host staging for run_host
     DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
@@ -153,6 +154,11 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
     }
     rc = upload_bf(c, cfg->bf_mat, cfg->num_doa);
     if (rc) { micloc_snn_destroy(c); return rc; }
+    if (cudaMalloc(&c->d_sm_slots, 256 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->d_sm_slots, 0, 256 * sizeof(unsigned int)) != cudaSuccess) {
+        micloc_snn_destroy(c);
+        return set_error(MICLOC_ERR_CUDA, "cudaMalloc(sm_slots) failed");
+    }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
     return MICLOC_OK;
@@ -161,7 +167,7 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
 extern "C" int micloc_snn_destroy(micloc_snn *c) {
     if (!c) return MICLOC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->d_taps); cudaFree(c->d_sos); cudaFree(c->d_W); cudaFree(c->d_Wd);
+    cudaFree(c->d_taps); cudaFree(c->d_sos); cudaFree(c->d_W); cudaFree(c->d_Wd); cudaFree(c->d_sm_slots);
     c->q.release(); c->spikes.release(); c->vmem.release(); c->gram.release(); c->flags.release(); c->part.release();
     for (int i = 0; i < 2; ++i) {
         c->h_audio[i].release(); c->h_spk[i].release(); c->h_pow[i].release(); c->h_doa[i].release(); c->h_flg[i].release();
@@ -364,7 +370,7 @@ extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64
     const long long l0 = g_launches.load();
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     MICLOC_TRY(launch_fused(c->p, c->d_taps, c->d_Wd, audio, dtype, B, T, spikes_dev, power_dev, doa_dev, flg,
-                            c->sm_count, st));
+                            c->d_sm_slots, c->sm_count, st));
     MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
     return MICLOC_OK;

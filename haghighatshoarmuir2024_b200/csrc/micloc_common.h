@@ -51,6 +51,7 @@ int launch_chain_any(const ChainParams &p, const void *audio, int dtype, const f
                      int nb, float *z, int8_t *spikes, int32_t *flags, long long B, long long T, cudaStream_t st);
 int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
-                 int sm_count, cudaStream_t st);
+                 unsigned int *sm_slots, int sm_count, cudaStream_t st);
+bool fused_supported(const ChainParams &p);
 
 }  // namespace micloc

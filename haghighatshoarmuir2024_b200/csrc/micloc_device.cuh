@@ -13,7 +13,7 @@
 namespace micloc {
 
 constexpr int kMaxSections = 4;   // biquads per band-pass
-constexpr int kClusterMax = 8;    // RZCC candidates buffered per open cluster
+constexpr int kClusterMax = 6;    // RZCC candidates buffered per open cluster
 constexpr int kFirR = 16;         // consecutive outputs per thread in the FIR
 constexpr int kFirJB = 8;         // taps per register block
 
@@ -137,92 +137,137 @@ __device__ __forceinline__ float biquad_step(const float (&sos)[kMaxSections][5]
 }
 
 // ---------------------------------------------------------------------------
-// RZCC: streaming find_peaks(cumsum(z), distance=w) for one channel.
+// RZCC: streaming find_peaks(cumsum(z), distance=w) for one channel
+// (micloc/spike_encoder.py:115-137 + scipy _local_maxima_1d / _select_by_peak_distance).
 //
-// Candidates: a peak of the cumulative sum sits where z goes + -> (zeros) -> -,
-// at the midpoint of the flat top (scipy _local_maxima_1d); first and last
-// sample are never peaks.  Candidates closer than w samples form a cluster;
-// a cluster is closed once w samples pass without a new candidate and is then
-// resolved by scipy's greedy rule (_select_by_peak_distance: highest cumsum
-// first, it removes every candidate nearer than w; ties -> later position).
-// Valleys are the same on -cumsum, independently (spike_encoder.py:131-135).
-// A cluster larger than kClusterMax sets `overflow` (the caller reruns the clip
-// through the unbounded encoder, micloc_rzcc_encode_f64 semantics).
+// Detection (every sample): a peak of the cumulative sum sits where z goes
+// + -> (zeros) -> -, at the midpoint of the flat top; a valley (peak of -cumsum,
+// spike_encoder.py:131-135) where z goes - -> (zeros) -> +.  First and last sample
+// are never peaks.  The height of a candidate is the cumulative sum on the flat
+// top, i.e. the running sum BEFORE the sample that ends it.  Heights are only
+// ever compared inside one cluster (< kClusterMax*w samples), and the cumulative
+// sum of a band-passed signal stays bounded, so a float32 running sum orders
+// them as the reference's float64 one does.
+// Candidates of a segment of kSeg samples are appended to a small list.
+//
+// Resolution (every kSeg samples): candidates of one polarity closer than w
+// samples form a cluster; a cluster is closed once w samples pass without a new
+// candidate and is then resolved by scipy's greedy rule (highest first, it removes
+// every candidate nearer than w; ties -> later position).  A list or cluster that
+// overflows sets `overflow` (the clip is flagged; micloc_rzcc_encode_f64 is the
+// unbounded encoder).
 // ---------------------------------------------------------------------------
-struct RzccCluster {
-    int n;
-    int last;                 // position of the newest candidate
-    int pos[kClusterMax];
-    double hgt[kClusterMax];
-};
+constexpr int kSeg = 32;          // samples between two cluster resolutions
+constexpr int kCandMax = 8;       // candidates buffered per segment and channel
+constexpr int kPlateauMax = 16;   // longest run of exact zeros inside a flat top the streaming encoder follows
 
 struct RzccState {
-    double csum;              // running cumulative sum (float64 like np.cumsum)
-    int rise;                 // index of the active '+' sample, -1 if none
-    int fall;                 // index of the active '-' sample, -1 if none
-    double rise_h, fall_h;    // cumsum at rise / -cumsum at fall
+    float csum;               // running cumulative sum
+    int r;                    // index of the last non-zero sample (-1: none yet)
+    int sgn;                  // 1 when that sample was positive
+    int ncand;                // candidates waiting in the segment list
+    int n0, n1;               // open cluster sizes: valleys, peaks
+    int last0, last1;         // position of the newest candidate of each open cluster
     int overflow;
-    RzccCluster pk, vl;
+    __device__ __forceinline__ int n(int pol) const { return pol ? n1 : n0; }
+    __device__ __forceinline__ int last(int pol) const { return pol ? last1 : last0; }
+    __device__ __forceinline__ void set_n(int pol, int v) { if (pol) n1 = v; else n0 = v; }
+    __device__ __forceinline__ void set_last(int pol, int v) { if (pol) last1 = v; else last0 = v; }
 };
 
 __device__ __forceinline__ void rzcc_reset(RzccState &s) {
-    s.csum = 0.0; s.rise = -1; s.fall = -1; s.rise_h = 0.0; s.fall_h = 0.0; s.overflow = 0;
-    s.pk.n = 0; s.pk.last = 0; s.vl.n = 0; s.vl.last = 0;
+    s.csum = 0.f; s.r = -1; s.sgn = 0; s.ncand = 0;
+    s.n0 = s.n1 = 0; s.last0 = s.last1 = 0; s.overflow = 0;
+}
+
+// Storage of one channel's candidate list and cluster buffers.  `stride` is the
+// distance between consecutive entries (1 for a private array, 32 for arrays
+// interleaved across the lanes of a warp in shared memory).
+struct RzccStore {
+    int *cand_pos;            // [kCandMax]   (pos << 1) | is_peak
+    float *cand_h;            // [kCandMax]   height, sign-adjusted so that higher wins
+    int *cl_pos;              // [2][kClusterMax]
+    float *cl_h;              // [2][kClusterMax]
+    int stride;
+};
+
+// one sample: update the running sum, detect a candidate that this sample confirms
+__device__ __forceinline__ void rzcc_detect(RzccState &s, const RzccStore &st, int bipolar, int t, float z,
+                                            int max_plateau) {
+    const float cprev = s.csum;
+    s.csum = cprev + z;
+    const bool nz = z != 0.f;
+    const bool pos = z > 0.f;
+    const bool ev = nz && (s.r >= 1) && (pos != (s.sgn != 0)) && (bipolar || s.sgn);
+    if (ev) {
+        // a flat top of exact zeros longer than max_plateau puts the spike further back than the
+        // fused kernel's ring reaches (digital silence inside a clip): flag the clip instead
+        if (t - 1 - s.r > max_plateau) {
+            s.overflow = 1;
+        } else if (s.ncand < kCandMax) {
+            st.cand_pos[s.ncand * st.stride] = (((s.r + t - 1) >> 1) << 1) | s.sgn;
+            st.cand_h[s.ncand * st.stride] = s.sgn ? cprev : -cprev;
+            ++s.ncand;
+        } else {
+            s.overflow = 1;
+        }
+    }
+    if (nz) { s.r = t; s.sgn = pos ? 1 : 0; }
 }
 
 template <typename Emit>
-__device__ __forceinline__ void rzcc_resolve(RzccCluster &cl, int w, int sign, Emit &&emit) {
-    if (cl.n == 1) { emit(cl.pos[0], sign); cl.n = 0; return; }
-    unsigned und = (1u << cl.n) - 1u;
+__device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, int pol, int w, Emit &&emit) {
+    const int n = s.n(pol);
+    int *cp = st.cl_pos + pol * kClusterMax * st.stride;
+    float *ch = st.cl_h + pol * kClusterMax * st.stride;
+    const int sign = pol ? 1 : -1;
+    s.set_n(pol, 0);
+    if (n == 1) { emit(cp[0], sign); return; }
+    unsigned und = (1u << n) - 1u;
     while (und) {
-        int best = -1;
-        for (int i = 0; i < cl.n; ++i)
-            if (((und >> i) & 1u) && (best < 0 || cl.hgt[i] >= cl.hgt[best])) best = i;
-        emit(cl.pos[best], sign);
-        for (int i = 0; i < cl.n; ++i) {
-            int d = cl.pos[i] - cl.pos[best];
+        int best = -1; float hb = 0.f;
+        for (int i = 0; i < n; ++i)
+            if ((und >> i) & 1u) {
+                const float h = ch[i * st.stride];
+                if (best < 0 || h >= hb) { best = i; hb = h; }
+            }
+        const int pb = cp[best * st.stride];
+        emit(pb, sign);
+        for (int i = 0; i < n; ++i) {
+            int d = cp[i * st.stride] - pb;
             d = d < 0 ? -d : d;
             if (d < w) und &= ~(1u << i);
         }
     }
-    cl.n = 0;
 }
 
+// end of a segment whose last processed sample is t_end: feed the buffered
+// candidates to the clusters, close what can be closed (everything when `final`).
+// emit(pos, sign) is called for every final spike; pos > t_end - (kClusterMax-1)*(w-1) - w - kSeg.
 template <typename Emit>
-__device__ __forceinline__ void rzcc_push(RzccState &s, RzccCluster &cl, int w, int sign, int pos,
-                                          double h, Emit &&emit) {
-    if (cl.n > 0 && pos - cl.last >= w) rzcc_resolve(cl, w, sign, emit);
-    if (cl.n == kClusterMax) { s.overflow = 1; return; }
-    cl.pos[cl.n] = pos; cl.hgt[cl.n] = h; cl.last = pos; ++cl.n;
-}
-
-// feed sample z at time t; emit(pos, sign) is called for every final spike,
-// always with pos < t and pos > t - kClusterMax*w - 1.
-template <typename Emit>
-__device__ __forceinline__ void rzcc_step(RzccState &s, int w, int bipolar, int t, float z,
-                                          Emit &&emit) {
-    s.csum += (double)z;
-    if (z > 0.f) {
-        if (bipolar && s.fall >= 0) {
-            rzcc_push(s, s.vl, w, -1, (s.fall + t - 1) >> 1, s.fall_h, emit);
-            s.fall = -1;
-        }
-        if (t >= 1) { s.rise = t; s.rise_h = s.csum; }
-    } else if (z < 0.f) {
-        if (s.rise >= 0) {
-            rzcc_push(s, s.pk, w, +1, (s.rise + t - 1) >> 1, s.rise_h, emit);
-            s.rise = -1;
-        }
-        if (t >= 1) { s.fall = t; s.fall_h = -s.csum; }
+__device__ __forceinline__ void rzcc_segment_end(RzccState &s, const RzccStore &st, int w, int t_end, bool final,
+                                                 Emit &&emit) {
+    for (int e = 0; e < s.ncand; ++e) {
+        const int pp = st.cand_pos[e * st.stride];
+        const float h = st.cand_h[e * st.stride];
+        const int pol = pp & 1, pos = pp >> 1;
+        if (s.n(pol) > 0 && pos - s.last(pol) >= w) rzcc_resolve(s, st, pol, w, emit);
+        const int n = s.n(pol);
+        if (n == kClusterMax) { s.overflow = 1; continue; }
+        st.cl_pos[(pol * kClusterMax + n) * st.stride] = pos;
+        st.cl_h[(pol * kClusterMax + n) * st.stride] = h;
+        s.set_last(pol, pos);
+        s.set_n(pol, n + 1);
     }
-    if (s.pk.n > 0 && t - s.pk.last >= w) rzcc_resolve(s.pk, w, +1, emit);
-    if (bipolar && s.vl.n > 0 && t - s.vl.last >= w) rzcc_resolve(s.vl, w, -1, emit);
+    s.ncand = 0;
+    for (int pol = 0; pol < 2; ++pol)
+        if (s.n(pol) > 0 && (final || t_end - s.last(pol) >= w)) rzcc_resolve(s, st, pol, w, emit);
 }
 
-template <typename Emit>
-__device__ __forceinline__ void rzcc_finish(RzccState &s, int w, int bipolar, Emit &&emit) {
-    if (s.pk.n > 0) rzcc_resolve(s.pk, w, +1, emit);
-    if (bipolar && s.vl.n > 0) rzcc_resolve(s.vl, w, -1, emit);
+// lag after which the spike raster is final: a spike at position p is decided at the
+// latest by the segment end t_end >= p + kPlateauMax/2 + (kClusterMax-1)*(w-1) + w + kSeg - 1.
+__host__ __device__ inline int rzcc_lag(int w) {
+    return (((kClusterMax - 1) * (w - 1) + w + kSeg + kPlateauMax / 2) + kSeg - 1) / kSeg * kSeg;
 }
 
 // ---------------------------------------------------------------------------

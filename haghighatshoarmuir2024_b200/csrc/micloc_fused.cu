@@ -1,247 +1,511 @@
 // micloc_fused.cu -- the fused hot-path kernel: raw audio in, spikes + per-DoA
 // power + DoA index out; nothing else touches HBM.
 //
-//   audio tile --(smem, mic-major, padded)--> STHT FIR (FP32 FFMA, register window)
-//     --> [in-phase | quadrature] --> SOS band-pass --> RZCC (cluster NMS)
-//     --> spike ring (smem) --> alpha-kernel neuron recurrences --> vmem tile (smem)
-//     --> Gram accumulation  C += v v^T   (registers, float64 across tiles)
-//   clip end:  power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
-//
 // Reference sites: micloc/snn_beamformer.py:283-370 and the callers' power/argmax
 // paper_plots/target_snn_localization.py:462-464.
 //
-// One CTA owns one clip at a time (persistent grid-stride over clips) and walks
-// it in time tiles; filter/RZCC/neuron state is carried in registers by one
-// thread per channel, spikes of the last RING steps live in a shared-memory
-// ring so the neuron stage can run D = kClusterMax*w steps behind the encoder
-// (the latency of the exact find_peaks(distance=w) decision).
+// One persistent CTA of four warps owns kSlots = 2 clips at a time and walks them
+// in time tiles of kTile = 64 samples.  The warps are specialised and run as a
+// software pipeline, one __syncthreads per tile:
+//
+//   aux warp   tile k+1  audio (HBM) -> mic-major ring in shared memory
+//   FIR warps  tile k    STHT quadrature FIR, one warp per clip: every lane owns 16
+//                        consecutive outputs of one microphone and walks the 240
+//                        non-zero Hilbert taps in blocks of 8 with a sliding register
+//                        window; the multiply-adds are packed FFMA2 (fma.rn.f32x2)
+//   chain warp tile k-1  one lane per (clip, channel): SOS band-pass, RZCC candidate
+//                        detection (+ cluster resolution every 32 samples) into a
+//                        spike ring, alpha-kernel neuron recurrences kLag samples
+//                        behind (the latency of the exact find_peaks decision)
+//   aux warp   tile k-2  Gram accumulation C += v v^T of the membrane tile, and the
+//                        finished part of the spike ring -> HBM
+//   clip end             power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
+//
+// Shared memory per clip (K = 480): 17 KB audio ring (480 samples of FIR history +
+// two tiles), 3.8 KB quadrature (double buffered), 8 KB membrane (double buffered),
+// 3.5 KB spike ring, 4 KB RZCC lists; three CTAs (six clips) fit one SM.
 #include <cuda_runtime.h>
 
 #include "micloc_common.h"
 
 namespace micloc {
 
+constexpr int kTile = 64;      // samples per pipeline step
+constexpr int kSlots = 2;      // clips per CTA
+constexpr int kRows = 8;       // microphone rows per clip slot in shared memory
+constexpr int kQPitch = kTile + 4;
+constexpr int kVmPitch = 32;   // floats per time step in the membrane tile: [slot][16]
+
 struct FusedGeom {
-    int TT;        // time tile
-    int pitch_x;   // floats per mic row of the input tile
-    int pitch_q;   // floats per mic row of the quadrature tile
-    int CP;        // padded channel count of the vmem tile (multiple of 4)
-    int ring;      // spike ring length (power of two)
-    int D;         // neuron-stage lag behind the encoder
-    int NP;        // 4x4 Gram blocks (upper triangle)
-    int NS;        // time slices per Gram block
-    int off_x, off_q, off_vm, off_ring;  // smem offsets in floats
+    int ring_x;      // audio ring length in samples (multiple of 16)
+    int pitch_x;     // floats per ring row; pitch_x / 4 is odd (conflict-free LDS.128 across mics)
+    int shift;       // ring coordinate of sample t is (t + shift) mod ring_x
+    int nblk;        // FIR tap blocks of 8 (multiple of 3)
+    int lag;         // neuron lag behind the encoder (rzcc_lag(w))
+    int out_lag;     // spike write-out lag, multiple of 32, >= lag
+    int ring_s;      // spike ring slots (power of two)
+    int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
+    int off_x, off_q, off_vm, off_is, off_cand, off_ring;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
-template <typename IN_T, int STRIDE, int NB>
-__global__ void __launch_bounds__(128, 4)
-k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
-        int8_t *__restrict__ spikes, float *__restrict__ power, int32_t *__restrict__ doa,
-        int32_t *__restrict__ flags, const __grid_constant__ ChainParams p,
-        const __grid_constant__ FusedGeom g, long long B, long long T) {
-    extern __shared__ __align__(16) float smem[];
-    float *taps_s = smem;
-    float *xs = smem + g.off_x;
-    float *qs = smem + g.off_q;
-    float *vm = smem + g.off_vm;
-    int8_t *ring = reinterpret_cast<int8_t *>(smem + g.off_ring);
-    __shared__ double red_v[128];
-    __shared__ int red_i[128];
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// acc.xy += w.xy * g   (one FFMA2)
+__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long w, unsigned long long g2) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(g2));
+}
 
-    const int tid = threadIdx.x;
-    const int C2 = p.C2, M = p.M, TT = g.TT, CP = g.CP;
-    const int rmask = g.ring - 1;
-    const bool chain_thread = tid < C2;
-    const bool inphase = tid < M;
+struct Chunk { unsigned long long p[8]; };   // 16 consecutive samples as 8 float pairs
 
-    // Gram role: (block pair, time slice)
-    const bool gram_thread = tid < g.NP * g.NS;
-    int bi = 0, bj = 0;
-    const int gslice = tid / g.NP;
+__device__ __forceinline__ void load_chunk(Chunk &c, const float *row, int coord) {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(row + coord);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const ulonglong2 u = src[v];
+        c.p[2 * v] = u.x; c.p[2 * v + 1] = u.y;
+    }
+}
+
+// 8 taps x 16 outputs: acc[ip] += g[jj] * W[ip + 7 - jj], W = lo pairs 0..7 | hi pairs 0..6
+__device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Chunk &lo, const Chunk &hi,
+                                          const float *__restrict__ taps8) {
+    const float4 g0 = *reinterpret_cast<const float4 *>(taps8);
+    const float4 g1 = *reinterpret_cast<const float4 *>(taps8 + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const unsigned long long g2 = pack2(g[jj], g[jj]);
+#pragma unroll
+        for (int ip = 0; ip < 8; ++ip) {
+            const int idx = ip + 7 - jj;
+            ffma2(acc[ip], idx < 8 ? lo.p[idx] : hi.p[idx - 8], g2);
+        }
+    }
+}
+
+// All four warps meet here once per pipeline step (the roles run different code).
+__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+struct FusedSmem {
+    float *taps, *xs, *qs, *vms, *is_s;
+    int *cand;
+    int8_t *ring;
+    double *gram;
+};
+
+// ============================== STHT FIR warp (one per clip slot) ==============================
+template <int MM>
+__device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g, int slot,
+                                         bool clip_ok, int lane, int NT, int k_last) {
+    const int M = MM ? MM : p.M;
+    const int f_chunk = lane >> 3, f_mic = lane & 7;     // lane = chunk * 8 + mic
+    const bool work = clip_ok && f_mic < M;
+    const float *row = sm.xs + (slot * M + f_mic) * g.pitch_x;
+    for (int k = -1; k <= k_last; ++k) {
+        if (work && k >= 0 && k < NT) {
+            unsigned long long acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0ull;
+            // ring coordinate of the window of tap block 0 (a multiple of 16 by the choice of shift)
+            const int c0 = (k * kTile + 16 * f_chunk - p.tap_first - 14 + g.shift + 2 * g.ring_x) % g.ring_x;
+            Chunk A, Bq, Cq;
+            { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
+            load_chunk(A, row, c0);
+            int cn = c0 - 16; if (cn < 0) cn += g.ring_x;
+            const float *tp = sm.taps;
+#pragma unroll 1
+            for (int jb = 0; jb < g.nblk; jb += 3) {
+                load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                fir_block(acc, A, Bq, tp);
+                load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                fir_block(acc, Cq, A, tp + 8);
+                load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                fir_block(acc, Bq, Cq, tp + 16);
+                tp += 24;
+            }
+            float *dst = sm.qs + (((k & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                float4 o;
+                unpack2(acc[2 * v], o.x, o.y);
+                unpack2(acc[2 * v + 1], o.z, o.w);
+                reinterpret_cast<float4 *>(dst)[v] = o;
+            }
+        }
+        tile_barrier();
+    }
+}
+
+// ===================== chain warp: band-pass + RZCC + neuron, lane = slot*16 + channel =====================
+// two biquads, direct form II transposed, coefficients in registers
+struct Sos2 { float b0[2], b1[2], b2[2], a1[2], a2[2]; };
+__device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, float x) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float y = fmaf(c.b0[k], x, st.s1[k]);
+        st.s1[k] = fmaf(c.b1[k], x, fmaf(-c.a1[k], y, st.s2[k]));
+        st.s2[k] = fmaf(c.b2[k], x, -c.a2[k] * y);
+        x = y;
+    }
+    return x;
+}
+
+template <typename IN_T, int MM>
+__device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                           const IN_T *__restrict__ audio, int32_t *__restrict__ flags,
+                                           long long clip0, long long B, long long T64, int lane, int k_last) {
+    const int M = MM ? MM : p.M, C2 = 2 * M;
+    const int T = (int)T64;
+    const int c_slot = lane >> 4, c_ch = lane & 15;
+    const bool slot_ok = clip0 + c_slot < B;
+    const bool c_valid = c_ch < C2 && slot_ok;
+    const bool c_inphase = c_ch < M;
+    const int rmask = g.ring_s - 1;
+    const int lag = g.lag, nL = p.nL, w = p.w, bipolar = p.bipolar;
+    const RzccStore store{sm.cand + lane, reinterpret_cast<float *>(sm.cand + kCandMax * 32) + lane,
+                          sm.cand + 2 * kCandMax * 32 + lane,
+                          reinterpret_cast<float *>(sm.cand + (2 * kCandMax + 2 * kClusterMax) * 32) + lane, 32};
+    int8_t *c_ring = sm.ring + (size_t)c_slot * g.ring_s * C2 + c_ch;
+    auto emit = [&](int pos, int sign) { c_ring[(pos & rmask) * C2] = (int8_t)sign; };
+    const IN_T *clip_audio = audio + (slot_ok ? clip0 + c_slot : clip0) * T64 * M;
+    Sos2 sos;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        sos.b0[k] = p.sos[k][0]; sos.b1[k] = p.sos[k][1]; sos.b2[k] = p.sos[k][2];
+        sos.a1[k] = p.sos[k][3]; sos.a2[k] = p.sos[k][4];
+    }
+
+    BiquadState bq; biquad_reset(bq);
+    RzccState rz; rzcc_reset(rz);
+    NeuronState nr; neuron_reset(nr);
+
+    for (int k = -1; k <= k_last; ++k) {
+        const int kc = k - 1;
+        const int t0 = kc * kTile;
+        if (kc >= 0 && t0 < T + lag) {
+            const bool from_is = kc < g.tiles_is;
+            if (from_is) {
+                // in-phase input of the first K/2 samples is the clip's tail (np.roll, snn_beamformer.py:325)
+                if (slot_ok) {
+                    float *dsti = sm.is_s + c_slot * kTile * M;
+                    for (int e = c_ch; e < kTile * M; e += 16) {
+                        const int t = t0 + e / M;
+                        float v = 0.f;
+                        if (t < T) {
+                            int src = (t - p.half) % T;
+                            if (src < 0) src += T;
+                            v = to_f32<IN_T>(clip_audio[(long long)src * M + (e % M)]);
+                        }
+                        dsti[e] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            float *vmo = sm.vms + (kc & 1) * kTile * kVmPitch + lane;
+            if (c_valid) {
+#pragma unroll 1
+                for (int sg = 0; sg < kTile / kSeg; ++sg) {
+                    const int ts = t0 + sg * kSeg;            // first sample of this segment
+                    // input pointer of this lane for the segment
+                    const float *xp;
+                    int stride = 1, wrap_at = kSeg;
+                    if (!c_inphase) {
+                        xp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
+                    } else if (from_is) {
+                        xp = sm.is_s + c_slot * kTile * M + sg * kSeg * M + c_ch;
+                        stride = M;
+                    } else {
+                        const int cin = (ts - p.half + g.shift) % g.ring_x;
+                        xp = sm.xs + (c_slot * M + c_ch) * g.pitch_x + cin;
+                        wrap_at = g.ring_x - cin;
+                    }
+                    // does any lane of the warp wrap inside this segment?  (warp-uniform: in-phase lanes share cin)
+                    const int cin_u = (ts - p.half + g.shift + g.ring_x) % g.ring_x;
+                    const bool fast = !from_is && ts + kSeg <= T && ts - lag - nL >= 0 && cin_u + kSeg <= g.ring_x;
+                    float *vseg = vmo + sg * kSeg * kVmPitch;
+                    if (fast) {
+                        int8_t *rclr = c_ring + (ts & rmask) * C2;              // slots of this segment's samples
+                        const int8_t *rs = c_ring + ((ts - lag) & rmask) * C2;  // final spikes, lag samples back
+                        int idx_d = (ts - lag - nL) & rmask;                    // and nL further back
+#pragma unroll 8
+                        for (int i = 0; i < kSeg; ++i) {
+                            const float z = biquad2_step(sos, bq, xp[i]);
+                            rclr[i * C2] = 0;
+                            rzcc_detect(rz, store, bipolar, ts + i, z, kPlateauMax);
+                            const float s = (float)rs[i * C2];
+                            const float sd = (float)c_ring[idx_d * C2];
+                            idx_d = (idx_d + 1) & rmask;
+                            vseg[i * kVmPitch] = neuron_step(p, nr, s, sd);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < kSeg; ++i) {
+                            const int t = ts + i;
+                            if (i == wrap_at) xp -= g.ring_x;
+                            if (t < T) {
+                                const float z = biquad2_step(sos, bq, xp[i * stride]);
+                                c_ring[(t & rmask) * C2] = 0;
+                                rzcc_detect(rz, store, bipolar, t, z, kPlateauMax);
+                            }
+                            const int u = t - lag;
+                            float v = 0.f;
+                            if (u >= 0 && u < T) {
+                                const float s = (float)c_ring[(u & rmask) * C2];
+                                const float sd = u >= nL ? (float)c_ring[((u - nL) & rmask) * C2] : 0.f;
+                                v = neuron_step(p, nr, s, sd);
+                            }
+                            vseg[i * kVmPitch] = v;
+                        }
+                    }
+                    // close what can be closed (everything once the clip's last sample went through)
+                    if (ts < T) {
+                        const bool last = ts + kSeg >= T;
+                        rzcc_segment_end(rz, store, w, last ? T - 1 : ts + kSeg - 1, last, emit);
+                    }
+                }
+            } else {
+                for (int i = 0; i < kTile; ++i) vmo[i * kVmPitch] = 0.f;
+            }
+        }
+        tile_barrier();
+    }
+    if (c_valid && rz.overflow && flags) atomicOr(flags + clip0 + c_slot, 1);
+}
+
+// ============ aux warp: audio tile k+1 -> ring, finished spikes -> HBM, Gram of membrane tile k-2 ============
+template <typename IN_T, int MM>
+__device__ __forceinline__ void aux_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                         const IN_T *__restrict__ audio, int8_t *__restrict__ spikes,
+                                         long long clip0, long long B, long long T64, int lane, int NT, int k_last) {
+    const int M = MM ? MM : p.M, C2 = 2 * M;
+    const int T = (int)T64;
+    const int rmask = g.ring_s - 1;
+    // Gram-lane geometry: lane = slot * 10 + upper-triangular 4x4 block pair
+    const int g_slot = lane / 10;
+    int g_bi = 0, g_bj = 0;
     {
-        int pr = tid % g.NP;  // enumerate upper-triangular (bi <= bj) block pairs
-        for (int r = 0; r < NB; ++r) {
-            const int len = NB - r;
-            if (pr < len) { bi = r; bj = r + pr; break; }
+        int pr = lane % 10;
+        for (int r = 0; r < 4; ++r) {
+            const int len = 4 - r;
+            if (pr < len) { g_bi = r; g_bj = r + pr; break; }
             pr -= len;
         }
     }
-
-    for (int i = tid; i < p.n_taps; i += blockDim.x) taps_s[i] = taps[i];
-
-    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-        const IN_T *clip = audio + b * T * M;
-        int8_t *spk_out = spikes ? spikes + b * T * C2 : nullptr;
-
-        // ---- per-clip state ----
-        BiquadState bq; biquad_reset(bq);
-        RzccState rz; rzcc_reset(rz);
-        NeuronState nr; neuron_reset(nr);
-        double acc64[16];
+    const bool g_lane = lane < 10 * kSlots;
+    double acc64[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc64[k] = 0.0;
-        for (int i = tid; i < g.ring * C2; i += blockDim.x) ring[i] = 0;
-        for (int i = tid; i < TT * CP; i += blockDim.x) vm[i] = 0.f;
-        long long src = ((-(long long)p.half) % T + T) % T;  // wrapped source index of the in-phase branch
-        __syncthreads();
+    for (int i = 0; i < 16; ++i) acc64[i] = 0.0;
 
-        auto emit = [&](int pos, int sign) { ring[(pos & rmask) * C2 + tid] = (int8_t)sign; };
-
-        for (long long t0 = 0; t0 < T + g.D; t0 += TT) {
-            // ---- phase 1+2: tile fill and STHT FIR ----
-            if (t0 < T) {
-                fir_fill_rows<IN_T>(xs, g.pitch_x, clip, T, M, 0, M, t0, p.span, TT + p.span + 8);
-                __syncthreads();
-                const int chunks = TT / kFirR;
-                for (int item = tid; item < M * chunks; item += blockDim.x) {
-                    const int mm = item / chunks, chunk = item % chunks;
-                    float acc[kFirR];
-                    fir_accumulate<STRIDE>(xs + mm * g.pitch_x, taps_s, p.n_taps, p.span, p.tap_first, chunk, acc);
-                    float *dst = qs + mm * g.pitch_q + fir_pad(chunk * kFirR);
+    for (int k = -1; k <= k_last; ++k) {
+        // (a) audio tile k+1 -> mic-major ring: every lane moves whole frames (all microphones of one
+        //     sample); the loads of a tile are all issued before the first store
+        const int kf = k + 1;
+        if (kf < NT) {
+            constexpr int NF = kSlots * (kTile / 32);
+            float v[NF][kRows];
+            int coord[NF];
 #pragma unroll
-                    for (int v = 0; v < kFirR / 4; ++v)
-                        *reinterpret_cast<float4 *>(dst + 4 * v) =
-                            make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
-                }
+            for (int f = 0; f < NF; ++f) {
+                const int s = f / (kTile / 32), h = f % (kTile / 32);
+                const int t = kf * kTile + h * 32 + lane;
+                coord[f] = (t + g.shift) % g.ring_x;
+                const bool ok = t < T && clip0 + s < B;
+                const IN_T *fr = audio + ((clip0 + (ok ? s : 0)) * T64 + (ok ? t : 0)) * M;
+#pragma unroll
+                for (int m = 0; m < kRows; ++m) v[f][m] = (ok && m < M) ? to_f32<IN_T>(fr[m]) : 0.f;
             }
-            __syncthreads();
-
-            // ---- phase 3: per-channel sequential chain ----
-            if (chain_thread) {
-                const float *xrow = inphase ? xs + tid * g.pitch_x : qs + (tid - M) * g.pitch_q;
-                for (int i = 0; i < TT; ++i) {
-                    const long long t = t0 + i;
-                    if (t < T) {
-                        float x;
-                        if (inphase) {
-                            if (t < p.half || p.span < p.half) x = to_f32<IN_T>(clip[src * M + tid]);
-                            else x = xrow[fir_pad(p.span + i - p.half)];
-                            if (++src == T) src = 0;
-                        } else {
-                            x = xrow[fir_pad(i)];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const int s = f / (kTile / 32);
+                float *rows = sm.xs + s * M * g.pitch_x + coord[f];
+#pragma unroll
+                for (int m = 0; m < kRows; ++m)
+                    if (m < M) rows[m * g.pitch_x] = v[f][m];
+            }
+        }
+        // (b) finished spikes -> HBM: times [64(k-1) - out_lag - 64, 64(k-1) - out_lag)
+        if (spikes) {
+            const int u0 = (k - 1) * kTile - g.out_lag - kTile;
+            const int rowb = C2;   // bytes per time step
+            for (int s = 0; s < kSlots; ++s) {
+                const long long clip = clip0 + s;
+                if (clip >= B || u0 + kTile <= 0 || u0 >= T) continue;
+                const int8_t *rg = sm.ring + (size_t)s * g.ring_s * C2;
+                int8_t *out = spikes + clip * T64 * C2;
+                for (int h = 0; h < kTile / 32; ++h) {
+                    const int ua = u0 + 32 * h;        // 32 time steps: contiguous in the ring and in HBM
+                    if (ua + 32 <= 0 || ua >= T) continue;
+                    const int8_t *srow = rg + (ua & rmask) * rowb;
+                    int8_t *drow = out + (long long)ua * rowb;
+                    const bool full = ua >= 0 && ua + 32 <= T && ((32 * rowb) % 16 == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(drow) & 15) == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(srow) & 15) == 0);
+                    if (full) {
+                        const int nv = 32 * rowb / 16;
+                        for (int v = lane; v < nv; v += 32)
+                            reinterpret_cast<int4 *>(drow)[v] = reinterpret_cast<const int4 *>(srow)[v];
+                    } else {
+                        for (int e = lane; e < 32 * rowb; e += 32) {
+                            const int u = ua + e / rowb;
+                            if (u >= 0 && u < T) drow[e] = srow[e];
                         }
-                        const float z = biquad_step(p.sos, p.nsec, bq, x);
-                        ring[((int)t & rmask) * C2 + tid] = 0;
-                        rzcc_step(rz, p.w, p.bipolar, (int)t, z, emit);
-                    } else if (t == T) {
-                        rzcc_finish(rz, p.w, p.bipolar, emit);
                     }
-                    const long long u = t - g.D;
-                    float v = 0.f;
-                    if (u >= 0 && u < T) {
-                        const float s = (float)ring[((int)u & rmask) * C2 + tid];
-                        const float sd = u >= p.nL ? (float)ring[((int)(u - p.nL) & rmask) * C2 + tid] : 0.f;
-                        v = neuron_step(p, nr, s, sd);
-                    }
-                    vm[i * CP + tid] = v;
                 }
             }
-            __syncthreads();
+        }
+        // (c) Gram of the membrane tile the chain warp wrote one step ago (its tile k-2)
+        const int kg = k - 2;
+        if (g_lane && kg >= 0 && kg * kTile < T + g.lag) {
+            const float *vm = sm.vms + (kg & 1) * kTile * kVmPitch + g_slot * 16;
+            unsigned long long a2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a2[i] = 0ull;
+#pragma unroll 4
+            for (int i = 0; i < kTile; ++i) {
+                const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
+                const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(vm + i * kVmPitch + 4 * g_bj);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned long long ar = pack2(av[r], av[r]);
+                    ffma2(a2[2 * r], c.x, ar);
+                    ffma2(a2[2 * r + 1], c.y, ar);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float lo, hi;
+                unpack2(a2[i], lo, hi);
+                acc64[2 * i] += (double)lo;
+                acc64[2 * i + 1] += (double)hi;
+            }
+        }
+        tile_barrier();
+    }
+    // hand the Gram matrices to the epilogue (they reuse the audio rings, dead by now)
+    if (g_lane) {
+        double *Cd = sm.gram + g_slot * 256;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int row = 4 * g_bi + k / 4, col = 4 * g_bj + k % 4;
+            Cd[row * 16 + col] = acc64[k];
+            if (g_bi != g_bj) Cd[col * 16 + row] = acc64[k];
+        }
+    }
+}
 
-            // ---- phase 4: Gram accumulation over the tile + spike write-out ----
-            if (gram_thread) {
-                float acc[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-                for (int i = gslice; i < TT; i += g.NS) {
-                    const float4 a = *reinterpret_cast<const float4 *>(vm + i * CP + 4 * bi);
-                    const float4 c = *reinterpret_cast<const float4 *>(vm + i * CP + 4 * bj);
-                    const float av[4] = {a.x, a.y, a.z, a.w};
-                    const float cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) acc[4 * r + s] = fmaf(av[r], cv[s], acc[4 * r + s]);
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) acc64[k] += (double)acc[k];
-            }
-            if (spk_out) {
-                const long long u0 = t0 - g.D;
-                for (int r = tid; r < TT; r += blockDim.x) {
-                    const long long u = u0 + r;
-                    if (u >= 0 && u < T) {
-                        const int8_t *srow = ring + ((int)u & rmask) * C2;
-                        int8_t *drow = spk_out + u * C2;
-                        for (int c = 0; c < C2; ++c) drow[c] = srow[c];
-                    }
-                }
-            }
-            // the next tile's fill/FIR touch xs/qs only; vm and ring are rewritten after two barriers
+template <typename IN_T, int MM>
+__global__ void __launch_bounds__(128, 3)
+k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
+        int8_t *__restrict__ spikes, float *__restrict__ power, int32_t *__restrict__ doa,
+        int32_t *__restrict__ flags, unsigned int *__restrict__ sm_slots,
+        const __grid_constant__ ChainParams p, const __grid_constant__ FusedGeom g, long long B, long long T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem sm;
+    sm.taps = reinterpret_cast<float *>(smem_raw);
+    sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
+    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2][kSlots*M][kQPitch]
+    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [2][kTile][kVmPitch]
+    sm.is_s = reinterpret_cast<float *>(smem_raw + g.off_is);    // [kSlots][kTile][M]
+    sm.cand = reinterpret_cast<int *>(smem_raw + g.off_cand);    // RZCC lists, interleaved over 32 lanes
+    sm.ring = reinterpret_cast<int8_t *>(smem_raw + g.off_ring); // [kSlots][ring_s][C2]
+    sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
+    double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
+    int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
+    __shared__ unsigned int s_rot;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = MM ? MM : p.M, C2 = 2 * M;
+
+    // Warp w of a CTA lands on SM sub-partition w % 4; rotate the roles per co-resident
+    // CTA so that every sub-partition gets its share of FIR warps.
+    if (tid == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned int k = atomicAdd(sm_slots + (smid & 255u), 1u) & 3u;
+        s_rot = (0x3120u >> (4 * k)) & 3u;   // 0, 2, 1, 3
+    }
+    for (int i = tid; i < 8 * g.nblk; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
+    __syncthreads();
+    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR of clip slot 0 / 1; 2: chain; 3: aux
+
+    const int NT = (int)((T + kTile - 1) / kTile);
+    const int k_last = (int)((T + g.out_lag + kTile - 1) / kTile) + 2;
+    const long long npairs = (B + kSlots - 1) / kSlots;
+
+    for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const long long clip0 = pair * kSlots;
+        {   // zero the audio rings: samples before the clip start are zeros (lfilter's zero state)
+            float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
+            const int n4 = kSlots * M * g.pitch_x / 4;
+            for (int i = tid; i < n4; i += blockDim.x) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
 
-        // ---- clip epilogue: reduce Gram partials (fixed order), power, argmax ----
-        double *part = reinterpret_cast<double *>(xs);            // [NP*NS][16]
-        double *Cd = part + g.NP * g.NS * 16;                     // [CP][CP]
-        if (gram_thread) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) part[tid * 16 + k] = acc64[k];
-        }
+        if (role < 2) fir_role<MM>(sm, p, g, role, clip0 + role < B, lane, NT, k_last);
+        else if (role == 2) chain_role<IN_T, MM>(sm, p, g, audio, flags, clip0, B, T, lane, k_last);
+        else aux_role<IN_T, MM>(sm, p, g, audio, spikes, clip0, B, T, lane, NT, k_last);
         __syncthreads();
-        for (int e = tid; e < g.NP * 16; e += blockDim.x) {
-            const int pr = e / 16, k = e % 16;
-            double s = 0.0;
-            for (int sl = 0; sl < g.NS; ++sl) s += part[(sl * g.NP + pr) * 16 + k];
-            int r = 0, rem = pr, pbi = 0, pbj = 0;
-            for (r = 0; r < NB; ++r) {
-                const int len = NB - r;
-                if (rem < len) { pbi = r; pbj = r + rem; break; }
-                rem -= len;
-            }
-            const int row = 4 * pbi + k / 4, col = 4 * pbj + k % 4;
-            Cd[row * CP + col] = s;
-            if (pbi != pbj) Cd[col * CP + row] = s;
-        }
-        __syncthreads();
-        double best = -1.0; int besti = 0x7fffffff;
+
+        // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
         const double inv_T = 1.0 / (double)T;
-        for (int gg = tid; gg < p.G; gg += blockDim.x) {
-            double w[4 * NB];
-#pragma unroll
-            for (int c = 0; c < 4 * NB; ++c) w[c] = c < C2 ? Wd[(long long)c * p.G + gg] : 0.0;
-            double accp = 0.0;
-#pragma unroll
-            for (int r = 0; r < 4 * NB; ++r) {
-                double rr = 0.0;
-#pragma unroll
-                for (int c = 0; c < 4 * NB; ++c) rr = fma(Cd[r * CP + c], w[c], rr);
-                accp = fma(w[r], rr, accp);
+        for (int s = 0; s < kSlots; ++s) {
+            const long long clip = clip0 + s;
+            if (clip >= B) break;
+            const double *Cd = sm.gram + s * 256;
+            double best = -1.0; int besti = 0x7fffffff;
+            for (int gg = tid; gg < p.G; gg += blockDim.x) {
+                double accp = 0.0;
+                for (int r = 0; r < C2; ++r) {
+                    double rr = 0.0;
+                    for (int c = 0; c < C2; ++c) rr = fma(Cd[r * 16 + c], Wd[(long long)c * p.G + gg], rr);
+                    accp = fma(Wd[(long long)r * p.G + gg], rr, accp);
+                }
+                accp *= inv_T;
+                if (power) power[clip * p.G + gg] = (float)accp;
+                if (accp > best) { best = accp; besti = gg; }
             }
-            accp *= inv_T;
-            if (power) power[b * p.G + gg] = (float)accp;
-            if (accp > best) { best = accp; besti = gg; }
-        }
-        red_v[tid] = best; red_i[tid] = besti;
-        __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if (tid < s) {
-                const double ov = red_v[tid + s]; const int oi = red_i[tid + s];
-                if (ov > red_v[tid] || (ov == red_v[tid] && oi < red_i[tid])) { red_v[tid] = ov; red_i[tid] = oi; }
+            red_v[tid] = best; red_i[tid] = besti;
+            __syncthreads();
+            for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+                if (tid < st) {
+                    const double ov = red_v[tid + st]; const int oi = red_i[tid + st];
+                    if (ov > red_v[tid] || (ov == red_v[tid] && oi < red_i[tid])) { red_v[tid] = ov; red_i[tid] = oi; }
+                }
+                __syncthreads();
             }
+            if (tid == 0 && doa) doa[clip] = red_i[0];
             __syncthreads();
         }
-        if (tid == 0 && doa) doa[b] = red_i[0];
-        if (chain_thread && rz.overflow && flags) atomicOr(flags + b, 1);
-        __syncthreads();
     }
 }
 
 static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <typename IN_T, int STRIDE, int NB>
+bool fused_supported(const ChainParams &p) {
+    return p.tap_stride == 2 && p.M <= kRows && p.nsec == 2 && (p.n_taps % 8) == 0;
+}
+
+template <typename IN_T, int MM>
 static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float *d_taps, const double *d_Wd,
                           const IN_T *audio, long long B, long long T, int8_t *spikes, float *power, int32_t *doa,
-                          int32_t *flags, int sm_count, cudaStream_t st) {
-    auto kern = k_fused<IN_T, STRIDE, NB>;
+                          int32_t *flags, unsigned int *sm_slots, int sm_count, cudaStream_t st) {
+    auto kern = k_fused<IN_T, MM>;
     MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
     int per_sm = 1;
     MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, g.smem_bytes));
     if (per_sm < 1) return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel does not fit (smem %d B)", g.smem_bytes);
     long long grid = (long long)sm_count * per_sm;
-    if (grid > B) grid = B;
-    kern<<<(unsigned)grid, 128, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, p, g, B, T);
+    const long long npairs = (B + kSlots - 1) / kSlots;
+    if (grid > npairs) grid = npairs;
+    kern<<<(unsigned)grid, 128, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
     count_launch(1);
     MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
@@ -249,44 +513,42 @@ static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float 
 
 int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
-                 int sm_count, cudaStream_t st) {
-    if (p.C2 > 32)
-        return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel supports up to 16 microphones (got %d); use the staged path", p.M);
+                 unsigned int *sm_slots, int sm_count, cudaStream_t st) {
+    if (!fused_supported(p))
+        return set_error(MICLOC_ERR_UNSUPPORTED,
+                         "fused kernel covers Hilbert-type STHT kernels (every other tap zero), a 2-section band-pass "
+                         "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
-    g.TT = 256;
-    g.D = ((kClusterMax * p.w + 7) / 8) * 8;
-    g.ring = next_pow2(g.TT + g.D + p.nL + 8);
-    g.pitch_x = fir_row_pitch(g.TT, p.span);
-    g.pitch_q = (fir_pad(g.TT) + 4 + 3) & ~3;
-    const int NB = p.C2 <= 16 ? 4 : 8;
-    g.CP = 4 * NB;
-    g.NP = NB * (NB + 1) / 2;
-    g.NS = 128 / g.NP;
-    int off = (p.n_taps + 3) & ~3;
-    g.off_x = off;
-    int x_floats = p.M * g.pitch_x;
-    const int epi_floats = (g.NP * g.NS * 16 + g.CP * g.CP) * 2;  // doubles reuse the xs region at clip end
-    if (x_floats < epi_floats) x_floats = epi_floats;
-    off += (x_floats + 3) & ~3;
-    g.off_q = off; off += p.M * g.pitch_q;
-    g.off_vm = off; off += g.TT * g.CP;
-    g.off_ring = off; off += (g.ring * p.C2 + 3) / 4;
-    g.smem_bytes = off * (int)sizeof(float);
+    // FIR tap blocks: groups of three blocks of 8 (zero taps appended by setup_stht up to a multiple of 8)
+    g.nblk = (p.n_taps / 8 + 2) / 3 * 3;
+    const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
+    g.ring_x = ((lookback + 2 * kTile) + 31) / 32 * 32;             // history + current tile + tile being filled
+    g.pitch_x = g.ring_x + 4;
+    g.shift = ((p.tap_first + 14) % 16 + 16) % 16;
+    g.lag = rzcc_lag(p.w);
+    g.out_lag = (g.lag + 31) / 32 * 32;
+    g.ring_s = next_pow2(g.out_lag + 2 * kTile > g.lag + p.nL + 1 ? g.out_lag + 2 * kTile : g.lag + p.nL + 1);
+    g.tiles_is = (p.half + kTile - 1) / kTile;
+    int off = (8 * g.nblk * (int)sizeof(float) + 15) & ~15;
+    g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
+    g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
+    g.off_vm = off; off += 2 * kTile * kVmPitch * (int)sizeof(float);
+    g.off_is = off; off += kSlots * kTile * p.M * (int)sizeof(float);
+    g.off_cand = off; off += (2 * kCandMax + 4 * kClusterMax) * 32 * (int)sizeof(int);
+    g.off_ring = off; off += (kSlots * g.ring_s * p.C2 + 15) & ~15;
+    g.smem_bytes = off;
+    if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
+        128 * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
+        return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);
-    if (T + g.D >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
-
-#define MICLOC_FUSED_CASE(IN, S, N)                                                                          \
-    return launch_fused_t<IN, S, N>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa, flags, \
-                                    sm_count, st)
+    if (T + g.lag + 8 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
+#define MICLOC_FUSED_CASE(IN, MMV)                                                                        \
+    return launch_fused_t<IN, MMV>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa, flags, \
+                                   sm_slots, sm_count, st)
     const bool i16 = dtype == MICLOC_I16;
-    if (p.tap_stride == 2) {
-        if (NB == 4) { if (i16) MICLOC_FUSED_CASE(int16_t, 2, 4); else MICLOC_FUSED_CASE(float, 2, 4); }
-        else         { if (i16) MICLOC_FUSED_CASE(int16_t, 2, 8); else MICLOC_FUSED_CASE(float, 2, 8); }
-    } else {
-        if (NB == 4) { if (i16) MICLOC_FUSED_CASE(int16_t, 1, 4); else MICLOC_FUSED_CASE(float, 1, 4); }
-        else         { if (i16) MICLOC_FUSED_CASE(int16_t, 1, 8); else MICLOC_FUSED_CASE(float, 1, 8); }
-    }
+    if (p.M == 7) { if (i16) MICLOC_FUSED_CASE(int16_t, 7); else MICLOC_FUSED_CASE(float, 7); }
+    if (i16) MICLOC_FUSED_CASE(int16_t, 0); else MICLOC_FUSED_CASE(float, 0);
 #undef MICLOC_FUSED_CASE
 }
 

@@ -55,8 +55,8 @@ def test_staged_taps_match_reference_golden(name):
 def test_fused_matches_reference_golden(name):
     g = H.load(name)
     eng = engine_for(g)
-    if eng.M > 16:
-        pytest.skip("fused kernel covers up to 16 microphones")
+    if eng.M > 8:
+        pytest.skip("fused kernel covers up to 8 microphones; larger arrays take the staged path")
     out = eng.run(to_dev(g["x"]), want_spikes=True, fused=True)
     torch.cuda.synchronize()
     spikes = out["spikes"][0].cpu().numpy()
