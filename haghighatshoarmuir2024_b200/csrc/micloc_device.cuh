@@ -13,7 +13,7 @@
 namespace micloc {
 
 constexpr int kMaxSections = 4;   // biquads per band-pass
-constexpr int kClusterMax = 6;    // RZCC candidates buffered per open cluster
+constexpr int kClusterMax = 8;    // RZCC candidates buffered per open cluster
 constexpr int kFirR = 16;         // consecutive outputs per thread in the FIR
 constexpr int kFirJB = 8;         // taps per register block
 
@@ -140,32 +140,33 @@ __device__ __forceinline__ float biquad_step(const float (&sos)[kMaxSections][5]
 // RZCC: streaming find_peaks(cumsum(z), distance=w) for one channel
 // (micloc/spike_encoder.py:115-137 + scipy _local_maxima_1d / _select_by_peak_distance).
 //
-// Detection (every sample): a peak of the cumulative sum sits where z goes
-// + -> (zeros) -> -, at the midpoint of the flat top; a valley (peak of -cumsum,
-// spike_encoder.py:131-135) where z goes - -> (zeros) -> +.  First and last sample
-// are never peaks.  The height of a candidate is the cumulative sum on the flat
-// top, i.e. the running sum BEFORE the sample that ends it.  Heights are only
-// ever compared inside one cluster (< kClusterMax*w samples), and the cumulative
-// sum of a band-passed signal stays bounded, so a float32 running sum orders
-// them as the reference's float64 one does.
-// Candidates of a segment of kSeg samples are appended to a small list.
+// Candidates: a peak of the cumulative sum sits where z goes + -> (zeros) -> -, at
+// the midpoint of the flat top; a valley (peak of -cumsum, spike_encoder.py:131-135)
+// where z goes - -> (zeros) -> +.  First and last sample are never peaks.  The
+// height of a candidate is the cumulative sum on the flat top, i.e. the running sum
+// BEFORE the sample that ends it.  Heights are only ever compared inside one cluster
+// (< kClusterMax*w samples) and the cumulative sum of a band-passed signal stays
+// bounded, so a float32 running sum orders them as the reference's float64 one does.
 //
-// Resolution (every kSeg samples): candidates of one polarity closer than w
-// samples form a cluster; a cluster is closed once w samples pass without a new
-// candidate and is then resolved by scipy's greedy rule (highest first, it removes
-// every candidate nearer than w; ties -> later position).  A list or cluster that
-// overflows sets `overflow` (the clip is flagged; micloc_rzcc_encode_f64 is the
-// unbounded encoder).
+// Clusters: candidates of one polarity closer than w samples form a cluster; it is
+// closed once w samples pass without a new candidate (checked every kSeg samples)
+// and is then resolved by scipy's greedy rule (highest first, it removes every
+// candidate nearer than w; ties -> later position).  A cluster that overflows, or a
+// flat top of more than kPlateauMax exact zeros, sets `overflow` (the clip is
+// flagged; micloc_rzcc_encode_f64 is the unbounded encoder).
+//
+// Two front ends feed the same cluster logic and give identical spikes:
+//   rzcc_detect         one sample at a time (staged kernel)
+//   rzcc_segment_masks  kSeg samples at once from sign / zero bit masks and the
+//                       per-sample running sums (fused kernel)
 // ---------------------------------------------------------------------------
-constexpr int kSeg = 32;          // samples between two cluster resolutions
-constexpr int kCandMax = 8;       // candidates buffered per segment and channel
+constexpr int kSeg = 32;          // samples between two cluster close checks
 constexpr int kPlateauMax = 16;   // longest run of exact zeros inside a flat top the streaming encoder follows
 
 struct RzccState {
     float csum;               // running cumulative sum
     int r;                    // index of the last non-zero sample (-1: none yet)
     int sgn;                  // 1 when that sample was positive
-    int ncand;                // candidates waiting in the segment list
     int n0, n1;               // open cluster sizes: valleys, peaks
     int last0, last1;         // position of the newest candidate of each open cluster
     int overflow;
@@ -176,44 +177,18 @@ struct RzccState {
 };
 
 __device__ __forceinline__ void rzcc_reset(RzccState &s) {
-    s.csum = 0.f; s.r = -1; s.sgn = 0; s.ncand = 0;
+    s.csum = 0.f; s.r = -1; s.sgn = 0;
     s.n0 = s.n1 = 0; s.last0 = s.last1 = 0; s.overflow = 0;
 }
 
-// Storage of one channel's candidate list and cluster buffers.  `stride` is the
-// distance between consecutive entries (1 for a private array, 32 for arrays
-// interleaved across the lanes of a warp in shared memory).
+// Cluster buffers of one channel.  `stride` is the distance between consecutive
+// entries (1 for a private array, 32 for arrays interleaved across the lanes of a
+// warp in shared memory).
 struct RzccStore {
-    int *cand_pos;            // [kCandMax]   (pos << 1) | is_peak
-    float *cand_h;            // [kCandMax]   height, sign-adjusted so that higher wins
     int *cl_pos;              // [2][kClusterMax]
-    float *cl_h;              // [2][kClusterMax]
+    float *cl_h;              // [2][kClusterMax]  height, sign-adjusted so that higher wins
     int stride;
 };
-
-// one sample: update the running sum, detect a candidate that this sample confirms
-__device__ __forceinline__ void rzcc_detect(RzccState &s, const RzccStore &st, int bipolar, int t, float z,
-                                            int max_plateau) {
-    const float cprev = s.csum;
-    s.csum = cprev + z;
-    const bool nz = z != 0.f;
-    const bool pos = z > 0.f;
-    const bool ev = nz && (s.r >= 1) && (pos != (s.sgn != 0)) && (bipolar || s.sgn);
-    if (ev) {
-        // a flat top of exact zeros longer than max_plateau puts the spike further back than the
-        // fused kernel's ring reaches (digital silence inside a clip): flag the clip instead
-        if (t - 1 - s.r > max_plateau) {
-            s.overflow = 1;
-        } else if (s.ncand < kCandMax) {
-            st.cand_pos[s.ncand * st.stride] = (((s.r + t - 1) >> 1) << 1) | s.sgn;
-            st.cand_h[s.ncand * st.stride] = s.sgn ? cprev : -cprev;
-            ++s.ncand;
-        } else {
-            s.overflow = 1;
-        }
-    }
-    if (nz) { s.r = t; s.sgn = pos ? 1 : 0; }
-}
 
 template <typename Emit>
 __device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, int pol, int w, Emit &&emit) {
@@ -241,34 +216,87 @@ __device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, 
     }
 }
 
-// end of a segment whose last processed sample is t_end: feed the buffered
-// candidates to the clusters, close what can be closed (everything when `final`).
-// emit(pos, sign) is called for every final spike; pos > t_end - (kClusterMax-1)*(w-1) - w - kSeg.
+// a new candidate (candidates arrive in time order): pol 1 = peak, 0 = valley
 template <typename Emit>
-__device__ __forceinline__ void rzcc_segment_end(RzccState &s, const RzccStore &st, int w, int t_end, bool final,
-                                                 Emit &&emit) {
-    for (int e = 0; e < s.ncand; ++e) {
-        const int pp = st.cand_pos[e * st.stride];
-        const float h = st.cand_h[e * st.stride];
-        const int pol = pp & 1, pos = pp >> 1;
-        if (s.n(pol) > 0 && pos - s.last(pol) >= w) rzcc_resolve(s, st, pol, w, emit);
-        const int n = s.n(pol);
-        if (n == kClusterMax) { s.overflow = 1; continue; }
-        st.cl_pos[(pol * kClusterMax + n) * st.stride] = pos;
-        st.cl_h[(pol * kClusterMax + n) * st.stride] = h;
-        s.set_last(pol, pos);
-        s.set_n(pol, n + 1);
-    }
-    s.ncand = 0;
+__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int pol, int pos, float h, int w,
+                                          Emit &&emit) {
+    if (s.n(pol) > 0 && pos - s.last(pol) >= w) rzcc_resolve(s, st, pol, w, emit);
+    const int n = s.n(pol);
+    if (n == kClusterMax) { s.overflow = 1; return; }
+    st.cl_pos[(pol * kClusterMax + n) * st.stride] = pos;
+    st.cl_h[(pol * kClusterMax + n) * st.stride] = h;
+    s.set_last(pol, pos);
+    s.set_n(pol, n + 1);
+}
+
+// every kSeg samples (t_end = last sample seen): close the clusters that can no longer
+// grow; everything when `final`.  A spike at position p is emitted at the latest by the
+// close check at t_end >= p + kPlateauMax/2 + (kClusterMax-1)*(w-1) + w + kSeg - 1.
+template <typename Emit>
+__device__ __forceinline__ void rzcc_close(RzccState &s, const RzccStore &st, int w, int t_end, bool final,
+                                           Emit &&emit) {
+#pragma unroll
     for (int pol = 0; pol < 2; ++pol)
         if (s.n(pol) > 0 && (final || t_end - s.last(pol) >= w)) rzcc_resolve(s, st, pol, w, emit);
 }
 
-// lag after which the spike raster is final: a spike at position p is decided at the
-// latest by the segment end t_end >= p + kPlateauMax/2 + (kClusterMax-1)*(w-1) + w + kSeg - 1.
-__host__ __device__ inline int rzcc_lag(int w) {
-    return (((kClusterMax - 1) * (w - 1) + w + kSeg + kPlateauMax / 2) + kSeg - 1) / kSeg * kSeg;
+// candidate test for sample t with value class (nz, positive) and the running sum before it
+template <typename Emit>
+__device__ __forceinline__ void rzcc_sample(RzccState &s, const RzccStore &st, int bipolar, int w, int t, bool nz,
+                                            bool positive, float cprev, Emit &&emit) {
+    const bool ev = nz && (s.r >= 1) && (positive != (s.sgn != 0)) && (bipolar || s.sgn);
+    if (ev) {
+        if (t - 1 - s.r > kPlateauMax) s.overflow = 1;
+        else rzcc_push(s, st, s.sgn, (s.r + t - 1) >> 1, s.sgn ? cprev : -cprev, w, emit);
+    }
+    if (nz) { s.r = t; s.sgn = positive ? 1 : 0; }
 }
+
+// one sample at a time
+template <typename Emit>
+__device__ __forceinline__ void rzcc_detect(RzccState &s, const RzccStore &st, int bipolar, int w, int t, float z,
+                                            Emit &&emit) {
+    const float cprev = s.csum;
+    s.csum = cprev + z;
+    rzcc_sample(s, st, bipolar, w, t, z != 0.f, z > 0.f, cprev, emit);
+}
+
+// kSeg samples ts .. ts+nvalid-1 at once.  Bit (31-i) of `neg` / `zero` says that sample ts+i is
+// negative (IEEE sign bit) / exactly zero; cs[i*cs_stride] is the running sum after sample ts+i and
+// `carry` the running sum before sample ts.
+template <typename Emit>
+__device__ __forceinline__ void rzcc_segment_masks(RzccState &s, const RzccStore &st, int bipolar, int w, int ts,
+                                                   int nvalid, unsigned neg, unsigned zero, const float *cs,
+                                                   int cs_stride, float carry, Emit &&emit) {
+    if (zero == 0u && nvalid == kSeg && s.r == ts - 1) {
+        // no exact zeros and no open flat top: a candidate sits right before every sign change
+        const unsigned prev = (neg >> 1) | (s.sgn ? 0u : 0x80000000u);
+        unsigned d = neg ^ prev;
+        if (ts == 0) d &= 0x7fffffffu;          // the first sample has no predecessor
+        if (!bipolar) d &= neg;                 // peaks only: + -> -
+        while (d) {
+            const int i = __clz(d);
+            d &= ~(0x80000000u >> i);
+            const int pos = ts + i - 1;
+            if (pos >= 1) {
+                const int peak = (neg >> (31 - i)) & 1u;      // the run before the change was positive
+                const float hc = i ? cs[(i - 1) * cs_stride] : carry;
+                rzcc_push(s, st, peak, pos, peak ? hc : -hc, w, emit);
+            }
+        }
+        s.r = ts + kSeg - 1;
+        s.sgn = (neg & 1u) ? 0 : 1;
+    } else {
+        for (int i = 0; i < nvalid; ++i) {
+            const bool nz = !((zero >> (31 - i)) & 1u);
+            const bool positive = nz && !((neg >> (31 - i)) & 1u);
+            rzcc_sample(s, st, bipolar, w, ts + i, nz, positive, i ? cs[(i - 1) * cs_stride] : carry, emit);
+        }
+    }
+}
+
+// number of samples after which the spike raster is final (see rzcc_close)
+__host__ __device__ inline int rzcc_lag(int w) { return (kClusterMax - 1) * (w - 1) + w + kSeg + kPlateauMax / 2; }
 
 // ---------------------------------------------------------------------------
 // neuron (synapse + membrane) alpha kernel h[n] = c*n*a^n, n < L, as two
@@ -282,9 +310,9 @@ __device__ __forceinline__ void neuron_reset(NeuronState &n) { n.p1 = n.p2 = n.q
 // s = spike at t, sd = spike at t-L (0 before the clip starts)
 __device__ __forceinline__ float neuron_step(const ChainParams &p, NeuronState &n, float s, float sd) {
     n.p2 = p.na * (n.p2 + n.p1);
-    n.p1 = fmaf(p.na, n.p1, s);
+    n.p1 = __fadd_rn(__fmul_rn(p.na, n.p1), s);      // not fused: the fused kernel adds +-1 under a predicate
     n.q2 = p.na * (n.q2 + n.q1);
-    n.q1 = fmaf(p.na, n.q1, sd);
+    n.q1 = __fadd_rn(__fmul_rn(p.na, n.q1), sd);
     const float tail = fmaf(p.nLf, n.q1, n.q2);
     return fmaf(-p.ncT, tail, p.nc * n.p2);
 }

@@ -6,24 +6,23 @@
 //
 // One persistent CTA of four warps owns kSlots = 2 clips at a time and walks them
 // in time tiles of kTile = 64 samples.  The warps are specialised and run as a
-// software pipeline, one __syncthreads per tile:
+// software pipeline, one barrier per tile (iteration k):
 //
-//   aux warp   tile k+1  audio (HBM) -> mic-major ring in shared memory
-//   FIR warps  tile k    STHT quadrature FIR, one warp per clip: every lane owns 16
-//                        consecutive outputs of one microphone and walks the 240
-//                        non-zero Hilbert taps in blocks of 8 with a sliding register
-//                        window; the multiply-adds are packed FFMA2 (fma.rn.f32x2)
-//   chain warp tile k-1  one lane per (clip, channel): SOS band-pass, RZCC candidate
-//                        detection (+ cluster resolution every 32 samples) into a
-//                        spike ring, alpha-kernel neuron recurrences kLag samples
-//                        behind (the latency of the exact find_peaks decision)
-//   aux warp   tile k-2  Gram accumulation C += v v^T of the membrane tile, and the
-//                        finished part of the spike ring -> HBM
-//   clip end             power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
-//
-// Shared memory per clip (K = 480): 17 KB audio ring (480 samples of FIR history +
-// two tiles), 3.8 KB quadrature (double buffered), 8 KB membrane (double buffered),
-// 3.5 KB spike ring, 4 KB RZCC lists; three CTAs (six clips) fit one SM.
+//   back warp   tile k+1   audio (HBM) -> mic-major ring in shared memory
+//   FIR warps   tile k     STHT quadrature FIR, one warp per clip: every lane owns 16
+//                          consecutive outputs of one microphone and walks the 240
+//                          non-zero Hilbert taps in blocks of 8 with a sliding register
+//                          window; the multiply-adds are packed FFMA2 (fma.rn.f32x2)
+//   front warp  tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running
+//                          sum, sign / zero bit masks; every 32 samples the masks are
+//                          turned into RZCC candidates and resolved (find_peaks distance
+//                          rule) into a bit-packed spike ring
+//   back warp   tile k-4   (the latency of the exact find_peaks decision) one lane per
+//                          (clip, channel): alpha-kernel neuron recurrences driven by the
+//                          final spike bits -> membrane tile; then Gram accumulation
+//                          C += v v^T of that tile with FFMA2, and the int8 spike raster
+//                          of the tile -> HBM
+//   clip end               power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 #include <cuda_runtime.h>
 
 #include "micloc_common.h"
@@ -32,20 +31,19 @@ namespace micloc {
 
 constexpr int kTile = 64;      // samples per pipeline step
 constexpr int kSlots = 2;      // clips per CTA
-constexpr int kRows = 8;       // microphone rows per clip slot in shared memory
+constexpr int kRows = 8;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmPitch = 32;   // floats per time step in the membrane tile: [slot][16]
+constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
 
 struct FusedGeom {
-    int ring_x;      // audio ring length in samples (multiple of 16)
-    int pitch_x;     // floats per ring row; pitch_x / 4 is odd (conflict-free LDS.128 across mics)
+    int ring_x;      // audio ring length in samples (multiple of 32)
+    int pitch_x;     // floats per ring row; pitch_x / 4 is odd (conflict-free LDS.128 across microphones)
     int shift;       // ring coordinate of sample t is (t + shift) mod ring_x
     int nblk;        // FIR tap blocks of 8 (multiple of 3)
-    int lag;         // neuron lag behind the encoder (rzcc_lag(w))
-    int out_lag;     // spike write-out lag, multiple of 32, >= lag
-    int ring_s;      // spike ring slots (power of two)
+    int dtile;       // the back warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
-    int off_x, off_q, off_vm, off_is, off_cand, off_ring;   // byte offsets in dynamic smem
+    int off_x, off_q, off_vm, off_is, off_cs, off_clus, off_bits, off_stage;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
@@ -94,9 +92,10 @@ __device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Ch
 __device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 struct FusedSmem {
-    float *taps, *xs, *qs, *vms, *is_s;
-    int *cand;
-    int8_t *ring;
+    float *taps, *xs, *qs, *vms, *is_s, *cs;
+    int *clus;
+    unsigned int *bits;     // [2 polarities][kRingWords][32 lanes]
+    int8_t *stage;          // [kSlots][kTile][C2]
     double *gram;
 };
 
@@ -143,7 +142,7 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
     }
 }
 
-// ===================== chain warp: band-pass + RZCC + neuron, lane = slot*16 + channel =====================
+// ============ front warp: band-pass + RZCC -> spike bits, lane = slot*16 + channel ============
 // two biquads, direct form II transposed, coefficients in registers
 struct Sos2 { float b0[2], b1[2], b2[2], a1[2], a2[2]; };
 __device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, float x) {
@@ -158,7 +157,7 @@ __device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, fl
 }
 
 template <typename IN_T, int MM>
-__device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+__device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
                                            const IN_T *__restrict__ audio, int32_t *__restrict__ flags,
                                            long long clip0, long long B, long long T64, int lane, int k_last) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
@@ -167,29 +166,29 @@ __device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParam
     const bool slot_ok = clip0 + c_slot < B;
     const bool c_valid = c_ch < C2 && slot_ok;
     const bool c_inphase = c_ch < M;
-    const int rmask = g.ring_s - 1;
-    const int lag = g.lag, nL = p.nL, w = p.w, bipolar = p.bipolar;
-    const RzccStore store{sm.cand + lane, reinterpret_cast<float *>(sm.cand + kCandMax * 32) + lane,
-                          sm.cand + 2 * kCandMax * 32 + lane,
-                          reinterpret_cast<float *>(sm.cand + (2 * kCandMax + 2 * kClusterMax) * 32) + lane, 32};
-    int8_t *c_ring = sm.ring + (size_t)c_slot * g.ring_s * C2 + c_ch;
-    auto emit = [&](int pos, int sign) { c_ring[(pos & rmask) * C2] = (int8_t)sign; };
+    const int w = p.w, bipolar = p.bipolar;
+    const RzccStore store{sm.clus + lane, reinterpret_cast<float *>(sm.clus + 2 * kClusterMax * 32) + lane, 32};
+    unsigned int *bits = sm.bits + lane;
+    // a final spike: set its bit in this channel's ring word (only this lane ever writes these words)
+    auto emit = [&](int pos, int sign) {
+        unsigned int *wd = bits + ((sign > 0 ? kRingWords : 0) + ((pos >> 5) & (kRingWords - 1))) * 32;
+        *wd |= 1u << (pos & 31);
+    };
     const IN_T *clip_audio = audio + (slot_ok ? clip0 + c_slot : clip0) * T64 * M;
+    float *cs = sm.cs + lane;
     Sos2 sos;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         sos.b0[k] = p.sos[k][0]; sos.b1[k] = p.sos[k][1]; sos.b2[k] = p.sos[k][2];
         sos.a1[k] = p.sos[k][3]; sos.a2[k] = p.sos[k][4];
     }
-
     BiquadState bq; biquad_reset(bq);
     RzccState rz; rzcc_reset(rz);
-    NeuronState nr; neuron_reset(nr);
 
     for (int k = -1; k <= k_last; ++k) {
         const int kc = k - 1;
         const int t0 = kc * kTile;
-        if (kc >= 0 && t0 < T + lag) {
+        if (kc >= 0 && t0 < T) {
             const bool from_is = kc < g.tiles_is;
             if (from_is) {
                 // in-phase input of the first K/2 samples is the clip's tail (np.roll, snn_beamformer.py:325)
@@ -208,12 +207,11 @@ __device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParam
                 }
                 __syncwarp();
             }
-            float *vmo = sm.vms + (kc & 1) * kTile * kVmPitch + lane;
             if (c_valid) {
 #pragma unroll 1
                 for (int sg = 0; sg < kTile / kSeg; ++sg) {
                     const int ts = t0 + sg * kSeg;            // first sample of this segment
-                    // input pointer of this lane for the segment
+                    if (ts >= T) break;
                     const float *xp;
                     int stride = 1, wrap_at = kSeg;
                     if (!c_inphase) {
@@ -226,52 +224,42 @@ __device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParam
                         xp = sm.xs + (c_slot * M + c_ch) * g.pitch_x + cin;
                         wrap_at = g.ring_x - cin;
                     }
-                    // does any lane of the warp wrap inside this segment?  (warp-uniform: in-phase lanes share cin)
+                    // this segment's words of the spike-bit ring start empty
+                    bits[((ts >> 5) & (kRingWords - 1)) * 32] = 0u;
+                    bits[(kRingWords + ((ts >> 5) & (kRingWords - 1))) * 32] = 0u;
+                    // (warp-uniform) no lane wraps around the audio ring inside this segment
                     const int cin_u = (ts - p.half + g.shift + g.ring_x) % g.ring_x;
-                    const bool fast = !from_is && ts + kSeg <= T && ts - lag - nL >= 0 && cin_u + kSeg <= g.ring_x;
-                    float *vseg = vmo + sg * kSeg * kVmPitch;
+                    const bool fast = !from_is && ts + kSeg <= T && cin_u + kSeg <= g.ring_x;
+                    const float carry = rz.csum;
+                    unsigned int neg = 0u, zero = 0u;
+                    float csum = carry;
+                    int nvalid = kSeg;
                     if (fast) {
-                        int8_t *rclr = c_ring + (ts & rmask) * C2;              // slots of this segment's samples
-                        const int8_t *rs = c_ring + ((ts - lag) & rmask) * C2;  // final spikes, lag samples back
-                        int idx_d = (ts - lag - nL) & rmask;                    // and nL further back
-#pragma unroll 8
+#pragma unroll
                         for (int i = 0; i < kSeg; ++i) {
                             const float z = biquad2_step(sos, bq, xp[i]);
-                            rclr[i * C2] = 0;
-                            rzcc_detect(rz, store, bipolar, ts + i, z, kPlateauMax);
-                            const float s = (float)rs[i * C2];
-                            const float sd = (float)c_ring[idx_d * C2];
-                            idx_d = (idx_d + 1) & rmask;
-                            vseg[i * kVmPitch] = neuron_step(p, nr, s, sd);
+                            csum += z;
+                            cs[i * 32] = csum;
+                            neg = __funnelshift_l(__float_as_uint(z), neg, 1);
+                            zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
                         }
                     } else {
+                        nvalid = T - ts < kSeg ? T - ts : kSeg;
 #pragma unroll 1
-                        for (int i = 0; i < kSeg; ++i) {
-                            const int t = ts + i;
+                        for (int i = 0; i < nvalid; ++i) {
                             if (i == wrap_at) xp -= g.ring_x;
-                            if (t < T) {
-                                const float z = biquad2_step(sos, bq, xp[i * stride]);
-                                c_ring[(t & rmask) * C2] = 0;
-                                rzcc_detect(rz, store, bipolar, t, z, kPlateauMax);
-                            }
-                            const int u = t - lag;
-                            float v = 0.f;
-                            if (u >= 0 && u < T) {
-                                const float s = (float)c_ring[(u & rmask) * C2];
-                                const float sd = u >= nL ? (float)c_ring[((u - nL) & rmask) * C2] : 0.f;
-                                v = neuron_step(p, nr, s, sd);
-                            }
-                            vseg[i * kVmPitch] = v;
+                            const float z = biquad2_step(sos, bq, xp[i * stride]);
+                            csum += z;
+                            cs[i * 32] = csum;
+                            neg |= (__float_as_uint(z) >> 31) << (31 - i);
+                            zero |= (z == 0.f ? 1u : 0u) << (31 - i);
                         }
                     }
-                    // close what can be closed (everything once the clip's last sample went through)
-                    if (ts < T) {
-                        const bool last = ts + kSeg >= T;
-                        rzcc_segment_end(rz, store, w, last ? T - 1 : ts + kSeg - 1, last, emit);
-                    }
+                    rz.csum = csum;
+                    rzcc_segment_masks(rz, store, bipolar, w, ts, nvalid, neg, zero, cs, 32, carry, emit);
+                    const bool last = ts + kSeg >= T;
+                    rzcc_close(rz, store, w, last ? T - 1 : ts + kSeg - 1, last, emit);
                 }
-            } else {
-                for (int i = 0; i < kTile; ++i) vmo[i * kVmPitch] = 0.f;
             }
         }
         tile_barrier();
@@ -279,14 +267,22 @@ __device__ __forceinline__ void chain_role(const FusedSmem &sm, const ChainParam
     if (c_valid && rz.overflow && flags) atomicOr(flags + clip0 + c_slot, 1);
 }
 
-// ============ aux warp: audio tile k+1 -> ring, finished spikes -> HBM, Gram of membrane tile k-2 ============
+// ==== back warp: audio tile k+1 -> ring; neuron + Gram + spike write-out of tile k - dtile ====
 template <typename IN_T, int MM>
-__device__ __forceinline__ void aux_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                         const IN_T *__restrict__ audio, int8_t *__restrict__ spikes,
-                                         long long clip0, long long B, long long T64, int lane, int NT, int k_last) {
+__device__ __forceinline__ void back_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                          const IN_T *__restrict__ audio, int8_t *__restrict__ spikes,
+                                          long long clip0, long long B, long long T64, int lane, int NT, int k_last) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
-    const int rmask = g.ring_s - 1;
+    // neuron-lane geometry: lane = slot * 16 + channel
+    const int c_slot = lane >> 4, c_ch = lane & 15;
+    const bool c_valid = c_ch < C2 && clip0 + c_slot < B;
+    const unsigned int *bits = sm.bits + lane;
+    int8_t *stg = sm.stage + c_slot * kTile * C2 + c_ch;
+    float *vmo = sm.vms + lane;
+    const float na = p.na, nc = p.nc, ncT = p.ncT, nLf = p.nLf;
+    const int nL = p.nL;
+    NeuronState nr; neuron_reset(nr);
     // Gram-lane geometry: lane = slot * 10 + upper-triangular 4x4 block pair
     const int g_slot = lane / 10;
     int g_bi = 0, g_bj = 0;
@@ -330,62 +326,98 @@ __device__ __forceinline__ void aux_role(const FusedSmem &sm, const ChainParams 
                     if (m < M) rows[m * g.pitch_x] = v[f][m];
             }
         }
-        // (b) finished spikes -> HBM: times [64(k-1) - out_lag - 64, 64(k-1) - out_lag)
-        if (spikes) {
-            const int u0 = (k - 1) * kTile - g.out_lag - kTile;
-            const int rowb = C2;   // bytes per time step
-            for (int s = 0; s < kSlots; ++s) {
-                const long long clip = clip0 + s;
-                if (clip >= B || u0 + kTile <= 0 || u0 >= T) continue;
-                const int8_t *rg = sm.ring + (size_t)s * g.ring_s * C2;
-                int8_t *out = spikes + clip * T64 * C2;
-                for (int h = 0; h < kTile / 32; ++h) {
-                    const int ua = u0 + 32 * h;        // 32 time steps: contiguous in the ring and in HBM
-                    if (ua + 32 <= 0 || ua >= T) continue;
-                    const int8_t *srow = rg + (ua & rmask) * rowb;
-                    int8_t *drow = out + (long long)ua * rowb;
-                    const bool full = ua >= 0 && ua + 32 <= T && ((32 * rowb) % 16 == 0) &&
-                                      ((reinterpret_cast<uintptr_t>(drow) & 15) == 0) &&
-                                      ((reinterpret_cast<uintptr_t>(srow) & 15) == 0);
-                    if (full) {
-                        const int nv = 32 * rowb / 16;
-                        for (int v = lane; v < nv; v += 32)
-                            reinterpret_cast<int4 *>(drow)[v] = reinterpret_cast<const int4 *>(srow)[v];
-                    } else {
-                        for (int e = lane; e < 32 * rowb; e += 32) {
-                            const int u = ua + e / rowb;
-                            if (u >= 0 && u < T) drow[e] = srow[e];
-                        }
+        // (b) neuron filter of tile j = k - dtile from the final spike bits
+        const int j = k - g.dtile;
+        const int u0 = j * kTile;
+        if (j >= 0 && u0 < T) {
+            if (c_valid) {
+#pragma unroll 1
+                for (int sg = 0; sg < kTile / kSeg; ++sg) {
+                    const int us = u0 + sg * kSeg;
+                    const int wi = (us >> 5) & (kRingWords - 1);
+                    unsigned int P = bits[(kRingWords + wi) * 32], Nn = bits[wi * 32];
+                    if (us >= T) { P = 0u; Nn = 0u; }
+                    // the same bits nL samples earlier (funnel over two ring words; zero before the clip start)
+                    const int d0 = us - nL;
+                    const int wd = (d0 >> 5) & (kRingWords - 1), wd1 = (wd + 1) & (kRingWords - 1), sh = d0 & 31;
+                    unsigned int PD = __funnelshift_r(bits[(kRingWords + wd) * 32], bits[(kRingWords + wd1) * 32], sh);
+                    unsigned int ND = __funnelshift_r(bits[wd * 32], bits[wd1 * 32], sh);
+                    if (d0 < 0) {
+                        const unsigned int keep = d0 <= -32 ? 0u : (0xffffffffu << (-d0));
+                        PD &= keep; ND &= keep;
+                    }
+                    const int nvalid = T - us < kSeg ? (T - us > 0 ? T - us : 0) : kSeg;
+                    if (nvalid < kSeg) {
+                        const unsigned int keep = nvalid <= 0 ? 0u : (0xffffffffu >> (32 - nvalid));
+                        P &= keep; Nn &= keep; PD &= keep; ND &= keep;
+                    }
+                    float *vseg = vmo + sg * kSeg * kVmPitch;
+                    int8_t *sseg = stg + sg * kSeg * C2;
+#pragma unroll
+                    for (int i = 0; i < kSeg; ++i) {
+                        // neuron_step with s, sd in {-1, 0, +1} given as bits
+                        nr.p2 = na * (nr.p2 + nr.p1);
+                        float a1 = na * nr.p1;
+                        if (P & (1u << i)) a1 += 1.f;
+                        if (Nn & (1u << i)) a1 -= 1.f;
+                        nr.p1 = a1;
+                        nr.q2 = na * (nr.q2 + nr.q1);
+                        float b1 = na * nr.q1;
+                        if (PD & (1u << i)) b1 += 1.f;
+                        if (ND & (1u << i)) b1 -= 1.f;
+                        nr.q1 = b1;
+                        const float tail = fmaf(nLf, nr.q1, nr.q2);
+                        float v = fmaf(-ncT, tail, nc * nr.p2);
+                        if (i >= nvalid) v = 0.f;
+                        vseg[i * kVmPitch] = v;
+                        sseg[i * C2] = (int8_t)(((P >> i) & 1u) - ((Nn >> i) & 1u));
                     }
                 }
             }
-        }
-        // (c) Gram of the membrane tile the chain warp wrote one step ago (its tile k-2)
-        const int kg = k - 2;
-        if (g_lane && kg >= 0 && kg * kTile < T + g.lag) {
-            const float *vm = sm.vms + (kg & 1) * kTile * kVmPitch + g_slot * 16;
-            unsigned long long a2[8];
+            __syncwarp();
+            // (c) Gram of the membrane tile: C += v v^T, 4x4 blocks, FFMA2
+            if (g_lane) {
+                const float *vm = sm.vms + g_slot * 16;
+                unsigned long long a2[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a2[i] = 0ull;
+                for (int i = 0; i < 8; ++i) a2[i] = 0ull;
 #pragma unroll 4
-            for (int i = 0; i < kTile; ++i) {
-                const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
-                const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(vm + i * kVmPitch + 4 * g_bj);
-                const float av[4] = {a.x, a.y, a.z, a.w};
+                for (int i = 0; i < kTile; ++i) {
+                    const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
+                    const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(vm + i * kVmPitch + 4 * g_bj);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const unsigned long long ar = pack2(av[r], av[r]);
-                    ffma2(a2[2 * r], c.x, ar);
-                    ffma2(a2[2 * r + 1], c.y, ar);
+                    for (int r = 0; r < 4; ++r) {
+                        const unsigned long long ar = pack2(av[r], av[r]);
+                        ffma2(a2[2 * r], c.x, ar);
+                        ffma2(a2[2 * r + 1], c.y, ar);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float lo, hi;
+                    unpack2(a2[i], lo, hi);
+                    acc64[2 * i] += (double)lo;
+                    acc64[2 * i + 1] += (double)hi;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float lo, hi;
-                unpack2(a2[i], lo, hi);
-                acc64[2 * i] += (double)lo;
-                acc64[2 * i + 1] += (double)hi;
+            // (d) int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
+            if (spikes) {
+                const int nrow = T - u0 < kTile ? T - u0 : kTile;
+                for (int s = 0; s < kSlots; ++s) {
+                    if (clip0 + s >= B) continue;
+                    const int8_t *src = sm.stage + s * kTile * C2;
+                    int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
+                    const int nbytes = nrow * C2;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0) {
+                        for (int v = lane; v < nbytes / 16; v += 32)
+                            reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
+                    } else {
+                        for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
+                    }
+                }
             }
+            __syncwarp();
         }
         tile_barrier();
     }
@@ -412,10 +444,12 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.taps = reinterpret_cast<float *>(smem_raw);
     sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
     sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2][kSlots*M][kQPitch]
-    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [2][kTile][kVmPitch]
+    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [kTile][kVmPitch]
     sm.is_s = reinterpret_cast<float *>(smem_raw + g.off_is);    // [kSlots][kTile][M]
-    sm.cand = reinterpret_cast<int *>(smem_raw + g.off_cand);    // RZCC lists, interleaved over 32 lanes
-    sm.ring = reinterpret_cast<int8_t *>(smem_raw + g.off_ring); // [kSlots][ring_s][C2]
+    sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [kSeg][32] running sums of the open segment
+    sm.clus = reinterpret_cast<int *>(smem_raw + g.off_clus);    // RZCC cluster buffers, interleaved over 32 lanes
+    sm.bits = reinterpret_cast<unsigned int *>(smem_raw + g.off_bits);   // [2][kRingWords][32]
+    sm.stage = reinterpret_cast<int8_t *>(smem_raw + g.off_stage);       // [kSlots][kTile][C2]
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
@@ -434,10 +468,10 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     }
     for (int i = tid; i < 8 * g.nblk; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
     __syncthreads();
-    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR of clip slot 0 / 1; 2: chain; 3: aux
+    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR of clip slot 0 / 1; 2: front; 3: back
 
     const int NT = (int)((T + kTile - 1) / kTile);
-    const int k_last = (int)((T + g.out_lag + kTile - 1) / kTile) + 2;
+    const int k_last = NT - 1 + g.dtile;
     const long long npairs = (B + kSlots - 1) / kSlots;
 
     for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -446,12 +480,15 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
             const int n4 = kSlots * M * g.pitch_x / 4;
             for (int i = tid; i < n4; i += blockDim.x) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // no spikes before the clip start; membrane columns of unused lanes stay zero
+            for (int i = tid; i < 2 * kRingWords * 32; i += blockDim.x) sm.bits[i] = 0u;
+            for (int i = tid; i < kTile * kVmPitch; i += blockDim.x) sm.vms[i] = 0.f;
         }
         __syncthreads();
 
         if (role < 2) fir_role<MM>(sm, p, g, role, clip0 + role < B, lane, NT, k_last);
-        else if (role == 2) chain_role<IN_T, MM>(sm, p, g, audio, flags, clip0, B, T, lane, k_last);
-        else aux_role<IN_T, MM>(sm, p, g, audio, spikes, clip0, B, T, lane, NT, k_last);
+        else if (role == 2) front_role<IN_T, MM>(sm, p, g, audio, flags, clip0, B, T, lane, k_last);
+        else back_role<IN_T, MM>(sm, p, g, audio, spikes, clip0, B, T, lane, NT, k_last);
         __syncthreads();
 
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
@@ -525,24 +562,30 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.ring_x = ((lookback + 2 * kTile) + 31) / 32 * 32;             // history + current tile + tile being filled
     g.pitch_x = g.ring_x + 4;
     g.shift = ((p.tap_first + 14) % 16 + 16) % 16;
-    g.lag = rzcc_lag(p.w);
-    g.out_lag = (g.lag + 31) / 32 * 32;
-    g.ring_s = next_pow2(g.out_lag + 2 * kTile > g.lag + p.nL + 1 ? g.out_lag + 2 * kTile : g.lag + p.nL + 1);
+    // a spike at p is final once the front warp passed p + rzcc_lag(w) - 1; the back warp works on
+    // tile k - dtile while the front warp has completed tile k - 2
+    g.dtile = 1 + (rzcc_lag(p.w) + 63 + kTile - 1) / kTile;
     g.tiles_is = (p.half + kTile - 1) / kTile;
     int off = (8 * g.nblk * (int)sizeof(float) + 15) & ~15;
     g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
     g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
-    g.off_vm = off; off += 2 * kTile * kVmPitch * (int)sizeof(float);
+    g.off_vm = off; off += kTile * kVmPitch * (int)sizeof(float);
     g.off_is = off; off += kSlots * kTile * p.M * (int)sizeof(float);
-    g.off_cand = off; off += (2 * kCandMax + 4 * kClusterMax) * 32 * (int)sizeof(int);
-    g.off_ring = off; off += (kSlots * g.ring_s * p.C2 + 15) & ~15;
+    g.off_cs = off; off += kSeg * 32 * (int)sizeof(float);
+    g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
+    g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
+    g.off_stage = off; off += (kSlots * kTile * p.C2 + 15) & ~15;
     g.smem_bytes = off;
+    // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
+    if (kTile * (g.dtile + 1) + p.nL + kSeg > kRingWords * 32)
+        return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
+                         "use the staged path", p.w, p.nL);
     if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
         128 * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);
-    if (T + g.lag + 8 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
+    if (T + 16 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
 #define MICLOC_FUSED_CASE(IN, MMV)                                                                        \
     return launch_fused_t<IN, MMV>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa, flags, \
                                    sm_slots, sm_count, st)

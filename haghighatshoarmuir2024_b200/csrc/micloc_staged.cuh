@@ -76,9 +76,8 @@ k_chain(const IN_T *__restrict__ audio, const float *__restrict__ q, const float
 
     BiquadState bq; biquad_reset(bq);
     RzccState rz; rzcc_reset(rz);
-    int cand_pos[kCandMax]; float cand_h[kCandMax];
     int cl_pos[2 * kClusterMax]; float cl_h[2 * kClusterMax];
-    const RzccStore store{cand_pos, cand_h, cl_pos, cl_h, 1};
+    const RzccStore store{cl_pos, cl_h, 1};
     int8_t *sp = spikes + b * T * CT + cc;
     auto emit = [&](int pos, int sign) { sp[(long long)pos * CT] = (int8_t)sign; };
 
@@ -93,9 +92,9 @@ k_chain(const IN_T *__restrict__ audio, const float *__restrict__ q, const float
         const float z = biquad_step(sos, p.nsec, bq, x);
         if (z_out) z_out[(b * T + t) * CT + cc] = z;
         sp[t * CT] = 0;
-        rzcc_detect(rz, store, p.bipolar, (int)t, z, kPlateauMax);
+        rzcc_detect(rz, store, p.bipolar, p.w, (int)t, z, emit);
         const bool last = t == T - 1;
-        if (last || (t & (kSeg - 1)) == kSeg - 1) rzcc_segment_end(rz, store, p.w, (int)t, last, emit);
+        if (last || (t & (kSeg - 1)) == kSeg - 1) rzcc_close(rz, store, p.w, (int)t, last, emit);
     }
     if (rz.overflow && flags) atomicOr(flags + b, 1);
 }
