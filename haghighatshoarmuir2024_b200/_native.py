@@ -66,6 +66,8 @@ SYMBOLS = {
     "micloc_launch_count": (_i64, []),
     "micloc_snn_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "micloc_snn_enable_timing": (C.c_int, [_vp, C.c_int]),
+    "micloc_snn_debug_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "micloc_snn_debug_cta_times": (C.c_int, [_vp, C.POINTER(C.c_uint64), _i32]),
     "micloc_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 

@@ -154,8 +154,8 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
     }
     rc = upload_bf(c, cfg->bf_mat, cfg->num_doa);
     if (rc) { micloc_snn_destroy(c); return rc; }
-    if (cudaMalloc(&c->d_sm_slots, 256 * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(c->d_sm_slots, 0, 256 * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&c->d_sm_slots, (320 + 16 * 1024) * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->d_sm_slots, 0, (320 + 16 * 1024) * sizeof(unsigned int)) != cudaSuccess) {
         micloc_snn_destroy(c);
         return set_error(MICLOC_ERR_CUDA, "cudaMalloc(sm_slots) failed");
     }
@@ -183,6 +183,27 @@ extern "C" int micloc_snn_set_bf(micloc_snn *c, const double *bf, int32_t G) {
     MICLOC_CUDA(cudaSetDevice(c->device));
     MICLOC_CUDA(cudaDeviceSynchronize());
     return upload_bf(c, bf, G);
+}
+
+// Debug: busy cycles per warp role of the fused kernel (FIR slot 0, FIR slot 1, front, neuron) and
+// the number of warps that reported, summed since the previous call; all zero unless the library
+// was built with -DMICLOC_ROLE_TIMING.
+extern "C" int micloc_snn_debug_counters(micloc_snn *c, uint64_t out[16]) {
+    if (!c || !out) return set_error(MICLOC_ERR_CONFIG, "null argument");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    MICLOC_CUDA(cudaDeviceSynchronize());
+    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + 256, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    MICLOC_CUDA(cudaMemset(c->d_sm_slots + 256, 0, 16 * sizeof(uint64_t)));
+    return MICLOC_OK;
+}
+
+// Debug: (start ns, end ns, SM id, role rotation, busy cycles of the 4 roles) of the first `n` CTAs of the last fused launch (MICLOC_ROLE_TIMING builds).
+extern "C" int micloc_snn_debug_cta_times(micloc_snn *c, uint64_t *out, int32_t n) {
+    if (!c || !out || n < 1 || n > 1024) return set_error(MICLOC_ERR_CONFIG, "bad argument");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    MICLOC_CUDA(cudaDeviceSynchronize());
+    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + 320, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return MICLOC_OK;
 }
 
 extern "C" int micloc_snn_enable_timing(micloc_snn *c, int enable) {

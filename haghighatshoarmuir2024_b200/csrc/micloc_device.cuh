@@ -190,43 +190,62 @@ struct RzccStore {
     int stride;
 };
 
-template <typename Emit>
-__device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, int pol, int w, Emit &&emit) {
-    const int n = s.n(pol);
-    int *cp = st.cl_pos + pol * kClusterMax * st.stride;
-    float *ch = st.cl_h + pol * kClusterMax * st.stride;
-    const int sign = pol ? 1 : -1;
-    s.set_n(pol, 0);
-    if (n == 1) { emit(cp[0], sign); return; }
-    unsigned und = (1u << n) - 1u;
+// scipy's greedy distance rule on one closed cluster of n >= 2 candidates: returns the bit mask of
+// the candidates that stay.  Rare (band-limited signals give single-candidate clusters), so it is
+// kept out of line: the fused kernel's instruction footprint matters more than this call.
+static __device__ __noinline__ unsigned rzcc_select(const int *cp, const float *ch, int stride, int n, int w) {
+    unsigned und = (1u << n) - 1u, kept = 0u;
     while (und) {
         int best = -1; float hb = 0.f;
         for (int i = 0; i < n; ++i)
             if ((und >> i) & 1u) {
-                const float h = ch[i * st.stride];
+                const float h = ch[i * stride];
                 if (best < 0 || h >= hb) { best = i; hb = h; }
             }
-        const int pb = cp[best * st.stride];
-        emit(pb, sign);
+        const int pb = cp[best * stride];
+        kept |= 1u << best;
         for (int i = 0; i < n; ++i) {
-            int d = cp[i * st.stride] - pb;
+            int d = cp[i * stride] - pb;
             d = d < 0 ? -d : d;
             if (d < w) und &= ~(1u << i);
         }
     }
+    return kept;
 }
 
-// a new candidate (candidates arrive in time order): pol 1 = peak, 0 = valley
+// POL 1 = peaks (+1 spikes), 0 = valleys (-1 spikes); compile-time so that the cluster state stays in
+// named registers
+template <int POL, typename Emit>
+__device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, int w, Emit &&emit) {
+    const int n = POL ? s.n1 : s.n0;
+    const int *cp = st.cl_pos + POL * kClusterMax * st.stride;
+    const float *ch = st.cl_h + POL * kClusterMax * st.stride;
+    constexpr int sign = POL ? 1 : -1;
+    if (POL) s.n1 = 0; else s.n0 = 0;
+    if (n == 1) { emit(cp[0], sign); return; }
+    unsigned kept = rzcc_select(cp, ch, st.stride, n, w);
+    while (kept) {
+        const int i = __ffs(kept) - 1;
+        kept &= kept - 1;
+        emit(cp[i * st.stride], sign);
+    }
+}
+
+// a new candidate (candidates of one polarity arrive in time order)
+template <int POL, typename Emit>
+__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int pos, float h, int w, Emit &&emit) {
+    if ((POL ? s.n1 : s.n0) > 0 && pos - (POL ? s.last1 : s.last0) >= w) rzcc_resolve<POL>(s, st, w, emit);
+    const int n = POL ? s.n1 : s.n0;
+    if (n == kClusterMax) { s.overflow = 1; return; }
+    st.cl_pos[(POL * kClusterMax + n) * st.stride] = pos;
+    st.cl_h[(POL * kClusterMax + n) * st.stride] = h;
+    if (POL) { s.last1 = pos; s.n1 = n + 1; } else { s.last0 = pos; s.n0 = n + 1; }
+}
+
 template <typename Emit>
 __device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int pol, int pos, float h, int w,
                                           Emit &&emit) {
-    if (s.n(pol) > 0 && pos - s.last(pol) >= w) rzcc_resolve(s, st, pol, w, emit);
-    const int n = s.n(pol);
-    if (n == kClusterMax) { s.overflow = 1; return; }
-    st.cl_pos[(pol * kClusterMax + n) * st.stride] = pos;
-    st.cl_h[(pol * kClusterMax + n) * st.stride] = h;
-    s.set_last(pol, pos);
-    s.set_n(pol, n + 1);
+    if (pol) rzcc_push<1>(s, st, pos, h, w, emit); else rzcc_push<0>(s, st, pos, h, w, emit);
 }
 
 // every kSeg samples (t_end = last sample seen): close the clusters that can no longer
@@ -235,9 +254,8 @@ __device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int
 template <typename Emit>
 __device__ __forceinline__ void rzcc_close(RzccState &s, const RzccStore &st, int w, int t_end, bool final,
                                            Emit &&emit) {
-#pragma unroll
-    for (int pol = 0; pol < 2; ++pol)
-        if (s.n(pol) > 0 && (final || t_end - s.last(pol) >= w)) rzcc_resolve(s, st, pol, w, emit);
+    if (s.n1 > 0 && (final || t_end - s.last1 >= w)) rzcc_resolve<1>(s, st, w, emit);
+    if (s.n0 > 0 && (final || t_end - s.last0 >= w)) rzcc_resolve<0>(s, st, w, emit);
 }
 
 // candidate test for sample t with value class (nz, positive) and the running sum before it
@@ -272,17 +290,18 @@ __device__ __forceinline__ void rzcc_segment_masks(RzccState &s, const RzccStore
         // no exact zeros and no open flat top: a candidate sits right before every sign change
         const unsigned prev = (neg >> 1) | (s.sgn ? 0u : 0x80000000u);
         unsigned d = neg ^ prev;
-        if (ts == 0) d &= 0x7fffffffu;          // the first sample has no predecessor
-        if (!bipolar) d &= neg;                 // peaks only: + -> -
-        while (d) {
-            const int i = __clz(d);
-            d &= ~(0x80000000u >> i);
-            const int pos = ts + i - 1;
-            if (pos >= 1) {
-                const int peak = (neg >> (31 - i)) & 1u;      // the run before the change was positive
-                const float hc = i ? cs[(i - 1) * cs_stride] : carry;
-                rzcc_push(s, st, peak, pos, peak ? hc : -hc, w, emit);
-            }
+        if (ts == 0) d &= 0x3fffffffu;          // sample 0 has no predecessor and cannot start a flat top
+        // peaks: + -> - (the sample that confirms it is negative); valleys: - -> +
+        unsigned dp = d & neg, dv = bipolar ? (d & ~neg) : 0u;
+        while (dp) {
+            const int i = __clz(dp);
+            dp &= ~(0x80000000u >> i);
+            rzcc_push<1>(s, st, ts + i - 1, i ? cs[(i - 1) * cs_stride] : carry, w, emit);
+        }
+        while (dv) {
+            const int i = __clz(dv);
+            dv &= ~(0x80000000u >> i);
+            rzcc_push<0>(s, st, ts + i - 1, -(i ? cs[(i - 1) * cs_stride] : carry), w, emit);
         }
         s.r = ts + kSeg - 1;
         s.sgn = (neg & 1u) ? 0 : 1;

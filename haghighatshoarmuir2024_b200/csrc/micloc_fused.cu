@@ -8,20 +8,20 @@
 // in time tiles of kTile = 64 samples.  The warps are specialised and run as a
 // software pipeline, one barrier per tile (iteration k):
 //
-//   back warp   tile k+1   audio (HBM) -> mic-major ring in shared memory
-//   FIR warps   tile k     STHT quadrature FIR, one warp per clip: every lane owns 16
-//                          consecutive outputs of one microphone and walks the 240
-//                          non-zero Hilbert taps in blocks of 8 with a sliding register
-//                          window; the multiply-adds are packed FFMA2 (fma.rn.f32x2)
-//   front warp  tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running
-//                          sum, sign / zero bit masks; every 32 samples the masks are
-//                          turned into RZCC candidates and resolved (find_peaks distance
-//                          rule) into a bit-packed spike ring
-//   back warp   tile k-4   (the latency of the exact find_peaks decision) one lane per
-//                          (clip, channel): alpha-kernel neuron recurrences driven by the
-//                          final spike bits -> membrane tile; then Gram accumulation
-//                          C += v v^T of that tile with FFMA2, and the int8 spike raster
-//                          of the tile -> HBM
+//   FIR warps   tile k+1   audio (HBM) -> mic-major ring in shared memory (each warp its own clip)
+//               tile k     STHT quadrature FIR: every lane owns 16 consecutive outputs of one
+//                          microphone and walks the 240 non-zero Hilbert taps in blocks of 8 with
+//                          a sliding register window; the multiply-adds are packed FFMA2
+//                          (fma.rn.f32x2)
+//               tile k-4   Gram accumulation C += v v^T of the membrane tile the neuron warp
+//                          finished in this step (named barrier), FFMA2 on 4x4 blocks
+//   front warp  tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
+//                          sign / zero bit masks; every 32 samples the masks are turned into RZCC
+//                          candidates and resolved (find_peaks distance rule) into a bit-packed
+//                          spike ring
+//   neuron warp tile k-4   (the latency of the exact find_peaks decision) one lane per (clip,
+//                          channel): alpha-kernel neuron recurrences driven by the final spike
+//                          bits -> membrane tile, and the int8 spike raster of the tile -> HBM
 //   clip end               power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 #include <cuda_runtime.h>
 
@@ -35,6 +35,7 @@ constexpr int kRows = 8;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmPitch = 32;   // floats per time step in the membrane tile: [slot][16]
 constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
+constexpr int kGramFlush = 8;  // tiles of float32 Gram accumulation between two folds into float64
 
 struct FusedGeom {
     int ring_x;      // audio ring length in samples (multiple of 32)
@@ -43,7 +44,7 @@ struct FusedGeom {
     int nblk;        // FIR tap blocks of 8 (multiple of 3)
     int dtile;       // the back warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
-    int off_x, off_q, off_vm, off_is, off_cs, off_clus, off_bits, off_stage;   // byte offsets in dynamic smem
+    int off_x, off_q, off_vm, off_is, off_cs, off_clus, off_bits, off_stage, off_gacc;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
@@ -72,11 +73,14 @@ __device__ __forceinline__ void load_chunk(Chunk &c, const float *row, int coord
 }
 
 // 8 taps x 16 outputs: acc[ip] += g[jj] * W[ip + 7 - jj], W = lo pairs 0..7 | hi pairs 0..6
+struct Taps8 { float4 a, b; };
+__device__ __forceinline__ void load_taps(Taps8 &t, const float *__restrict__ taps8) {
+    t.a = *reinterpret_cast<const float4 *>(taps8);
+    t.b = *reinterpret_cast<const float4 *>(taps8 + 4);
+}
 __device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Chunk &lo, const Chunk &hi,
-                                          const float *__restrict__ taps8) {
-    const float4 g0 = *reinterpret_cast<const float4 *>(taps8);
-    const float4 g1 = *reinterpret_cast<const float4 *>(taps8 + 4);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                                          const Taps8 &t) {
+    const float g[8] = {t.a.x, t.a.y, t.a.z, t.a.w, t.b.x, t.b.y, t.b.z, t.b.w};
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
         const unsigned long long g2 = pack2(g[jj], g[jj]);
@@ -91,23 +95,100 @@ __device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Ch
 // All four warps meet here once per pipeline step (the roles run different code).
 __device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
+// Optional role timing (MICLOC_ROLE_TIMING): busy cycles of each warp role between barriers,
+// summed into sm_slots[256 + 2*role] (64-bit) by lane 0; read back by micloc_snn_debug_counters.
+#ifdef MICLOC_ROLE_TIMING
+__device__ __forceinline__ long long rt_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+struct RoleTimer {
+    long long t0, busy;
+    __device__ __forceinline__ void start() { t0 = rt_clock(); busy = 0; }
+    __device__ __forceinline__ void before_barrier() { busy += rt_clock() - t0; }
+    __device__ __forceinline__ void after_barrier() {
+        // BAR.SYNC only blocks at the next consumer: touch shared memory, then read the clock
+        unsigned int v;
+        long long t;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(0) : "memory");
+        asm volatile("{ .reg .u32 d; mov.u32 d, %1; mov.u64 %0, %%clock64; }" : "=l"(t) : "r"(v));
+        t0 = t;
+    }
+    __device__ __forceinline__ void flush(unsigned int *sm_slots, int role, int lane) {
+        if (lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + 256) + role, (unsigned long long)busy);
+            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + 256) + 4 + role, 1ull);
+            if (blockIdx.x < 1024)
+                (reinterpret_cast<unsigned long long *>(sm_slots + 320) + 8 * blockIdx.x)[4 + role] = (unsigned long long)busy;
+        }
+    }
+};
+#define ROLE_TIMER_DECL RoleTimer rt_; rt_.start()
+#define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(); rt_.after_barrier(); } while (0)
+#define ROLE_TIMER_FLUSH(role) rt_.flush(sm.dbg, role, lane)
+#define PHASE_DECL long long ph_[6] = {0, 0, 0, 0, 0, 0}, pht_ = rt_clock()
+#define PHASE_MARK(i) do { const long long n_ = rt_clock(); ph_[i] += n_ - pht_; pht_ = n_; } while (0)
+#define PHASE_FLUSH() do { if (lane == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(reinterpret_cast<unsigned long long *>(sm.dbg + 256) + 8 + i_, (unsigned long long)ph_[i_]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_MARK(i)
+#define PHASE_FLUSH()
+#define ROLE_TIMER_DECL
+#define ROLE_BARRIER() tile_barrier()
+#define ROLE_TIMER_FLUSH(role)
+#endif
+
 struct FusedSmem {
     float *taps, *xs, *qs, *vms, *is_s, *cs;
     int *clus;
     unsigned int *bits;     // [2 polarities][kRingWords][32 lanes]
     int8_t *stage;          // [kSlots][kTile][C2]
-    double *gram;
+    double *gram;           // [kSlots][16][16], clip epilogue only (reuses the audio rings)
+    double *gacc;           // [kSlots][10 block pairs][16] float64 Gram accumulators
+    unsigned int *dbg;      // sm_slots (debug counters behind the first 256 entries)
 };
 
-// ============================== STHT FIR warp (one per clip slot) ==============================
-template <int MM>
-__device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g, int slot,
-                                         bool clip_ok, int lane, int NT, int k_last) {
+// ======= FIR warp (one per clip slot): audio tile k+1 -> ring, STHT FIR of tile k =======
+
+template <typename IN_T, int MM>
+__device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                         const IN_T *__restrict__ audio, long long clip, bool clip_ok, long long T64,
+                                         int slot, int lane, int NT, int k_last) {
     const int M = MM ? MM : p.M;
-    const int f_chunk = lane >> 3, f_mic = lane & 7;     // lane = chunk * 8 + mic
+    const int T = (int)T64;
+    const int f_chunk = lane >> 3, f_mic = lane & 7;     // FIR lanes: lane = chunk * 8 + mic
     const bool work = clip_ok && f_mic < M;
     const float *row = sm.xs + (slot * M + f_mic) * g.pitch_x;
+    const IN_T *src = audio + (clip_ok ? clip : 0) * T64 * M;
+    float *rows_w = sm.xs + slot * M * g.pitch_x;
+    // this lane's first sample of the tile being filled (tile 0 at k = -1): time, frame, ring coordinate
+    int fill_t = lane;
+    const IN_T *fill_src = src + (lane < T ? lane * M : 0);
+    int fill_c = (lane + g.shift) % g.ring_x;
+    ROLE_TIMER_DECL;
+    PHASE_DECL;
+    unsigned long long a2[8];       // float32 Gram partial sums of this lane's block pair and time slice
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a2[i] = 0ull;
+
     for (int k = -1; k <= k_last; ++k) {
+        // (a) audio tile k+1 -> mic-major ring: every lane moves whole frames (all microphones of one
+        //     sample); the loads are issued here and stored after the FIR so that their latency is hidden
+        const int kf = k + 1;
+        const bool filling = kf < NT && clip_ok;
+        float v[kTile / 32][kRows];
+        if (filling) {
+#pragma unroll
+            for (int h = 0; h < kTile / 32; ++h) {
+                const bool ok = fill_t + 32 * h < T;
+                const IN_T *fr = fill_src + (ok ? 32 * h * M : 0);
+#pragma unroll
+                for (int m = 0; m < kRows; ++m) v[h][m] = (ok && m < M) ? to_f32<IN_T>(fr[m]) : 0.f;
+            }
+        }
+        PHASE_MARK(0);
+        // (b) STHT quadrature FIR of tile k
         if (work && k >= 0 && k < NT) {
             unsigned long long acc[8];
 #pragma unroll
@@ -118,15 +199,22 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
             { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
             load_chunk(A, row, c0);
             int cn = c0 - 16; if (cn < 0) cn += g.ring_x;
+            // window chunks and taps are fetched one block ahead of their use
             const float *tp = sm.taps;
+            Taps8 t0, t1;
+            load_taps(t0, tp);
 #pragma unroll 1
             for (int jb = 0; jb < g.nblk; jb += 3) {
                 load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                fir_block(acc, A, Bq, tp);
+                load_taps(t1, tp + 8);
+                fir_block(acc, A, Bq, t0);
                 load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                fir_block(acc, Cq, A, tp + 8);
+                load_taps(t0, tp + 16);
+                fir_block(acc, Cq, A, t1);
                 load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                fir_block(acc, Bq, Cq, tp + 16);
+                load_taps(t1, tp + 24);                 // first block of the next round (zero padding behind the last)
+                fir_block(acc, Bq, Cq, t0);
+                t0 = t1;
                 tp += 24;
             }
             float *dst = sm.qs + (((k & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
@@ -138,8 +226,27 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
                 reinterpret_cast<float4 *>(dst)[v] = o;
             }
         }
-        tile_barrier();
+        PHASE_MARK(1);
+        if (filling) {
+#pragma unroll
+            for (int h = 0; h < kTile / 32; ++h) {
+                int c = fill_c + 32 * h; if (c >= g.ring_x) c -= g.ring_x;
+#pragma unroll
+                for (int m = 0; m < kRows; ++m)
+                    if (m < M) rows_w[m * g.pitch_x + c] = v[h][m];
+            }
+            // next tile: time, source frame and ring coordinate of this lane's first sample
+            fill_t += kTile;
+            fill_src += (fill_t < T ? kTile * M : 0);
+            fill_c += kTile; if (fill_c >= g.ring_x) fill_c -= g.ring_x;
+        }
+        PHASE_MARK(2);
+        PHASE_MARK(4);
+        ROLE_BARRIER();
+        PHASE_MARK(5);
     }
+    ROLE_TIMER_FLUSH(slot);
+    PHASE_FLUSH();
 }
 
 // ============ front warp: band-pass + RZCC -> spike bits, lane = slot*16 + channel ============
@@ -184,6 +291,7 @@ __device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParam
     }
     BiquadState bq; biquad_reset(bq);
     RzccState rz; rzcc_reset(rz);
+    ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
         const int kc = k - 1;
@@ -235,13 +343,26 @@ __device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParam
                     float csum = carry;
                     int nvalid = kSeg;
                     if (fast) {
+                        float xn[8];
 #pragma unroll
-                        for (int i = 0; i < kSeg; ++i) {
-                            const float z = biquad2_step(sos, bq, xp[i]);
-                            csum += z;
-                            cs[i * 32] = csum;
-                            neg = __funnelshift_l(__float_as_uint(z), neg, 1);
-                            zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
+                        for (int i = 0; i < 8; ++i) xn[i] = xp[i];
+#pragma unroll 1
+                        for (int o = 0; o < kSeg / 8; ++o) {
+                            float xc[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) xc[i] = xn[i];
+                            if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float z = biquad2_step(sos, bq, xc[i]);
+                                csum += z;
+                                cs[(8 * o + i) * 32] = csum;
+                                neg = __funnelshift_l(__float_as_uint(z), neg, 1);
+                                zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
+                            }
                         }
                     } else {
                         nvalid = T - ts < kSeg ? T - ts : kSeg;
@@ -262,19 +383,19 @@ __device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParam
                 }
             }
         }
-        tile_barrier();
+        ROLE_BARRIER();
     }
+    ROLE_TIMER_FLUSH(2);
     if (c_valid && rz.overflow && flags) atomicOr(flags + clip0 + c_slot, 1);
 }
 
-// ==== back warp: audio tile k+1 -> ring; neuron + Gram + spike write-out of tile k - dtile ====
-template <typename IN_T, int MM>
-__device__ __forceinline__ void back_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                          const IN_T *__restrict__ audio, int8_t *__restrict__ spikes,
-                                          long long clip0, long long B, long long T64, int lane, int NT, int k_last) {
+// ==== neuron warp: alpha-kernel recurrences + int8 spike write-out of tile k - dtile, lane = slot*16 + channel ====
+template <int MM>
+__device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                            int8_t *__restrict__ spikes, long long clip0, long long B, long long T64,
+                                            int lane, int k_last) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
-    // neuron-lane geometry: lane = slot * 16 + channel
     const int c_slot = lane >> 4, c_ch = lane & 15;
     const bool c_valid = c_ch < C2 && clip0 + c_slot < B;
     const unsigned int *bits = sm.bits + lane;
@@ -283,7 +404,7 @@ __device__ __forceinline__ void back_role(const FusedSmem &sm, const ChainParams
     const float na = p.na, nc = p.nc, ncT = p.ncT, nLf = p.nLf;
     const int nL = p.nL;
     NeuronState nr; neuron_reset(nr);
-    // Gram-lane geometry: lane = slot * 10 + upper-triangular 4x4 block pair
+    // Gram lanes: lane = slot * 10 + upper-triangular 4x4 block pair of the slot's 16x16 matrix
     const int g_slot = lane / 10;
     int g_bi = 0, g_bj = 0;
     {
@@ -295,66 +416,43 @@ __device__ __forceinline__ void back_role(const FusedSmem &sm, const ChainParams
         }
     }
     const bool g_lane = lane < 10 * kSlots;
-    double acc64[16];
+    double *gacc = sm.gacc + lane * 16;
+    unsigned long long a2[8];       // float32 Gram partial sums of this lane's block pair
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc64[i] = 0.0;
+    for (int i = 0; i < 8; ++i) a2[i] = 0ull;
+    ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        // (a) audio tile k+1 -> mic-major ring: every lane moves whole frames (all microphones of one
-        //     sample); the loads of a tile are all issued before the first store
-        const int kf = k + 1;
-        if (kf < NT) {
-            constexpr int NF = kSlots * (kTile / 32);
-            float v[NF][kRows];
-            int coord[NF];
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                const int s = f / (kTile / 32), h = f % (kTile / 32);
-                const int t = kf * kTile + h * 32 + lane;
-                coord[f] = (t + g.shift) % g.ring_x;
-                const bool ok = t < T && clip0 + s < B;
-                const IN_T *fr = audio + ((clip0 + (ok ? s : 0)) * T64 + (ok ? t : 0)) * M;
-#pragma unroll
-                for (int m = 0; m < kRows; ++m) v[f][m] = (ok && m < M) ? to_f32<IN_T>(fr[m]) : 0.f;
-            }
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                const int s = f / (kTile / 32);
-                float *rows = sm.xs + s * M * g.pitch_x + coord[f];
-#pragma unroll
-                for (int m = 0; m < kRows; ++m)
-                    if (m < M) rows[m * g.pitch_x] = v[f][m];
-            }
-        }
-        // (b) neuron filter of tile j = k - dtile from the final spike bits
         const int j = k - g.dtile;
         const int u0 = j * kTile;
-        if (j >= 0 && u0 < T) {
-            if (c_valid) {
+        const bool live = j >= 0 && u0 < T;
+        if (live && c_valid) {
 #pragma unroll 1
-                for (int sg = 0; sg < kTile / kSeg; ++sg) {
-                    const int us = u0 + sg * kSeg;
-                    const int wi = (us >> 5) & (kRingWords - 1);
-                    unsigned int P = bits[(kRingWords + wi) * 32], Nn = bits[wi * 32];
-                    if (us >= T) { P = 0u; Nn = 0u; }
-                    // the same bits nL samples earlier (funnel over two ring words; zero before the clip start)
-                    const int d0 = us - nL;
-                    const int wd = (d0 >> 5) & (kRingWords - 1), wd1 = (wd + 1) & (kRingWords - 1), sh = d0 & 31;
-                    unsigned int PD = __funnelshift_r(bits[(kRingWords + wd) * 32], bits[(kRingWords + wd1) * 32], sh);
-                    unsigned int ND = __funnelshift_r(bits[wd * 32], bits[wd1 * 32], sh);
-                    if (d0 < 0) {
-                        const unsigned int keep = d0 <= -32 ? 0u : (0xffffffffu << (-d0));
-                        PD &= keep; ND &= keep;
-                    }
-                    const int nvalid = T - us < kSeg ? (T - us > 0 ? T - us : 0) : kSeg;
-                    if (nvalid < kSeg) {
-                        const unsigned int keep = nvalid <= 0 ? 0u : (0xffffffffu >> (32 - nvalid));
-                        P &= keep; Nn &= keep; PD &= keep; ND &= keep;
-                    }
-                    float *vseg = vmo + sg * kSeg * kVmPitch;
-                    int8_t *sseg = stg + sg * kSeg * C2;
+            for (int sg = 0; sg < kTile / kSeg; ++sg) {
+                const int us = u0 + sg * kSeg;
+                const int wi = (us >> 5) & (kRingWords - 1);
+                unsigned int P = bits[(kRingWords + wi) * 32], Nn = bits[wi * 32];
+                if (us >= T) { P = 0u; Nn = 0u; }
+                // the same bits nL samples earlier (funnel over two ring words; zero before the clip start)
+                const int d0 = us - nL;
+                const int wd = (d0 >> 5) & (kRingWords - 1), wd1 = (wd + 1) & (kRingWords - 1), sh = d0 & 31;
+                unsigned int PD = __funnelshift_r(bits[(kRingWords + wd) * 32], bits[(kRingWords + wd1) * 32], sh);
+                unsigned int ND = __funnelshift_r(bits[wd * 32], bits[wd1 * 32], sh);
+                if (d0 < 0) {
+                    const unsigned int keep = d0 <= -32 ? 0u : (0xffffffffu << (-d0));
+                    PD &= keep; ND &= keep;
+                }
+                const int nvalid = T - us < kSeg ? (T - us > 0 ? T - us : 0) : kSeg;
+                if (nvalid < kSeg) {
+                    const unsigned int keep = nvalid <= 0 ? 0u : (0xffffffffu >> (32 - nvalid));
+                    P &= keep; Nn &= keep; PD &= keep; ND &= keep;
+                }
+                float *vseg = vmo + sg * kSeg * kVmPitch;
+                int8_t *sseg = stg + sg * kSeg * C2;
+#pragma unroll 1
+                for (int o = 0; o < kSeg / 8; ++o) {
 #pragma unroll
-                    for (int i = 0; i < kSeg; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         // neuron_step with s, sd in {-1, 0, +1} given as bits
                         nr.p2 = na * (nr.p2 + nr.p1);
                         float a1 = na * nr.p1;
@@ -368,69 +466,62 @@ __device__ __forceinline__ void back_role(const FusedSmem &sm, const ChainParams
                         nr.q1 = b1;
                         const float tail = fmaf(nLf, nr.q1, nr.q2);
                         float v = fmaf(-ncT, tail, nc * nr.p2);
-                        if (i >= nvalid) v = 0.f;
-                        vseg[i * kVmPitch] = v;
-                        sseg[i * C2] = (int8_t)(((P >> i) & 1u) - ((Nn >> i) & 1u));
+                        if (8 * o + i >= nvalid) v = 0.f;
+                        vseg[(8 * o + i) * kVmPitch] = v;
+                        sseg[(8 * o + i) * C2] = (int8_t)(((P >> i) & 1u) - ((Nn >> i) & 1u));
                     }
+                    P >>= 8; Nn >>= 8; PD >>= 8; ND >>= 8;
                 }
             }
-            __syncwarp();
-            // (c) Gram of the membrane tile: C += v v^T, 4x4 blocks, FFMA2
-            if (g_lane) {
-                const float *vm = sm.vms + g_slot * 16;
-                unsigned long long a2[8];
+        }
+        __syncwarp();
+        // Gram of the membrane tile: C += v v^T on 4x4 blocks with FFMA2, float32 partial sums in
+        // registers, folded into the float64 accumulators every kGramFlush tiles
+        if (live && g_lane) {
+            const float *vm = sm.vms + g_slot * 16;
+#pragma unroll 8
+            for (int i = 0; i < kTile; ++i) {
+                const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
+                const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(vm + i * kVmPitch + 4 * g_bj);
+                const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a2[i] = 0ull;
-#pragma unroll 4
-                for (int i = 0; i < kTile; ++i) {
-                    const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
-                    const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(vm + i * kVmPitch + 4 * g_bj);
-                    const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const unsigned long long ar = pack2(av[r], av[r]);
-                        ffma2(a2[2 * r], c.x, ar);
-                        ffma2(a2[2 * r + 1], c.y, ar);
-                    }
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned long long ar = pack2(av[r], av[r]);
+                    ffma2(a2[2 * r], c.x, ar);
+                    ffma2(a2[2 * r + 1], c.y, ar);
                 }
+            }
+            if ((j % kGramFlush) == kGramFlush - 1 || (j + 1) * kTile >= T) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float lo, hi;
                     unpack2(a2[i], lo, hi);
-                    acc64[2 * i] += (double)lo;
-                    acc64[2 * i + 1] += (double)hi;
+                    a2[i] = 0ull;
+                    gacc[2 * i] += (double)lo;
+                    gacc[2 * i + 1] += (double)hi;
                 }
             }
-            // (d) int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
-            if (spikes) {
-                const int nrow = T - u0 < kTile ? T - u0 : kTile;
-                for (int s = 0; s < kSlots; ++s) {
-                    if (clip0 + s >= B) continue;
-                    const int8_t *src = sm.stage + s * kTile * C2;
-                    int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
-                    const int nbytes = nrow * C2;
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0) {
-                        for (int v = lane; v < nbytes / 16; v += 32)
-                            reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
-                    } else {
-                        for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
-                    }
+        }
+        __syncwarp();
+        // int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
+        if (live && spikes) {
+            const int nrow = T - u0 < kTile ? T - u0 : kTile;
+            for (int s = 0; s < kSlots; ++s) {
+                if (clip0 + s >= B) continue;
+                const int8_t *src = sm.stage + s * kTile * C2;
+                int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
+                const int nbytes = nrow * C2;
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0) {
+                    for (int v = lane; v < nbytes / 16; v += 32)
+                        reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
+                } else {
+                    for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
                 }
             }
-            __syncwarp();
         }
-        tile_barrier();
+        ROLE_BARRIER();
     }
-    // hand the Gram matrices to the epilogue (they reuse the audio rings, dead by now)
-    if (g_lane) {
-        double *Cd = sm.gram + g_slot * 256;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int row = 4 * g_bi + k / 4, col = 4 * g_bj + k % 4;
-            Cd[row * 16 + col] = acc64[k];
-            if (g_bi != g_bj) Cd[col * 16 + row] = acc64[k];
-        }
-    }
+    ROLE_TIMER_FLUSH(3);
 }
 
 template <typename IN_T, int MM>
@@ -451,12 +542,20 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.bits = reinterpret_cast<unsigned int *>(smem_raw + g.off_bits);   // [2][kRingWords][32]
     sm.stage = reinterpret_cast<int8_t *>(smem_raw + g.off_stage);       // [kSlots][kTile][C2]
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
+    sm.gacc = reinterpret_cast<double *>(smem_raw + g.off_gacc);
+    sm.dbg = sm_slots;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
     __shared__ unsigned int s_rot;
+    __shared__ long long s_pair;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = MM ? MM : p.M, C2 = 2 * M;
+#ifdef MICLOC_ROLE_TIMING
+    long long dbg_c0 = rt_clock();
+    unsigned long long dbg_g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+#endif
 
     // Warp w of a CTA lands on SM sub-partition w % 4; rotate the roles per co-resident
     // CTA so that every sub-partition gets its share of FIR warps.
@@ -464,17 +563,24 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         const unsigned int k = atomicAdd(sm_slots + (smid & 255u), 1u) & 3u;
-        s_rot = (0x3120u >> (4 * k)) & 3u;   // 0, 2, 1, 3
+        s_rot = (0x3120u >> (4 * k)) & 3u;   // 0, 2, 1, 3 for the 1st .. 4th CTA that lands on this SM
     }
-    for (int i = tid; i < 8 * g.nblk; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
+    for (int i = tid; i < 8 * g.nblk + 8; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
     __syncthreads();
-    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR of clip slot 0 / 1; 2: front; 3: back
+    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR (+ fill, Gram) of clip slot 0 / 1; 2: front; 3: neuron
 
     const int NT = (int)((T + kTile - 1) / kTile);
     const int k_last = NT - 1 + g.dtile;
     const long long npairs = (B + kSlots - 1) / kSlots;
 
-    for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    // Clip pairs are handed out dynamically: co-resident CTAs do not run at the same speed (the warp
+    // scheduler favours the youngest CTA of an SM), so a static split would wait for the slowest one.
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_pair = (long long)atomicAdd(sm_slots + 255, 1u);
+        __syncthreads();
+        const long long pair = s_pair;
+        if (pair >= npairs) break;
         const long long clip0 = pair * kSlots;
         {   // zero the audio rings: samples before the clip start are zeros (lfilter's zero state)
             float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
@@ -483,12 +589,28 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             // no spikes before the clip start; membrane columns of unused lanes stay zero
             for (int i = tid; i < 2 * kRingWords * 32; i += blockDim.x) sm.bits[i] = 0u;
             for (int i = tid; i < kTile * kVmPitch; i += blockDim.x) sm.vms[i] = 0.f;
+            for (int i = tid; i < kSlots * 160; i += blockDim.x) sm.gacc[i] = 0.0;
         }
         __syncthreads();
 
-        if (role < 2) fir_role<MM>(sm, p, g, role, clip0 + role < B, lane, NT, k_last);
+        if (role < 2) fir_role<IN_T, MM>(sm, p, g, audio, clip0 + role, clip0 + role < B, T, role, lane, NT, k_last);
         else if (role == 2) front_role<IN_T, MM>(sm, p, g, audio, flags, clip0, B, T, lane, k_last);
-        else back_role<IN_T, MM>(sm, p, g, audio, spikes, clip0, B, T, lane, NT, k_last);
+        else neuron_role<MM>(sm, p, g, spikes, clip0, B, T, lane, k_last);
+        __syncthreads();
+        // unpack the block-pair accumulators into full symmetric matrices (the audio rings are dead now)
+        for (int e = tid; e < kSlots * 160; e += blockDim.x) {
+            const int sl = e / 160, pr0 = (e % 160) / 16, kk = e % 16;
+            int bi = 0, bj = 0, pr = pr0;
+            for (int r = 0; r < 4; ++r) {
+                const int len = 4 - r;
+                if (pr < len) { bi = r; bj = r + pr; break; }
+                pr -= len;
+            }
+            const int row = 4 * bi + kk / 4, col = 4 * bj + kk % 4;
+            const double v = sm.gacc[e];
+            sm.gram[sl * 256 + row * 16 + col] = v;
+            if (bi != bj) sm.gram[sl * 256 + col * 16 + row] = v;
+        }
         __syncthreads();
 
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
@@ -500,8 +622,10 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             double best = -1.0; int besti = 0x7fffffff;
             for (int gg = tid; gg < p.G; gg += blockDim.x) {
                 double accp = 0.0;
+#pragma unroll 1
                 for (int r = 0; r < C2; ++r) {
                     double rr = 0.0;
+#pragma unroll 2
                     for (int c = 0; c < C2; ++c) rr = fma(Cd[r * 16 + c], Wd[(long long)c * p.G + gg], rr);
                     accp = fma(Wd[(long long)r * p.G + gg], rr, accp);
                 }
@@ -522,9 +646,24 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             __syncthreads();
         }
     }
+#ifdef MICLOC_ROLE_TIMING
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + 256);
+        d[14] = (unsigned long long)(rt_clock() - dbg_c0);
+        d[15] = g1 - dbg_g0;
+    }
+    if (tid == 0 && blockIdx.x < 1024) {
+        unsigned long long g1;
+        unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + 320) + 8 * blockIdx.x;
+        d[0] = dbg_g0; d[1] = g1; d[2] = smid; d[3] = s_rot;
+    }
+#endif
 }
-
-static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 bool fused_supported(const ChainParams &p) {
     return p.tap_stride == 2 && p.M <= kRows && p.nsec == 2 && (p.n_taps % 8) == 0;
@@ -536,12 +675,15 @@ static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float 
                           int32_t *flags, unsigned int *sm_slots, int sm_count, cudaStream_t st) {
     auto kern = k_fused<IN_T, MM>;
     MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    // all of the SM's L1/shared array as shared memory: three CTAs of ~71 KB must be resident together
+    MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
     MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, g.smem_bytes));
     if (per_sm < 1) return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel does not fit (smem %d B)", g.smem_bytes);
     long long grid = (long long)sm_count * per_sm;
     const long long npairs = (B + kSlots - 1) / kSlots;
     if (grid > npairs) grid = npairs;
+    MICLOC_CUDA(cudaMemsetAsync(sm_slots, 0, 256 * sizeof(unsigned int), st));   // role rotation restarts per launch
     kern<<<(unsigned)grid, 128, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
     count_launch(1);
     MICLOC_CUDA(cudaGetLastError());
@@ -566,7 +708,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     // tile k - dtile while the front warp has completed tile k - 2
     g.dtile = 1 + (rzcc_lag(p.w) + 63 + kTile - 1) / kTile;
     g.tiles_is = (p.half + kTile - 1) / kTile;
-    int off = (8 * g.nblk * (int)sizeof(float) + 15) & ~15;
+    int off = ((8 * g.nblk + 8) * (int)sizeof(float) + 15) & ~15;
     g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
     g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
     g.off_vm = off; off += kTile * kVmPitch * (int)sizeof(float);
@@ -575,6 +717,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (kSlots * kTile * p.C2 + 15) & ~15;
+    g.off_gacc = off; off += kSlots * 160 * (int)sizeof(double);
     g.smem_bytes = off;
     // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
     if (kTile * (g.dtile + 1) + p.nL + kSeg > kRingWords * 32)

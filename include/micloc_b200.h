@@ -172,6 +172,15 @@ int64_t micloc_launch_count(void);
  * runs summed in n_runs, then forgets them. */
 int micloc_snn_last_kernel_ms(micloc_snn *ctx, float *ms, int32_t *n_runs);
 int micloc_snn_enable_timing(micloc_snn *ctx, int enable);
+/* Debug counters of the fused kernel (busy cycles per warp role: FIR slot 0, FIR slot 1, front,
+ * neuron; then the number of warps that reported each; then six sub-phase sums of the FIR warps);
+ * zeros unless the library was built with
+ * -DMICLOC_ROLE_TIMING.  Synchronises the device. */
+int micloc_snn_debug_counters(micloc_snn *ctx, uint64_t out[16]);
+/* Debug: out[8*i .. 8*i+7] = (start ns, end ns, SM id, role rotation, busy cycles of FIR0, FIR1, front,
+ * neuron) of CTA i of the last fused launch, i < n <= 1024
+ * (MICLOC_ROLE_TIMING builds only). */
+int micloc_snn_debug_cta_times(micloc_snn *ctx, uint64_t *out, int32_t n);
 /* FP32 FMA-pipe micro-benchmark on `device` (the measured denominator of the
  * roofline in bench.py): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
 int micloc_fp32_peak(int device, int variant, double *tflops);

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Busy cycles per warp role of the fused kernel (needs a library built with
+`make -C haghighatshoarmuir2024_b200/csrc -B EXTRA=-DMICLOC_ROLE_TIMING`).  Runs on the GPU box."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench as Bn
+from haghighatshoarmuir2024_b200 import _native as N
+from haghighatshoarmuir2024_b200.montecarlo import BandSetup, SnrSweep
+
+d, bands = Bn.load_workload()
+setups = [BandSetup(band=bands[0], tau=float(d["tau_0"]), bf_mat=d["bf_0"])]
+sweep = SnrSweep(setups, d["r_vec"], d["theta_vec"], Bn.FS, float(d["kernel_duration"]), Bn.T_CLIP, device=0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 888
+audio, _, _ = sweep.synthesize(0, B, seed=1, snr_db_grid=Bn.SNR_GRID)
+eng = sweep.engines[0]
+lib = N.lib()
+out = (ctypes.c_uint64 * 16)()
+for rep in range(3):
+    lib.micloc_snn_debug_counters(eng._h, out)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.run(audio, want_spikes=True, want_power=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    lib.micloc_snn_debug_counters(eng._h, out)
+    v = list(out)
+    names = ["fir0", "fir1", "front", "neuron"]
+    iters = (Bn.T_CLIP // 64) + 5
+    print(f"rep {rep}: {ms:.3f} ms, {B / ms:.1f} clips/ms; " + ", ".join(
+        f"{n}: {v[i] / max(v[4 + i], 1) / iters:.0f} busy cyc/tile ({v[4 + i]} warps)" for i, n in enumerate(names)))
+    nf = max(v[4] + v[5], 1)
+    print("   FIR warp phases (cyc/tile): " + ", ".join(f"{n}: {v[8 + i] / nf / iters:.0f}" for i, n in enumerate(
+        ["fill-load", "fir", "fill-store", "-", "post", "tile-barrier"])))
+    print(f"   CTA 0: {v[14]} clock64 cycles in {v[15]} ns -> {v[14] / max(v[15], 1) * 1e3:.0f} MHz")
+
+n = min(444, (B + 1) // 2)  # CTAs of the launch (148 SMs x 3)
+buf = (ctypes.c_uint64 * (8 * n))()
+lib.micloc_snn_debug_cta_times(eng._h, buf, n)
+a = np.array(list(buf), dtype=np.float64).reshape(n, 8)
+t0 = a[:, 0].min()
+start, end, smid, rot = (a[:, 0] - t0) / 1e6, (a[:, 1] - t0) / 1e6, a[:, 2].astype(int), a[:, 3].astype(int)
+print("CTA start ms: max %.3f; end ms: min %.3f median %.3f max %.3f; CTAs per SM: %s" % (
+    start.max(), end.min(), np.median(end), end.max(), np.bincount(np.bincount(smid))))
+iters = Bn.T_CLIP // 64 + 5
+for r in sorted(set(rot)):
+    m = rot == r
+    print(f"rot {r}: {m.sum()} CTAs, end ms mean {end[m].mean():.2f} (min {end[m].min():.2f} max {end[m].max():.2f}); busy cyc/tile "
+          + ", ".join(f"{nm} {a[m, 4 + i].mean() / iters:.0f}" for i, nm in enumerate(["fir0", "fir1", "front", "neuron"])))
