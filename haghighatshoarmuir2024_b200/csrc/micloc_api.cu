@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,8 @@ extern "C" int64_t micloc_launch_count(void) { return g_launches.load(); }
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+static constexpr size_t kSlotWords = 320 + 16 * 1024;
+
 struct micloc_snn {
     int device = 0;
     ChainParams p{};
@@ -49,7 +52,8 @@ struct micloc_snn {
     float *d_sos = nullptr;        // [1][kMaxSections][5]
     float *d_W = nullptr;          // [C2][G] f32
     double *d_Wd = nullptr;        // [C2][G] f64
-    unsigned int *d_sm_slots = nullptr;  // [256] per-SM CTA arrival counters (role rotation of the fused kernel)
+    unsigned int *d_sm_slots = nullptr;  // [2][kSlotWords]: per-SM CTA arrival counters + clip-pair counter of the fused
+                                         // kernel (+ debug counters); one set per concurrently running launch
     DevBuf q, spikes, vmem, gram, flags, part;
     // host staging for run_host
     DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
@@ -154,8 +158,8 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
     }
     rc = upload_bf(c, cfg->bf_mat, cfg->num_doa);
     if (rc) { micloc_snn_destroy(c); return rc; }
-    if (cudaMalloc(&c->d_sm_slots, (320 + 16 * 1024) * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(c->d_sm_slots, 0, (320 + 16 * 1024) * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&c->d_sm_slots, 2 * kSlotWords * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->d_sm_slots, 0, 2 * kSlotWords * sizeof(unsigned int)) != cudaSuccess) {
         micloc_snn_destroy(c);
         return set_error(MICLOC_ERR_CUDA, "cudaMalloc(sm_slots) failed");
     }
@@ -376,9 +380,11 @@ extern "C" int micloc_snn_gram(micloc_snn *c, const void *audio, int dtype, int6
     return MICLOC_OK;
 }
 
-extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
-                              int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
-                              int fused, void *stream) {
+// `slot_set` picks the counter block of the fused kernel: launches that may overlap in time (the two
+// staging streams of micloc_snn_run_host) must not share the dynamic clip-pair counter.
+static int snn_run_impl(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                        int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                        int fused, void *stream, int slot_set) {
     if (!fused)
         return micloc_snn_run_taps(c, audio, dtype, B, T, nullptr, nullptr, spikes_dev, nullptr, nullptr,
                                    power_dev, doa_dev, flags_dev, stream);
@@ -391,10 +397,16 @@ extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64
     const long long l0 = g_launches.load();
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     MICLOC_TRY(launch_fused(c->p, c->d_taps, c->d_Wd, audio, dtype, B, T, spikes_dev, power_dev, doa_dev, flg,
-                            c->d_sm_slots, c->sm_count, st));
+                            c->d_sm_slots + (size_t)slot_set * kSlotWords, c->sm_count, st));
     MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
     return MICLOC_OK;
+}
+
+extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
+                              int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                              int fused, void *stream) {
+    return snn_run_impl(c, audio, dtype, B, T, spikes_dev, power_dev, doa_dev, flags_dev, fused, stream, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -410,6 +422,10 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
     const size_t clip_in = (size_t)T * p.M * esz, clip_spk = (size_t)T * p.C2;
     // chunk so that two chunks of input stay under ~1 GiB and every chunk fills the GPU
     long long chunk = (long long)((512ull << 20) / clip_in);
+    if (const char *e = getenv("MICLOC_HOST_CHUNK_CLIPS")) {   // tests: force several chunks on small batches
+        const long long v = atoll(e);
+        if (v > 0) chunk = v;
+    }
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
     for (int i = 0; i < 2; ++i) {
@@ -429,8 +445,8 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
                                     (size_t)nb * clip_in, cudaMemcpyHostToDevice, st));
         int8_t *d_spk = spikes_host ? (int8_t *)c->h_spk[slot].ptr : nullptr;
         float *d_pow = power_host ? (float *)c->h_pow[slot].ptr : nullptr;
-        int rc = micloc_snn_run(c, c->h_audio[slot].ptr, dtype, nb, T, d_spk, d_pow, (int32_t *)c->h_doa[slot].ptr,
-                                (int32_t *)c->h_flg[slot].ptr, fused, st);
+        int rc = snn_run_impl(c, c->h_audio[slot].ptr, dtype, nb, T, d_spk, d_pow, (int32_t *)c->h_doa[slot].ptr,
+                              (int32_t *)c->h_flg[slot].ptr, fused, st, slot);
         if (rc) return rc;
         if (spikes_host)
             MICLOC_CUDA(cudaMemcpyAsync(spikes_host + (size_t)b0 * clip_spk, d_spk, (size_t)nb * clip_spk,

@@ -170,6 +170,20 @@ def test_run_host_end_to_end_equals_device_path():
     np.testing.assert_array_equal(host["power"].numpy(), dev["power"].cpu().numpy())
 
 
+def test_run_host_overlapping_chunks_equal_device_path(monkeypatch):
+    """Several chunks in flight on the two staging streams (the fused kernel's dynamic clip-pair
+    counter is per stream) must give what one device launch gives."""
+    g = H.load("snn_c1_bipolar")
+    x, _ = H.synth_clips(g, 700, 1200, seed=9)
+    eng = engine_for(g, 1200)
+    dev = eng.run(to_dev(x), want_spikes=True, fused=True)
+    monkeypatch.setenv("MICLOC_HOST_CHUNK_CLIPS", "90")
+    for _ in range(3):
+        host = eng.run_host(torch.from_numpy(x).pin_memory(), want_spikes=True, fused=True)
+        assert np.array_equal(host["doa"].numpy(), dev["doa"].cpu().numpy())
+        assert np.array_equal(host["spikes"].numpy(), dev["spikes"].cpu().numpy())
+
+
 # ---------------------------------------------------------------------------
 # stand-alone stages
 # ---------------------------------------------------------------------------
