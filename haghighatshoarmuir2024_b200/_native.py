@@ -36,12 +36,13 @@ class XyloConfig(C.Structure):
     _fields_ = [
         ("num_mic", _i32), ("kernel_len", _i32), ("stht_kernel", _dp),
         ("num_bands", _i32), ("n_sections", _i32), ("sos", _dp),
+        ("n_ba", _i32), ("ba_b", _dp), ("ba_a", _dp),
         ("robust_width", _i32), ("bipolar", _i32),
         ("num_hidden", _i32), ("num_doa", _i32),
         ("w_in", C.POINTER(C.c_int8)), ("w_rec", C.POINTER(C.c_int8)),
         ("threshold", C.POINTER(C.c_int16)), ("dash_syn", C.POINTER(C.c_int8)),
         ("dash_mem", C.POINTER(C.c_int8)), ("bias", C.POINTER(C.c_int16)),
-        ("weight_shift", _i32), ("max_spikes", _i32),
+        ("weight_shift_in", _i32), ("weight_shift_rec", _i32), ("max_spikes", _i32),
     ]
 
 
@@ -59,8 +60,8 @@ SYMBOLS = {
     "micloc_hilbert_beamform": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _dp, _dp, _i32, _vp, _vp, _vp, _vp]),
     "micloc_xylo_create": (C.c_int, [C.POINTER(XyloConfig), C.c_int, C.POINTER(_vp)]),
     "micloc_xylo_destroy": (C.c_int, [_vp]),
-    "micloc_xylo_run": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "micloc_xylo_process": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "micloc_xylo_run": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "micloc_xylo_process": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "micloc_last_error": (C.c_char_p, []),
     "micloc_version": (C.c_int, []),
     "micloc_launch_count": (_i64, []),

@@ -1,19 +1,557 @@
-// micloc_xylo.cu -- Xylo-quantised integer chain (placeholder until the kernel lands).
+// micloc_xylo.cu -- Xylo-quantised integer chain (BASELINE config 3).
+//
+// Reference sites (paths under /root/reference):
+//   Demo.spike_encoding   micloc/xylo_snn_localization.py:315-356  STHT -> hstack(I,Q) -> Butterworth
+//                         filterbank (micloc/filterbank.py:40-44) -> RZCC with the band-0 encoder ->
+//                         pos/neg split
+//   Demo.xylo_process     micloc/xylo_snn_localization.py:358-377  rockpool XyloSim hidden layer:
+//                         integer LIF (bit-shift decay, int8 weights, 16-bit state, subtractive
+//                         multi-spike reset); rec["Spikes"] = hidden raster
+//   extract_rate / peak   micloc/xylo_snn_localization.py:379-427, micloc/utils.py:84-121 as used by
+//                         paper_plots/target_xylo_localization.py:594-605
+//
+// Two front ends produce the signed spike raster int8 [B][T][2M*F]:
+//   fast  (exact = 0): float32 STHT FIR (k_stht) + float32 SOS band filters + streaming RZCC (k_chain)
+//   exact (exact = 1): float64 throughout with the reference's own operation order -- lfilter's
+//                      direct-form-II-transposed FIR / IIR (product rounded, then added, oldest tap
+//                      first) and find_peaks on a float64 np.cumsum -- so that the spikes, and with
+//                      them every integer downstream, are bit-identical to numpy/scipy.
+// The integer network then runs as ONE kernel, one thread per (clip, hidden neuron) looping over
+// time with I_syn / V_mem / spike count in registers; the input spikes of a clip are turned into
+// per-step event masks in shared memory and each event is one predicated add of an int16 weight.
 #include <cuda_runtime.h>
+
+#include <vector>
 
 #include "micloc_common.h"
 
+namespace micloc {
+
+// ---------------------------------------------------------------------------
+// exact float64 front end
+// ---------------------------------------------------------------------------
+constexpr int kF64Tile = 256;   // outputs per CTA and microphone
+constexpr int kF64MG = 8;       // microphones per CTA
+
+// q[b][t][m] = lfilter(h, [1], x)[t][m] in float64, summed exactly as scipy's DF2T delay line does:
+// ((x[t-K+1] h[K-1] + x[t-K+2] h[K-2]) + ...) + x[t] h[0], every product rounded before its add.
+template <typename IN_T>
+__global__ void __launch_bounds__(kF64Tile)
+k_stht_f64(const IN_T *__restrict__ audio, const double *__restrict__ h, double *__restrict__ q,
+           int M, int K, long long T, int ntiles) {
+    extern __shared__ __align__(16) double smd[];
+    double *hs = smd;                                   // [K]
+    double *xs = smd + K;                               // [mg][kF64Tile + K - 1], microphone-major
+    const int pitch = kF64Tile + K - 1;
+    const long long b = blockIdx.x / ntiles;
+    const long long t0 = (long long)(blockIdx.x % ntiles) * kF64Tile;
+    const int m0 = blockIdx.y * kF64MG;
+    const int mg = min(kF64MG, M - m0);
+    const IN_T *clip = audio + b * T * M;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) hs[i] = h[i];
+    for (int e = threadIdx.x; e < pitch * mg; e += blockDim.x) {
+        const int l = e / mg, mm = e % mg;
+        const long long t = t0 - (K - 1) + l;
+        xs[mm * pitch + l] = (t >= 0 && t < T) ? (double)clip[t * M + m0 + mm] : 0.0;
+    }
+    __syncthreads();
+    const long long t = t0 + threadIdx.x;
+    if (t >= T) return;
+    // the microphones of the group are independent dependency chains: walk them together
+    const double *xr = xs + threadIdx.x;                    // xr[mm*pitch + j] = x[t - (K-1) + j][m0 + mm]
+    double acc[kF64MG];
+#pragma unroll
+    for (int mm = 0; mm < kF64MG; ++mm) acc[mm] = mm < mg ? __dmul_rn(xr[mm * pitch], hs[K - 1]) : 0.0;
+#pragma unroll 2
+    for (int j = 1; j < K; ++j) {
+        const double hj = hs[K - 1 - j];
+#pragma unroll
+        for (int mm = 0; mm < kF64MG; ++mm)
+            if (mm < mg) acc[mm] = __dadd_rn(acc[mm], __dmul_rn(xr[mm * pitch + j], hj));
+    }
+#pragma unroll
+    for (int mm = 0; mm < kF64MG; ++mm)
+        if (mm < mg) q[(b * T + t) * M + m0 + mm] = acc[mm];
+}
+
+constexpr int kMaxBa = 9;       // len(b) of a band filter (order-4 band-pass at most)
+
+// z[b][t][band*2M + c] = lfilter(b_band, a_band, hstack(I, Q))[t][c] in float64, DF2T evaluated in
+// scipy's order: y = z0 + b0 x; z[k] = (z[k+1] + x b[k+1]) - y a[k+1], the last delay being
+// x b[N-1] - y a[N-1] (= the same expression with z[N-1] == 0).  One thread per (clip, band,
+// channel), sequential in time.  NBA = len(b) rounded up to 3, 5 or 9 (coefficients zero-padded).
+template <typename IN_T, int NBA>
+__global__ void __launch_bounds__(128)
+k_iir_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, const double *__restrict__ ba_b,
+          const double *__restrict__ ba_a, double *__restrict__ z, int M, int half, int nba, int nb,
+          long long B, long long T) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C2 = 2 * M, CT = C2 * nb;
+    if (idx >= B * CT) return;
+    const long long b = idx / CT;
+    const int cc = (int)(idx % CT);
+    const int band = cc / C2, c = cc % C2;
+    double bb[NBA], aa[NBA], zs[NBA];
+#pragma unroll
+    for (int k = 0; k < NBA; ++k) {
+        bb[k] = k < nba ? ba_b[band * nba + k] : 0.0;
+        aa[k] = k < nba ? ba_a[band * nba + k] : 0.0;
+        zs[k] = 0.0;
+    }
+    const bool inphase = c < M;
+    const IN_T *xa = audio + b * T * M + (inphase ? c : 0);
+    const double *xq = q + b * T * M + (inphase ? 0 : c - M);
+    double *zo = z + b * T * CT + cc;
+    long long src = ((-(long long)half) % T + T) % T;   // (t - K/2) mod T at t = 0 (np.roll)
+    for (long long t = 0; t < T; ++t) {
+        double x;
+        if (inphase) { x = (double)xa[src * M]; if (++src == T) src = 0; }
+        else x = xq[t * M];
+        const double y = __dadd_rn(zs[0], __dmul_rn(bb[0], x));
+#pragma unroll
+        for (int k = 0; k < NBA - 1; ++k)
+            zs[k] = __dsub_rn(__dadd_rn(zs[k + 1], __dmul_rn(x, bb[k + 1])), __dmul_rn(y, aa[k + 1]));
+        zo[t * CT] = y;
+    }
+}
+
+template <typename IN_T>
+static void launch_iir_f64(const IN_T *audio, const double *q, const double *ba_b, const double *ba_a, double *z,
+                           int M, int half, int nba, int nb, long long B, long long T, cudaStream_t st) {
+    const long long nthr = B * 2 * M * nb;
+    const unsigned grid = (unsigned)((nthr + 127) / 128);
+    if (nba <= 3) k_iir_f64<IN_T, 3><<<grid, 128, 0, st>>>(audio, q, ba_b, ba_a, z, M, half, nba, nb, B, T);
+    else if (nba <= 5) k_iir_f64<IN_T, 5><<<grid, 128, 0, st>>>(audio, q, ba_b, ba_a, z, M, half, nba, nb, B, T);
+    else k_iir_f64<IN_T, kMaxBa><<<grid, 128, 0, st>>>(audio, q, ba_b, ba_a, z, M, half, nba, nb, B, T);
+}
+
+// ---------------------------------------------------------------------------
+// integer LIF network (XyloSim hidden layer)
+// ---------------------------------------------------------------------------
+constexpr int kLifTile = 256;   // time steps staged in shared memory at once
+
+__device__ __forceinline__ int xylo_decay(int v, int dash) {
+    int dv = v >> dash;                       // arithmetic shift
+    dv = dv == 0 ? (v > 0 ? 1 : 0) : dv;      // by at least one towards zero (v < 0 never shifts to 0)
+    return v - dv;
+}
+__device__ __forceinline__ int xylo_sat16(int v) { return max(-32768, min(32767, v)); }
+
+// spikes: SIGNED_IN ? int8 [B][T][CI] in {-1,0,+1} (bipolar: input channel c is the positive part of
+// column c, channel CI + c its negative part) : int8 [B][T][N_in] in {0,1}.
+// grid = (B, neuron chunks); block = chunk size rounded up to a warp.
+template <bool SIGNED_IN, int W>
+__global__ void __launch_bounds__(512)
+k_xylo_lif(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in, const int16_t *__restrict__ w,
+           const int16_t *__restrict__ thr, const int8_t *__restrict__ dash_syn, const int8_t *__restrict__ dash_mem,
+           const int16_t *__restrict__ bias, int max_spikes, int N, int npb, long long T,
+           uint8_t *__restrict__ raster, int32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    int16_t *w_s = reinterpret_cast<int16_t *>(sm_raw);                            // [N_in][npb_pad]
+    const int npb_pad = (npb + 7) & ~7;
+    unsigned int *masks = reinterpret_cast<unsigned int *>(sm_raw + (((size_t)N_in * npb_pad * 2 + 15) & ~(size_t)15));   // [kLifTile][W]
+    int8_t *raw = reinterpret_cast<int8_t *>(masks + kLifTile * W);               // [kLifTile][row]
+    const int row = SIGNED_IN ? CI : N_in;
+
+    const long long b = blockIdx.x;
+    const int n0 = blockIdx.y * npb;
+    const int tid = threadIdx.x;
+    const int n = n0 + tid;
+    const bool live = tid < npb && n < N;
+    for (int e = tid; e < N_in * npb; e += blockDim.x) {
+        const int i = e / npb, j = e % npb;
+        w_s[i * npb_pad + j] = (n0 + j < N) ? w[(long long)i * N + n0 + j] : (int16_t)0;
+    }
+    int isyn = 0, vmem = 0, count = 0;
+    const int th = live ? thr[n] : 0x7fffffff;
+    const int ds = live ? dash_syn[n] : 0, dm = live ? dash_mem[n] : 0;
+    const int bs = (live && bias) ? bias[n] : 0;
+    const int16_t *wn = w_s + tid;
+    const int8_t *src = spikes + b * T * row;
+    uint8_t *ras = raster ? raster + b * T * N + n : nullptr;
+
+    for (long long t0 = 0; t0 < T; t0 += kLifTile) {
+        const int len = (int)min((long long)kLifTile, T - t0);
+        __syncthreads();                                 // previous tile fully consumed
+        {   // stage the raw spike bytes of this tile (coalesced; 16-byte vectors when aligned)
+            const int8_t *g = src + t0 * row;
+            const int nbytes = len * row;
+            if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+                const int nv = nbytes >> 4;
+                for (int v = tid; v < nv; v += blockDim.x)
+                    reinterpret_cast<int4 *>(raw)[v] = __ldg(reinterpret_cast<const int4 *>(g) + v);
+                for (int e = (nv << 4) + tid; e < nbytes; e += blockDim.x) raw[e] = g[e];
+            } else {
+                for (int e = tid; e < nbytes; e += blockDim.x) raw[e] = g[e];
+            }
+        }
+        __syncthreads();
+        for (int s = tid; s < len; s += blockDim.x) {    // event masks of the tile's steps
+            unsigned int m[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) m[k] = 0u;
+            const int8_t *r = raw + s * row;
+            for (int c = 0; c < row; ++c) {
+                const int v = r[c];
+                int bit = -1;
+                if (SIGNED_IN) { if (v > 0) bit = c; else if (v < 0 && bipolar) bit = CI + c; }
+                else if (v != 0) bit = c;
+                if (bit >= 0) {
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+                        if ((bit >> 5) == k) m[k] |= 1u << (bit & 31);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < W; ++k) masks[s * W + k] = m[k];
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 1
+            for (int s0 = 0; s0 < len; s0 += 8) {
+                // the event masks of 8 steps first: their shared-memory latency stays off the
+                // per-step dependency chain (steps past the tile's end read stale words and are skipped)
+                unsigned int mk[8][W];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int k = 0; k < W; ++k) mk[u][k] = masks[(s0 + u) * W + k];   // the same word for the whole CTA: a broadcast
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (s0 + u < len) {
+                        isyn = xylo_decay(isyn, ds);
+#pragma unroll
+                        for (int k = 0; k < W; ++k) {
+                            unsigned int m = mk[u][k];
+                            while (m) {                  // warp-uniform loop over this step's input events
+                                const int i = __ffs(m) - 1 + 32 * k;
+                                m &= m - 1;
+                                isyn += wn[i * npb_pad];
+                            }
+                        }
+                        isyn = xylo_sat16(isyn);
+                        vmem = xylo_sat16(xylo_decay(vmem, dm) + isyn + bs);
+                        int ns = 0;
+                        if (vmem >= th) {
+                            do { vmem -= th; ++ns; } while (vmem >= th && ns < max_spikes);
+                            count += ns;
+                        }
+                        if (ras) ras[(t0 + s0 + u) * N] = (uint8_t)ns;
+                    }
+                }
+            }
+        }
+    }
+    if (live && counts) counts[b * N + n] = count;
+}
+
+// One CTA per clip: S[g] = sum_f counts[f*G + g]; doa = first argmax S; doa_peak = first argmax of the
+// 'full' box-car sums of S, minus win/2, modulo G (micloc/utils.py:84-121 on integers).
+__global__ void __launch_bounds__(128)
+k_xylo_doa(const int32_t *__restrict__ counts, int G, int F, int win, int32_t *__restrict__ doa,
+           int32_t *__restrict__ doa_peak) {
+    extern __shared__ __align__(16) long long S[];      // [G]
+    __shared__ long long red_v[128];
+    __shared__ int red_i[128];
+    const long long b = blockIdx.x;
+    const int32_t *c = counts + b * (long long)G * F;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        long long a = 0;
+        for (int f = 0; f < F; ++f) a += c[(long long)f * G + g];
+        S[g] = a;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && (!doa_peak || win < 1)) break;
+        const int J = pass == 0 ? G : G + win - 1;
+        long long best = -1; int besti = 0x7fffffff;
+        for (int j = threadIdx.x; j < J; j += blockDim.x) {
+            long long v;
+            if (pass == 0) v = S[j];
+            else {
+                const int lo = max(0, j - win + 1), hi = min(j, G - 1);
+                v = 0;
+                for (int k = lo; k <= hi; ++k) v += S[k];
+            }
+            if (v > best) { best = v; besti = j; }      // ascending j: first maximum kept
+        }
+        red_v[threadIdx.x] = best; red_i[threadIdx.x] = besti;
+        __syncthreads();
+        for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+            if (threadIdx.x < st) {
+                const long long ov = red_v[threadIdx.x + st]; const int oi = red_i[threadIdx.x + st];
+                if (ov > red_v[threadIdx.x] || (ov == red_v[threadIdx.x] && oi < red_i[threadIdx.x])) {
+                    red_v[threadIdx.x] = ov; red_i[threadIdx.x] = oi;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (pass == 0) { if (doa) doa[b] = red_i[0]; }
+            else {
+                int idx = (red_i[0] - win / 2) % G;
+                if (idx < 0) idx += G;
+                doa_peak[b] = idx;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// signed raster [n][CI] -> Demo.spike_encoding's layout [n][N_in] in {0,1}
+__global__ void __launch_bounds__(256)
+k_xylo_split(const int8_t *__restrict__ s, int8_t *__restrict__ out, long long rows, int CI, int bipolar) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * CI) return;
+    const long long r = i / CI;
+    const int c = (int)(i % CI);
+    const int v = s[i];
+    if (bipolar) {
+        out[r * 2 * CI + c] = v > 0;
+        out[r * 2 * CI + CI + c] = v < 0;
+    } else {
+        out[r * CI + c] = (int8_t)v;
+    }
+}
+
+}  // namespace micloc
+
 using namespace micloc;
 
-extern "C" int micloc_xylo_create(const micloc_xylo_config *, int, micloc_xylo **out) {
-    if (out) *out = nullptr;
-    return set_error(MICLOC_ERR_UNSUPPORTED, "xylo path not built yet");
+struct micloc_xylo {
+    int device = 0;
+    ChainParams p{};
+    int F = 1, N = 0, G = 0, N_in = 0, CT = 0, nba = 0, max_spikes = 31;
+    bool has_rec = false;
+    float *d_taps = nullptr;        // float32 compacted STHT taps (fast front end)
+    float *d_band_sos = nullptr;    // [F][kMaxSections][5]
+    double *d_h = nullptr;          // [K] float64 STHT kernel (exact front end)
+    double *d_ba_b = nullptr, *d_ba_a = nullptr;   // [F][nba]
+    int16_t *d_w = nullptr;         // [N_in][N] input weights, shift applied
+    int16_t *d_thr = nullptr, *d_bias = nullptr;
+    int8_t *d_ds = nullptr, *d_dm = nullptr;
+    DevBuf q, qd, zd, signed_spk, counts, flags;
+};
+
+extern "C" int micloc_xylo_destroy(micloc_xylo *c) {
+    if (!c) return MICLOC_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_taps); cudaFree(c->d_band_sos); cudaFree(c->d_h); cudaFree(c->d_ba_b); cudaFree(c->d_ba_a);
+    cudaFree(c->d_w); cudaFree(c->d_thr); cudaFree(c->d_bias); cudaFree(c->d_ds); cudaFree(c->d_dm);
+    c->q.release(); c->qd.release(); c->zd.release(); c->signed_spk.release(); c->counts.release(); c->flags.release();
+    delete c;
+    return MICLOC_OK;
 }
-extern "C" int micloc_xylo_destroy(micloc_xylo *) { return MICLOC_OK; }
-extern "C" int micloc_xylo_run(micloc_xylo *, const void *, int, int64_t, int64_t, int8_t *, uint8_t *, int32_t *,
-                               int32_t *, int32_t *, int32_t, int32_t *, void *) {
-    return set_error(MICLOC_ERR_UNSUPPORTED, "xylo path not built yet");
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t n) {
+    MICLOC_CUDA(cudaMalloc((void **)dst, n * sizeof(T)));
+    MICLOC_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return MICLOC_OK;
 }
-extern "C" int micloc_xylo_process(micloc_xylo *, const int8_t *, int64_t, int64_t, uint8_t *, int32_t *, void *) {
-    return set_error(MICLOC_ERR_UNSUPPORTED, "xylo path not built yet");
+
+extern "C" int micloc_xylo_create(const micloc_xylo_config *cfg, int device, micloc_xylo **out) {
+    if (!cfg || !out) return set_error(MICLOC_ERR_CONFIG, "null config");
+    *out = nullptr;
+    if (cfg->num_mic < 1 || cfg->num_mic > 128)
+        return set_error(MICLOC_ERR_CONFIG, "num_mic %d out of range [1, 128]", cfg->num_mic);
+    if (!cfg->stht_kernel || !cfg->sos || !cfg->w_in || !cfg->threshold || !cfg->dash_syn || !cfg->dash_mem)
+        return set_error(MICLOC_ERR_CONFIG, "null array in config");
+    if (cfg->num_bands < 1 || cfg->num_bands > 16) return set_error(MICLOC_ERR_CONFIG, "num_bands %d out of range [1, 16]", cfg->num_bands);
+    if (cfg->robust_width < 1) return set_error(MICLOC_ERR_CONFIG, "`distance` must be greater or equal to 1");
+    if (cfg->num_doa < 1 || cfg->num_hidden != cfg->num_doa * cfg->num_bands)
+        return set_error(MICLOC_ERR_CONFIG, "num_hidden %d must equal num_doa %d x num_bands %d", cfg->num_hidden, cfg->num_doa, cfg->num_bands);
+    if (cfg->n_ba < 0 || cfg->n_ba > kMaxBa || (cfg->n_ba > 0 && (!cfg->ba_b || !cfg->ba_a)))
+        return set_error(MICLOC_ERR_CONFIG, "bad b/a filter description (n_ba %d, at most %d)", cfg->n_ba, kMaxBa);
+    if (cfg->weight_shift_in < 0 || cfg->weight_shift_in > 7 || cfg->weight_shift_rec < 0 || cfg->weight_shift_rec > 7)
+        return set_error(MICLOC_ERR_CONFIG, "weight shifts must be in [0, 7]");
+    if (cfg->max_spikes < 1 || cfg->max_spikes > 255) return set_error(MICLOC_ERR_CONFIG, "max_spikes must be in [1, 255]");
+    const int CT = 2 * cfg->num_mic * cfg->num_bands;
+    const int N_in = CT * (cfg->bipolar ? 2 : 1);
+    if (N_in > 128) return set_error(MICLOC_ERR_UNSUPPORTED, "at most 128 input channels (got %d)", N_in);
+    const int N = cfg->num_hidden;
+    bool has_rec = false;
+    if (cfg->w_rec)
+        for (size_t i = 0; i < (size_t)N * N && !has_rec; ++i) has_rec = cfg->w_rec[i] != 0;
+    if (has_rec)
+        return set_error(MICLOC_ERR_UNSUPPORTED, "non-zero quantised recurrent weights are not supported on the device "
+                                                 "(the reference's w_rec = -0.1/N quantises to zero)");
+    for (int n = 0; n < N; ++n) {
+        if (cfg->threshold[n] < 1) return set_error(MICLOC_ERR_CONFIG, "threshold[%d] = %d must be >= 1", n, cfg->threshold[n]);
+        if (cfg->dash_syn[n] < 0 || cfg->dash_syn[n] > 15 || cfg->dash_mem[n] < 0 || cfg->dash_mem[n] > 15)
+            return set_error(MICLOC_ERR_CONFIG, "dash[%d] out of range [0, 15]", n);
+    }
+    MICLOC_CUDA(cudaSetDevice(device));
+    micloc_xylo *c = new micloc_xylo();
+    c->device = device;
+    ChainParams &p = c->p;
+    p.M = cfg->num_mic; p.C2 = 2 * cfg->num_mic;
+    p.w = cfg->robust_width; p.bipolar = cfg->bipolar ? 1 : 0;
+    p.nsec = cfg->n_sections;
+    p.na = 0.5f; p.nc = 1.f; p.ncT = 0.f; p.nLf = 1.f; p.nL = 1; p.G = cfg->num_doa;
+    c->F = cfg->num_bands; c->N = N; c->G = cfg->num_doa; c->N_in = N_in; c->CT = CT; c->nba = cfg->n_ba;
+    c->max_spikes = cfg->max_spikes;
+    int rc = setup_stht(p, cfg->stht_kernel, cfg->kernel_len, &c->d_taps);
+    if (rc) { micloc_xylo_destroy(c); return rc; }
+    std::vector<float> sosf((size_t)c->F * kMaxSections * 5);
+    for (int f = 0; f < c->F && !rc; ++f)
+        rc = sos_to_f32(cfg->sos + (size_t)f * cfg->n_sections * 6, cfg->n_sections, &sosf[(size_t)f * kMaxSections * 5]);
+    if (!rc) { for (int k = 0; k < kMaxSections * 5; ++k) (&p.sos[0][0])[k] = sosf[k]; }
+    if (!rc) rc = upload(&c->d_band_sos, sosf.data(), sosf.size());
+    if (!rc) rc = upload(&c->d_h, cfg->stht_kernel, (size_t)cfg->kernel_len);
+    if (!rc && cfg->n_ba > 0) {
+        rc = upload(&c->d_ba_b, cfg->ba_b, (size_t)c->F * cfg->n_ba);
+        if (!rc) rc = upload(&c->d_ba_a, cfg->ba_a, (size_t)c->F * cfg->n_ba);
+        for (int f = 0; f < c->F && !rc; ++f)
+            if (cfg->ba_a[(size_t)f * cfg->n_ba] != 1.0) rc = set_error(MICLOC_ERR_CONFIG, "band filter %d: a[0] must be 1", f);
+    }
+    if (!rc) {
+        std::vector<int16_t> w16((size_t)N_in * N);
+        for (size_t i = 0; i < w16.size(); ++i) w16[i] = (int16_t)((int)cfg->w_in[i] << cfg->weight_shift_in);
+        rc = upload(&c->d_w, w16.data(), w16.size());
+    }
+    if (!rc) rc = upload(&c->d_thr, cfg->threshold, (size_t)N);
+    if (!rc) rc = upload(&c->d_ds, cfg->dash_syn, (size_t)N);
+    if (!rc) rc = upload(&c->d_dm, cfg->dash_mem, (size_t)N);
+    if (!rc && cfg->bias) rc = upload(&c->d_bias, cfg->bias, (size_t)N);
+    if (rc) { micloc_xylo_destroy(c); return rc; }
+    *out = c;
+    return MICLOC_OK;
+}
+
+static int check_xylo_args(micloc_xylo *c, const void *in, int64_t B, int64_t T) {
+    if (!c) return set_error(MICLOC_ERR_CONFIG, "null context");
+    if (!in) return set_error(MICLOC_ERR_SHAPE, "null input pointer");
+    if (B < 1 || T < 1) return set_error(MICLOC_ERR_SHAPE, "empty batch (B=%lld, T=%lld)", (long long)B, (long long)T);
+    if (T > (1ll << 30) || B > 0x7fffffffll) return set_error(MICLOC_ERR_SHAPE, "batch too large");
+    return MICLOC_OK;
+}
+
+// integer network on a spike raster already on the device
+template <bool SIGNED_IN>
+static int launch_lif(micloc_xylo *c, const int8_t *spikes, long long B, long long T, uint8_t *raster,
+                      int32_t *counts, cudaStream_t st) {
+    const int N = c->N;
+    const int nchunks = (N + 479) / 480;                       // <= 480 neurons (15 warps) per CTA
+    const int npb = (N + nchunks - 1) / nchunks;
+    const int threads = (npb + 31) & ~31;
+    const int W = (c->N_in + 31) / 32;
+    const int npb_pad = (npb + 7) & ~7;
+    const int row = SIGNED_IN ? c->CT : c->N_in;
+    const size_t smem = (((size_t)c->N_in * npb_pad * 2 + 15) & ~(size_t)15) + (size_t)kLifTile * W * 4 + (size_t)kLifTile * row + 16;
+    if (smem > 227 * 1024) return set_error(MICLOC_ERR_UNSUPPORTED, "LIF kernel needs %zu B of shared memory", smem);
+    dim3 grid((unsigned)B, (unsigned)nchunks);
+#define MICLOC_LIF_CASE(WW)                                                                                       \
+    case WW: {                                                                                                    \
+        auto kern = k_xylo_lif<SIGNED_IN, WW>;                                                                    \
+        MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        kern<<<grid, threads, smem, st>>>(spikes, c->CT, c->p.bipolar, c->N_in, c->d_w, c->d_thr, c->d_ds, c->d_dm, \
+                                          c->d_bias, c->max_spikes, N, npb, T, raster, counts);                   \
+    } break
+    switch (W) {
+        MICLOC_LIF_CASE(1);
+        MICLOC_LIF_CASE(2);
+        MICLOC_LIF_CASE(3);
+        MICLOC_LIF_CASE(4);
+        default: return set_error(MICLOC_ERR_UNSUPPORTED, "too many input channels");
+    }
+#undef MICLOC_LIF_CASE
+    count_launch(1);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+static int launch_doa(micloc_xylo *c, const int32_t *counts, long long B, int32_t *doa, int32_t *doa_peak, int win,
+                      cudaStream_t st) {
+    if (!doa && !doa_peak) return MICLOC_OK;
+    if (doa_peak && (win < 1 || (win & 1) == 0 || win > c->G / 2))
+        return set_error(MICLOC_ERR_CONFIG, "averaging window size should be odd and at most half the DoA grid");  // utils.py:103-111
+    const size_t smem = (size_t)c->G * sizeof(long long);
+    MICLOC_CUDA(cudaFuncSetAttribute(k_xylo_doa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_xylo_doa<<<(unsigned)B, 128, smem, st>>>(counts, c->G, c->F, doa_peak ? win : 0, doa, doa_peak);
+    count_launch(1);
+    MICLOC_CUDA(cudaGetLastError());
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int64_t B, int64_t T, int exact,
+                               int8_t *spikes_in_dev, uint8_t *raster_dev, int32_t *counts_dev,
+                               int32_t *doa_dev, int32_t *doa_peak_dev, int32_t peak_win,
+                               int32_t *flags_dev, void *stream) {
+    MICLOC_TRY(check_xylo_args(c, audio, B, T));
+    if (dtype != MICLOC_F32 && dtype != MICLOC_I16) return set_error(MICLOC_ERR_SHAPE, "dtype must be MICLOC_F32 or MICLOC_I16");
+    if (exact && c->nba < 1) return set_error(MICLOC_ERR_CONFIG, "the exact front end needs the band filters in b/a form (n_ba)");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ChainParams &p = c->p;
+    const int CT = c->CT;
+    int32_t *counts = counts_dev;
+    if (!counts) { MICLOC_TRY(c->counts.reserve((size_t)B * c->N * sizeof(int32_t))); counts = (int32_t *)c->counts.ptr; }
+    int32_t *flg = flags_dev;
+    if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
+    MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
+    // the batch goes through in chunks that bound the scratch (float64 intermediates of the exact front end)
+    const size_t per_clip = (size_t)T * (exact ? (size_t)p.M * 8 + (size_t)CT * 8 * 2 + (size_t)CT * 3 : (size_t)p.M * 4 + CT);
+    long long chunk = (long long)(((size_t)6 << 30) / per_clip);
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    MICLOC_TRY(c->signed_spk.reserve((size_t)chunk * T * CT));
+    if (exact) {
+        MICLOC_TRY(c->qd.reserve((size_t)chunk * T * p.M * sizeof(double)));
+        MICLOC_TRY(c->zd.reserve((size_t)chunk * T * CT * sizeof(double)));
+    } else {
+        MICLOC_TRY(c->q.reserve((size_t)chunk * T * p.M * sizeof(float)));
+    }
+    const size_t esz = dtype == MICLOC_I16 ? 2 : 4;
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = B - b0 < chunk ? B - b0 : chunk;
+        const char *a = (const char *)audio + (size_t)b0 * T * p.M * esz;
+        int8_t *sgn = (int8_t *)c->signed_spk.ptr;
+        if (exact) {
+            const int ntiles = (int)((T + kF64Tile - 1) / kF64Tile);
+            const int mgmax = p.M < kF64MG ? p.M : kF64MG;
+            const size_t smem = ((size_t)p.K + (size_t)mgmax * (kF64Tile + p.K - 1)) * sizeof(double);
+            if (smem > 227 * 1024) return set_error(MICLOC_ERR_UNSUPPORTED, "exact STHT tile needs %zu B of shared memory", smem);
+            dim3 grid((unsigned)(nb * ntiles), (unsigned)((p.M + kF64MG - 1) / kF64MG));
+            if (dtype == MICLOC_I16) {
+                MICLOC_CUDA(cudaFuncSetAttribute(k_stht_f64<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_stht_f64<int16_t><<<grid, kF64Tile, smem, st>>>((const int16_t *)a, c->d_h, (double *)c->qd.ptr, p.M, p.K, T, ntiles);
+                launch_iir_f64((const int16_t *)a, (const double *)c->qd.ptr, c->d_ba_b, c->d_ba_a, (double *)c->zd.ptr, p.M,
+                               p.half, c->nba, c->F, nb, T, st);
+            } else {
+                MICLOC_CUDA(cudaFuncSetAttribute(k_stht_f64<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_stht_f64<float><<<grid, kF64Tile, smem, st>>>((const float *)a, c->d_h, (double *)c->qd.ptr, p.M, p.K, T, ntiles);
+                launch_iir_f64((const float *)a, (const double *)c->qd.ptr, c->d_ba_b, c->d_ba_a, (double *)c->zd.ptr, p.M,
+                               p.half, c->nba, c->F, nb, T, st);
+            }
+            count_launch(2);
+            MICLOC_CUDA(cudaGetLastError());
+            MICLOC_TRY(micloc_rzcc_encode_f64((const double *)c->zd.ptr, nb, T, CT, p.w, p.bipolar, sgn, c->device, st));
+        } else {
+            MICLOC_TRY(launch_stht_any(p, c->d_taps, a, dtype, (float *)c->q.ptr, nb, T, st));
+            MICLOC_TRY(launch_chain_any(p, a, dtype, (const float *)c->q.ptr, c->d_band_sos, c->F, nullptr, sgn, flg + b0, nb, T, st));
+        }
+        if (spikes_in_dev) {
+            const long long rows = nb * T;
+            k_xylo_split<<<(unsigned)((rows * CT + 255) / 256), 256, 0, st>>>(sgn, spikes_in_dev + (size_t)b0 * T * c->N_in, rows, CT, p.bipolar);
+            count_launch(1);
+        }
+        MICLOC_TRY(launch_lif<true>(c, sgn, nb, T, raster_dev ? raster_dev + (size_t)b0 * T * c->N : nullptr,
+                                    counts + (size_t)b0 * c->N, st));
+    }
+    MICLOC_TRY(launch_doa(c, counts, B, doa_dev, doa_peak_dev, peak_win, st));
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_xylo_process(micloc_xylo *c, const int8_t *spikes_in_dev, int64_t B, int64_t T,
+                                   uint8_t *raster_dev, int32_t *counts_dev, int32_t *doa_dev,
+                                   int32_t *doa_peak_dev, int32_t peak_win, void *stream) {
+    MICLOC_TRY(check_xylo_args(c, spikes_in_dev, B, T));
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *counts = counts_dev;
+    if (!counts) { MICLOC_TRY(c->counts.reserve((size_t)B * c->N * sizeof(int32_t))); counts = (int32_t *)c->counts.ptr; }
+    MICLOC_TRY(launch_lif<false>(c, spikes_in_dev, B, T, raster_dev, counts, st));
+    MICLOC_TRY(launch_doa(c, counts, B, doa_dev, doa_peak_dev, peak_win, st));
+    return MICLOC_OK;
 }

@@ -122,44 +122,55 @@ int micloc_hilbert_beamform(micloc_snn *ctx, const void *audio_dev, int dtype, i
                             float *y_dev, float *power_dev, int32_t *doa_dev, void *stream);
 
 /* ---- Xylo integer chain ---------------------------------------------------- */
+/* Network constants are what rockpool's mapper + global_quantize + config_from_specification
+ * hand to XyloSim (micloc/xylo_snn_localization.py:268-290); the host package restates that
+ * quantisation (haghighatshoarmuir2024_b200/xylo_snn_localization.py: quantize_network). */
 typedef struct {
     int32_t num_mic;            /* M                                                      */
     int32_t kernel_len;         /* K                                                      */
     const double *stht_kernel;  /* [K]                       xylo_snn_localization.py:327  */
     int32_t num_bands;          /* F                         xylo_snn_localization.py:148-152 */
-    int32_t n_sections;         /* biquads per band filter (order 1 -> 1, order 2 -> 2)    */
+    int32_t n_sections;         /* biquads per band filter (order 1 -> 1, order 2 -> 2): float32 front end */
     const double *sos;          /* [F][n_sections][6]        filterbank.py:79-81           */
+    int32_t n_ba;               /* len(b) == len(a) per band (2*order + 1): float64 exact front end; 0 = none */
+    const double *ba_b;         /* [F][n_ba]                 filterbank.py:79-81 (output="ba") */
+    const double *ba_a;         /* [F][n_ba], a[0] == 1                                    */
     int32_t robust_width;       /* band-0 width for all bands  xylo_snn_localization.py:346 */
     int32_t bipolar;            /* 1: inputs = [pos | neg]   xylo_snn_localization.py:350-354 */
     int32_t num_hidden;         /* N = G*F hidden neurons                                  */
     int32_t num_doa;            /* G                                                       */
     const int8_t *w_in;         /* [N_in][N] int8, N_in = 2M*F*(bipolar?2:1)               */
-    const int8_t *w_rec;        /* [N][N] int8 or NULL when all-zero                       */
-    const int16_t *threshold;   /* [N]                                                     */
+    const int8_t *w_rec;        /* [N][N] int8 or NULL; must be all-zero on the device     */
+    const int16_t *threshold;   /* [N] >= 1                                                */
     const int8_t *dash_syn;     /* [N] bit-shift decay of I_syn                            */
     const int8_t *dash_mem;     /* [N] bit-shift decay of V_mem                            */
     const int16_t *bias;        /* [N] or NULL                                             */
-    int32_t weight_shift;       /* left shift applied to weighted input (XyloSim)          */
-    int32_t max_spikes;         /* spikes per neuron per step cap (hidden: 31)             */
+    int32_t weight_shift_in;    /* left shift applied to input weights (0 in the reference) */
+    int32_t weight_shift_rec;   /* left shift applied to recurrent weights                 */
+    int32_t max_spikes;         /* spikes per hidden neuron per step (31)                  */
 } micloc_xylo_config;
 
 int micloc_xylo_create(const micloc_xylo_config *cfg, int device, micloc_xylo **out);
 int micloc_xylo_destroy(micloc_xylo *ctx);
 
 /* audio -> input spikes (Demo.spike_encoding) -> hidden spike counts -> DoA.
+ *   exact != 0: float64 front end with scipy's operation order (spikes bit-identical to the
+ *               reference's numpy/scipy path); 0: float32 front end (float-path tolerance).
  *   spikes_in_dev [B][T][N_in] int8 in {0,1}      (nullable)
  *   raster_dev    [B][T][N] uint8 hidden spikes per step = rec["Spikes"] (nullable)
  *   counts_dev    [B][N] int32 = sum_t raster     (nullable)
- *   doa_dev       [B] int32: argmax over g of band-folded counts (nullable)
- *   doa_peak_dev  [B] int32: utils.find_peak_location(rate, win) (nullable; win odd) */
-int micloc_xylo_run(micloc_xylo *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+ *   doa_dev       [B] int32: first argmax over g of the band-summed counts (nullable)
+ *   doa_peak_dev  [B] int32: utils.find_peak_location(counts, peak_win) (nullable; win odd)
+ *   flags_dev     [B] int32, bit0 = RZCC cluster overflow of the float32 front end (nullable) */
+int micloc_xylo_run(micloc_xylo *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T, int exact,
                     int8_t *spikes_in_dev, uint8_t *raster_dev, int32_t *counts_dev,
                     int32_t *doa_dev, int32_t *doa_peak_dev, int32_t peak_win,
                     int32_t *flags_dev, void *stream);
 
 /* Integer network only (Demo.xylo_process): spikes_in_dev [B][T][N_in] int8 {0,1}. */
 int micloc_xylo_process(micloc_xylo *ctx, const int8_t *spikes_in_dev, int64_t B, int64_t T,
-                        uint8_t *raster_dev, int32_t *counts_dev, void *stream);
+                        uint8_t *raster_dev, int32_t *counts_dev, int32_t *doa_dev,
+                        int32_t *doa_peak_dev, int32_t peak_win, void *stream);
 
 /* ---- misc ------------------------------------------------------------------ */
 const char *micloc_last_error(void);

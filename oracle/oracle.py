@@ -55,6 +55,10 @@ def lib():
         _lib.mo_rzcc.argtypes = [_dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp]
         _lib.mo_snn_apply.restype = C.c_int
         _lib.mo_snn_run_batch.restype = C.c_int
+        _lib.mo_xylo_encode.restype = C.c_int
+        _lib.mo_xylo_lif.restype = None
+        _lib.mo_xylo_rate_doa.restype = None
+        _lib.mo_xylo_run_batch.restype = C.c_int
     return _lib
 
 
@@ -186,3 +190,119 @@ def beamformer_apply(x, h, b, a, bf_mat) -> np.ndarray:
     lib().mo_beamformer_apply(_p(x), C.c_int(T), C.c_int(M), _p(h), C.c_int(len(h)), _p(b), _p(a),
                               C.c_int(len(b)), _p(bf_re), _p(bf_im), C.c_int(G), _p(yr), _p(yi))
     return yr + 1j * yi
+
+
+# --------------------------------------------------------------------------------------
+# Xylo integer chain (micloc/xylo_snn_localization.py:315-398; XyloSim restated, parity unpinned)
+# --------------------------------------------------------------------------------------
+class _XyloCfg(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("K", C.c_int), ("h", _dp),
+        ("F", C.c_int), ("nba", C.c_int), ("b", _dp), ("a", _dp),
+        ("robust_width", C.c_double), ("bipolar", C.c_int),
+        ("N_in", C.c_int), ("N", C.c_int), ("G", C.c_int),
+        ("w_in", C.c_void_p), ("w_rec", C.c_void_p), ("threshold", C.c_void_p),
+        ("dash_syn", C.c_void_p), ("dash_mem", C.c_void_p), ("bias", C.c_void_p),
+        ("weight_shift_in", C.c_int), ("weight_shift_rec", C.c_int), ("max_spikes", C.c_int),
+    ]
+
+
+@dataclass
+class XyloConfig:
+    """Host constants of Demo (front end) + the quantised hidden layer."""
+    h: np.ndarray                # STHT kernel [K]
+    b: np.ndarray                # [F, nba] band-filter numerators
+    a: np.ndarray                # [F, nba] denominators (a[:, 0] == 1)
+    robust_width: float
+    bipolar: bool
+    num_mic: int
+    num_doa: int
+    w_in: np.ndarray             # int8 [N_in, N]
+    threshold: np.ndarray        # int16 [N]
+    dash_syn: np.ndarray         # int8 [N]
+    dash_mem: np.ndarray         # int8 [N]
+    w_rec: Optional[np.ndarray] = None
+    bias: Optional[np.ndarray] = None
+    weight_shift_in: int = 0
+    weight_shift_rec: int = 0
+    max_spikes: int = 31
+
+    def _c(self):
+        self.h = _f64(self.h)
+        self.b = _f64(np.atleast_2d(self.b)); self.a = _f64(np.atleast_2d(self.a))
+        self.w_in = np.ascontiguousarray(self.w_in, dtype=np.int8)
+        self.threshold = np.ascontiguousarray(self.threshold, dtype=np.int16)
+        self.dash_syn = np.ascontiguousarray(self.dash_syn, dtype=np.int8)
+        self.dash_mem = np.ascontiguousarray(self.dash_mem, dtype=np.int8)
+        if self.w_rec is not None:
+            self.w_rec = np.ascontiguousarray(self.w_rec, dtype=np.int8)
+        if self.bias is not None:
+            self.bias = np.ascontiguousarray(self.bias, dtype=np.int16)
+        vp = lambda arr: None if arr is None else arr.ctypes.data_as(C.c_void_p)
+        c = _XyloCfg()
+        c.M = self.num_mic; c.K = len(self.h); c.h = _p(self.h)
+        c.F, c.nba = self.b.shape; c.b = _p(self.b); c.a = _p(self.a)
+        c.robust_width = float(self.robust_width); c.bipolar = int(bool(self.bipolar))
+        c.N_in, c.N = self.w_in.shape; c.G = self.num_doa
+        assert c.N_in == 2 * c.M * c.F * (2 if self.bipolar else 1) and c.N == c.G * c.F
+        c.w_in = vp(self.w_in); c.w_rec = vp(self.w_rec); c.threshold = vp(self.threshold)
+        c.dash_syn = vp(self.dash_syn); c.dash_mem = vp(self.dash_mem); c.bias = vp(self.bias)
+        c.weight_shift_in = self.weight_shift_in; c.weight_shift_rec = self.weight_shift_rec
+        c.max_spikes = self.max_spikes
+        return c
+
+
+def xylo_encode(cfg: XyloConfig, x: np.ndarray):
+    """Demo.spike_encoding (micloc/xylo_snn_localization.py:315-356) on one clip x[T, M]:
+    returns (spikes_in int8 [T, N_in] in {0,1}, signed raster int8 [T, 2M*F])."""
+    x = _f64(x)
+    T, M = x.shape
+    c = cfg._c()
+    assert M == c.M
+    spk = np.zeros((T, c.N_in), dtype=np.int8)
+    sgn = np.zeros((T, 2 * M * c.F), dtype=np.int8)
+    rc = lib().mo_xylo_encode(C.byref(c), _p(x), C.c_int(T), spk.ctypes.data_as(C.c_void_p), sgn.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError("`distance` must be greater or equal to 1")
+    return spk, sgn
+
+
+def xylo_lif(cfg: XyloConfig, spikes_in: np.ndarray):
+    """Hidden layer of XyloSim (Demo.xylo_process, :358-377) on one clip: (raster uint8 [T, N], counts int32 [N])."""
+    s = np.ascontiguousarray(spikes_in, dtype=np.int8)
+    c = cfg._c()
+    T = s.shape[0]
+    assert s.shape[1] == c.N_in
+    raster = np.zeros((T, c.N), dtype=np.uint8)
+    counts = np.zeros(c.N, dtype=np.int32)
+    lib().mo_xylo_lif(C.byref(c), s.ctypes.data_as(C.c_void_p), C.c_int(T), raster.ctypes.data_as(C.c_void_p),
+                      counts.ctypes.data_as(C.c_void_p))
+    return raster, counts
+
+
+def xylo_rate_doa(counts: np.ndarray, G: int, F: int, T: int, fs: float, win: int = 0):
+    """extract_rate (:379-398) + argmax + find_peak_location (micloc/utils.py:84-121): (rate [G], doa, doa_peak)."""
+    cnt = np.ascontiguousarray(counts, dtype=np.int32)
+    rate = np.empty(G)
+    d0, d1 = C.c_int(0), C.c_int(-1)
+    lib().mo_xylo_rate_doa(cnt.ctypes.data_as(C.c_void_p), C.c_int(G), C.c_int(F), C.c_int(T), C.c_double(fs),
+                           C.c_int(win), _p(rate), C.byref(d0), C.byref(d1))
+    return rate, d0.value, d1.value
+
+
+def xylo_run_batch(cfg: XyloConfig, audio: np.ndarray, fs: float, win: int = 0, nthreads: int = 1,
+                   want_spikes: bool = False):
+    """Batched Xylo chain over audio[B, T, M] (float32 or int16) on `nthreads` host threads."""
+    assert audio.dtype in (np.float32, np.int16) and audio.flags.c_contiguous
+    B, T, M = audio.shape
+    c = cfg._c()
+    assert M == c.M
+    counts = np.empty((B, c.N), dtype=np.int32)
+    doa = np.empty(B, dtype=np.int32)
+    doa_peak = np.empty(B, dtype=np.int32)
+    sgn = np.empty((B, T, 2 * M * c.F), dtype=np.int8) if want_spikes else None
+    used = lib().mo_xylo_run_batch(
+        C.byref(c), audio.ctypes.data_as(C.c_void_p), int(audio.dtype == np.int16), C.c_int(B), C.c_int(T),
+        C.c_double(fs), C.c_int(win), counts.ctypes.data_as(C.c_void_p), doa.ctypes.data_as(C.c_void_p),
+        doa_peak.ctypes.data_as(C.c_void_p), None if sgn is None else sgn.ctypes.data_as(C.c_void_p), C.c_int(nthreads))
+    return {"counts": counts, "doa": doa, "doa_peak": doa_peak, "spikes_signed": sgn, "threads": int(used)}

@@ -21,7 +21,7 @@ def declared_functions():
 def test_header_declares_the_documented_entry_points():
     names = declared_functions()
     for must in ("micloc_snn_create", "micloc_snn_run", "micloc_snn_run_taps", "micloc_snn_run_host",
-                 "micloc_rzcc_encode_f64", "micloc_hilbert_beamform", "micloc_xylo_create", "micloc_xylo_run",
+                 "micloc_rzcc_encode_f64", "micloc_hilbert_beamform", "micloc_xylo_create", "micloc_xylo_run", "micloc_xylo_process",
                  "micloc_last_error"):
         assert must in names
 
@@ -53,3 +53,11 @@ def test_bad_config_is_rejected_before_touching_the_gpu():
     assert rc == N.ERR_CONFIG and b"num_mic" in lib.micloc_last_error()
     with pytest.raises(ValueError):
         N.check(rc)
+
+
+def test_bad_xylo_config_is_rejected_before_touching_the_gpu():
+    lib = N.lib()
+    cfg = N.XyloConfig()         # num_mic == 0
+    h = ctypes.c_void_p()
+    rc = lib.micloc_xylo_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc == N.ERR_CONFIG and b"num_mic" in lib.micloc_last_error()
