@@ -21,6 +21,7 @@
 // per-step event masks in shared memory and each event is one predicated add of an int16 weight.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "micloc_common.h"
@@ -130,18 +131,45 @@ static void launch_iir_f64(const IN_T *audio, const double *q, const double *ba_
 // ---------------------------------------------------------------------------
 constexpr int kLifTile = 256;   // time steps staged in shared memory at once
 
-__device__ __forceinline__ int xylo_decay(int v, int dash) {
-    int dv = v >> dash;                       // arithmetic shift
-    dv = dv == 0 ? (v > 0 ? 1 : 0) : dv;      // by at least one towards zero (v < 0 never shifts to 0)
-    return v - dv;
-}
+// bit-shift decay: v -= v >> dash (arithmetic), by at least one towards zero.  For v < 0 the shift
+// never reaches 0, for v > 0 it is raised to 1, for v == 0 it stays 0: dv = max(v >> dash, min(v, 1)).
+__device__ __forceinline__ int xylo_decay(int v, int dash) { return v - max(v >> dash, min(v, 1)); }
 __device__ __forceinline__ int xylo_sat16(int v) { return max(-32768, min(32767, v)); }
 
 // spikes: SIGNED_IN ? int8 [B][T][CI] in {-1,0,+1} (bipolar: input channel c is the positive part of
 // column c, channel CI + c its negative part) : int8 [B][T][N_in] in {0,1}.
 // grid = (B, neuron chunks); block = chunk size rounded up to a warp.
-template <bool SIGNED_IN, int W>
-__global__ void __launch_bounds__(512)
+// one time step of one hidden neuron; returns the number of spikes it fired (th2 = 2 * th)
+template <bool SAT_ISYN>
+__device__ __forceinline__ int xylo_step(int &isyn, int &vmem, int in, int ds, int dm, int bs, int th, int th2,
+                                         int max_spikes) {
+    isyn = xylo_decay(isyn, ds) + in;
+    if (SAT_ISYN) isyn = xylo_sat16(isyn);
+    int v = xylo_sat16(xylo_decay(vmem, dm) + isyn + bs);
+    const bool fire = v >= th, multi = v >= th2;     // two independent compares
+    int ns = fire ? 1 : 0;
+    v -= fire ? th : 0;                              // the common single spike, predicated
+    if (multi) {                                     // rare: several spikes in one step
+        while (v >= th && ns < max_spikes) { v -= th; ++ns; }
+    }
+    vmem = v;
+    return ns;
+}
+
+// named barriers (ids 1..4): full[buf] = masks of a tile are ready, empty[buf] = they have been consumed
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Warp-specialised: the LAST warp of the CTA is the producer, it stages the raw spike bytes of tile
+// k+1 and turns them into per-step event masks while the neuron warps run tile k (two mask buffers,
+// handed over with named barriers).  Neuron threads: one (clip, hidden neuron) each, state in registers.
+// SAT_ISYN = false when the host proved that I_syn cannot leave the int16 range
+// (2^dash_syn * (sum_i |w_i| + 1) <= 32767 for every neuron).
+#ifndef MICLOC_LIF_MINB
+#define MICLOC_LIF_MINB 3      // CTAs of 512 threads per SM the register budget is cut for
+#endif
+template <bool SIGNED_IN, int W, bool SAT_ISYN, bool RASTER>
+__global__ void __launch_bounds__(512, MICLOC_LIF_MINB)
 k_xylo_lif(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in, const int16_t *__restrict__ w,
            const int16_t *__restrict__ thr, const int8_t *__restrict__ dash_syn, const int8_t *__restrict__ dash_mem,
            const int16_t *__restrict__ bias, int max_spikes, int N, int npb, long long T,
@@ -149,98 +177,131 @@ k_xylo_lif(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in, con
     extern __shared__ __align__(16) unsigned char sm_raw[];
     int16_t *w_s = reinterpret_cast<int16_t *>(sm_raw);                            // [N_in][npb_pad]
     const int npb_pad = (npb + 7) & ~7;
-    unsigned int *masks = reinterpret_cast<unsigned int *>(sm_raw + (((size_t)N_in * npb_pad * 2 + 15) & ~(size_t)15));   // [kLifTile][W]
-    int8_t *raw = reinterpret_cast<int8_t *>(masks + kLifTile * W);               // [kLifTile][row]
+    unsigned int *masks = reinterpret_cast<unsigned int *>(sm_raw + (((size_t)N_in * npb_pad * 2 + 15) & ~(size_t)15));   // [2][kLifTile][W]
+    int8_t *raw = reinterpret_cast<int8_t *>(masks + 2 * kLifTile * W);           // [kLifTile][row], producer only
     const int row = SIGNED_IN ? CI : N_in;
 
     const long long b = blockIdx.x;
     const int n0 = blockIdx.y * npb;
     const int tid = threadIdx.x;
-    const int n = n0 + tid;
-    const bool live = tid < npb && n < N;
-    for (int e = tid; e < N_in * npb; e += blockDim.x) {
+    const int nthreads = blockDim.x;
+    const int n_cons = nthreads - 32;                     // neuron threads
+    const int ntiles = (int)((T + kLifTile - 1) / kLifTile);
+    for (int e = tid; e < N_in * npb; e += nthreads) {
         const int i = e / npb, j = e % npb;
         w_s[i * npb_pad + j] = (n0 + j < N) ? w[(long long)i * N + n0 + j] : (int16_t)0;
     }
-    int isyn = 0, vmem = 0, count = 0;
-    const int th = live ? thr[n] : 0x7fffffff;
-    const int ds = live ? dash_syn[n] : 0, dm = live ? dash_mem[n] : 0;
-    const int bs = (live && bias) ? bias[n] : 0;
-    const int16_t *wn = w_s + tid;
-    const int8_t *src = spikes + b * T * row;
-    uint8_t *ras = raster ? raster + b * T * N + n : nullptr;
+    __syncthreads();
 
-    for (long long t0 = 0; t0 < T; t0 += kLifTile) {
-        const int len = (int)min((long long)kLifTile, T - t0);
-        __syncthreads();                                 // previous tile fully consumed
-        {   // stage the raw spike bytes of this tile (coalesced; 16-byte vectors when aligned)
-            const int8_t *g = src + t0 * row;
-            const int nbytes = len * row;
-            if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
-                const int nv = nbytes >> 4;
-                for (int v = tid; v < nv; v += blockDim.x)
-                    reinterpret_cast<int4 *>(raw)[v] = __ldg(reinterpret_cast<const int4 *>(g) + v);
-                for (int e = (nv << 4) + tid; e < nbytes; e += blockDim.x) raw[e] = g[e];
-            } else {
-                for (int e = tid; e < nbytes; e += blockDim.x) raw[e] = g[e];
-            }
-        }
-        __syncthreads();
-        for (int s = tid; s < len; s += blockDim.x) {    // event masks of the tile's steps
-            unsigned int m[W];
-#pragma unroll
-            for (int k = 0; k < W; ++k) m[k] = 0u;
-            const int8_t *r = raw + s * row;
-            for (int c = 0; c < row; ++c) {
-                const int v = r[c];
-                int bit = -1;
-                if (SIGNED_IN) { if (v > 0) bit = c; else if (v < 0 && bipolar) bit = CI + c; }
-                else if (v != 0) bit = c;
-                if (bit >= 0) {
-#pragma unroll
-                    for (int k = 0; k < W; ++k)
-                        if ((bit >> 5) == k) m[k] |= 1u << (bit & 31);
+    if (tid >= n_cons) {
+        // ---------------- producer warp ----------------
+        const int lane = tid - n_cons;
+        const int8_t *src = spikes + b * T * row;
+        for (int k = 0; k < ntiles; ++k) {
+            const long long t0 = (long long)k * kLifTile;
+            const int len = (int)min((long long)kLifTile, T - t0);
+            {   // raw spike bytes of the tile (coalesced; 16-byte vectors when aligned)
+                const int8_t *g = src + t0 * row;
+                const int nbytes = len * row;
+                if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+                    const int nv = nbytes >> 4;
+                    for (int v = lane; v < nv; v += 32)
+                        reinterpret_cast<int4 *>(raw)[v] = __ldg(reinterpret_cast<const int4 *>(g) + v);
+                    for (int e = (nv << 4) + lane; e < nbytes; e += 32) raw[e] = g[e];
+                } else {
+                    for (int e = lane; e < nbytes; e += 32) raw[e] = g[e];
                 }
             }
+            __syncwarp();
+            if (k >= 2) bar_sync_named(3 + (k & 1), nthreads);       // buffer k&1 has been consumed (tile k-2)
+            unsigned int *mk = masks + (k & 1) * kLifTile * W;
+            const int len8 = (len + 7) & ~7;                         // the consumers read whole groups of 8 steps
+            for (int s = lane; s < len8; s += 32) {
+                unsigned int m[W];
 #pragma unroll
-            for (int k = 0; k < W; ++k) masks[s * W + k] = m[k];
-        }
-        __syncthreads();
-        if (live) {
-#pragma unroll 1
-            for (int s0 = 0; s0 < len; s0 += 8) {
-                // the event masks of 8 steps first: their shared-memory latency stays off the
-                // per-step dependency chain (steps past the tile's end read stale words and are skipped)
-                unsigned int mk[8][W];
+                for (int q = 0; q < W; ++q) m[q] = 0u;
+                if (s < len) {
+                    const int8_t *r = raw + s * row;
+                    for (int c = 0; c < row; ++c) {
+                        const int v = r[c];
+                        int bit = -1;
+                        if (SIGNED_IN) { if (v > 0) bit = c; else if (v < 0 && bipolar) bit = CI + c; }
+                        else if (v != 0) bit = c;
+                        if (bit >= 0) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-#pragma unroll
-                    for (int k = 0; k < W; ++k) mk[u][k] = masks[(s0 + u) * W + k];   // the same word for the whole CTA: a broadcast
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (s0 + u < len) {
-                        isyn = xylo_decay(isyn, ds);
-#pragma unroll
-                        for (int k = 0; k < W; ++k) {
-                            unsigned int m = mk[u][k];
-                            while (m) {                  // warp-uniform loop over this step's input events
-                                const int i = __ffs(m) - 1 + 32 * k;
-                                m &= m - 1;
-                                isyn += wn[i * npb_pad];
-                            }
+                            for (int q = 0; q < W; ++q)
+                                if ((bit >> 5) == q) m[q] |= 1u << (bit & 31);
                         }
-                        isyn = xylo_sat16(isyn);
-                        vmem = xylo_sat16(xylo_decay(vmem, dm) + isyn + bs);
-                        int ns = 0;
-                        if (vmem >= th) {
-                            do { vmem -= th; ++ns; } while (vmem >= th && ns < max_spikes);
-                            count += ns;
-                        }
-                        if (ras) ras[(t0 + s0 + u) * N] = (uint8_t)ns;
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < W; ++q) mk[s * W + q] = m[q];
+            }
+            __threadfence_block();
+            bar_arrive_named(1 + (k & 1), nthreads);                 // masks of tile k are ready
+        }
+        return;
+    }
+
+    // ---------------- neuron threads ----------------
+    const int n = n0 + tid;
+    const bool live = tid < npb && n < N;
+    int isyn = 0, vmem = 0, count = 0;
+    const int th = live ? thr[n] : 0x3fffffff;
+    const int th2 = 2 * th;
+    const int ds = live ? dash_syn[n] : 0, dm = live ? dash_mem[n] : 0;
+    const int bs = (live && bias) ? bias[n] : 0;
+    const unsigned wn_addr = (unsigned)__cvta_generic_to_shared(w_s + tid);   // this neuron's column of the weight tile
+    const int row_bytes = npb_pad * 2;
+    uint8_t *rp = (RASTER && live) ? raster + b * T * N + n : nullptr;
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int len = (int)min((long long)kLifTile, T - (long long)k * kLifTile);
+        bar_sync_named(1 + (k & 1), nthreads);                       // wait for the masks of tile k
+        if (live) {
+            const unsigned int *mk = masks + (k & 1) * kLifTile * W;
+#pragma unroll 1
+            for (int s0 = 0; s0 < len; s0 += 8) {
+                // (A) weighted input of 8 steps: per step a warp-uniform loop over the input events, one add
+                //     of an int16 weight each.  It does not depend on the neuron state, so its shared-memory
+                //     latency stays off the recurrence
+                int wsum[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int acc = 0;
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {
+                        unsigned int m = mk[(s0 + u) * W + q];       // the same word for the whole CTA: a broadcast
+                        while (m) {
+                            const int i = 31 - __clz(m);             // highest pending event
+                            m ^= 1u << i;
+                            int wv;
+                            asm("ld.shared.s16 %0, [%1];" : "=r"(wv) : "r"(wn_addr + (unsigned)((i + 32 * q) * row_bytes)));
+                            acc += wv;
+                        }
+                    }
+                    wsum[u] = acc;
+                }
+                // (B) the integer LIF recurrence of the 8 steps, state in registers
+                if (s0 + 8 <= len) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int ns = xylo_step<SAT_ISYN>(isyn, vmem, wsum[u], ds, dm, bs, th, th2, max_spikes);
+                        count += ns;
+                        if (RASTER) { *rp = (uint8_t)ns; rp += N; }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (s0 + u < len) {
+                            const int ns = xylo_step<SAT_ISYN>(isyn, vmem, wsum[u], ds, dm, bs, th, th2, max_spikes);
+                            count += ns;
+                            if (RASTER) { *rp = (uint8_t)ns; rp += N; }
+                        }
+                }
             }
         }
+        if (k + 2 < ntiles) bar_arrive_named(3 + (k & 1), nthreads); // buffer k&1 may be refilled (tile k+2)
     }
     if (live && counts) counts[b * N + n] = count;
 }
@@ -323,6 +384,7 @@ struct micloc_xylo {
     ChainParams p{};
     int F = 1, N = 0, G = 0, N_in = 0, CT = 0, nba = 0, max_spikes = 31;
     bool has_rec = false;
+    bool sat_isyn = true;           // I_syn can reach the int16 limits: keep the clamps
     float *d_taps = nullptr;        // float32 compacted STHT taps (fast front end)
     float *d_band_sos = nullptr;    // [F][kMaxSections][5]
     double *d_h = nullptr;          // [K] float64 STHT kernel (exact front end)
@@ -331,13 +393,22 @@ struct micloc_xylo {
     int16_t *d_thr = nullptr, *d_bias = nullptr;
     int8_t *d_ds = nullptr, *d_dm = nullptr;
     DevBuf q, qd, zd, signed_spk, counts, flags;
+    // float32 front end through the fused SNN kernel (one band, <= 8 microphones): its spike raster is
+    // exactly Demo.spike_encoding's signed raster; the neuron / power tail runs on a dummy 1-column bf_mat
+    bool use_fused = false;
+    ChainParams pf{};
+    double *d_Wd1 = nullptr;        // [2M][1] zeros
+    unsigned int *d_sm_slots = nullptr;
+    int sm_count = 148;
 };
+static constexpr size_t kXyloSlotWords = 320 + 16 * 1024;
 
 extern "C" int micloc_xylo_destroy(micloc_xylo *c) {
     if (!c) return MICLOC_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_taps); cudaFree(c->d_band_sos); cudaFree(c->d_h); cudaFree(c->d_ba_b); cudaFree(c->d_ba_a);
     cudaFree(c->d_w); cudaFree(c->d_thr); cudaFree(c->d_bias); cudaFree(c->d_ds); cudaFree(c->d_dm);
+    cudaFree(c->d_Wd1); cudaFree(c->d_sm_slots);
     c->q.release(); c->qd.release(); c->zd.release(); c->signed_spk.release(); c->counts.release(); c->flags.release();
     delete c;
     return MICLOC_OK;
@@ -409,11 +480,35 @@ extern "C" int micloc_xylo_create(const micloc_xylo_config *cfg, int device, mic
         std::vector<int16_t> w16((size_t)N_in * N);
         for (size_t i = 0; i < w16.size(); ++i) w16[i] = (int16_t)((int)cfg->w_in[i] << cfg->weight_shift_in);
         rc = upload(&c->d_w, w16.data(), w16.size());
+        // |I_syn| <= 2^dash_syn * (sum_i |w_i| + 1) by induction over the decay recurrence
+        c->sat_isyn = false;
+        for (int n = 0; n < N && !c->sat_isyn; ++n) {
+            long long sabs = 1;
+            for (int i = 0; i < N_in; ++i) sabs += w16[(size_t)i * N + n] < 0 ? -w16[(size_t)i * N + n] : w16[(size_t)i * N + n];
+            if ((sabs << cfg->dash_syn[n]) > 32767) c->sat_isyn = true;
+        }
     }
     if (!rc) rc = upload(&c->d_thr, cfg->threshold, (size_t)N);
     if (!rc) rc = upload(&c->d_ds, cfg->dash_syn, (size_t)N);
     if (!rc) rc = upload(&c->d_dm, cfg->dash_mem, (size_t)N);
     if (!rc && cfg->bias) rc = upload(&c->d_bias, cfg->bias, (size_t)N);
+    if (!rc) {
+        c->pf = p;
+        c->pf.G = 1;
+        if (c->pf.nsec == 1) {      // identity second section: y = 1*x + 0 exactly
+            c->pf.nsec = 2;
+            c->pf.sos[1][0] = 1.f; c->pf.sos[1][1] = c->pf.sos[1][2] = c->pf.sos[1][3] = c->pf.sos[1][4] = 0.f;
+        }
+        c->use_fused = c->F == 1 && fused_supported(c->pf);
+        if (c->use_fused) {
+            std::vector<double> z((size_t)p.C2, 0.0);
+            rc = upload(&c->d_Wd1, z.data(), z.size());
+            if (!rc && (cudaMalloc(&c->d_sm_slots, kXyloSlotWords * sizeof(unsigned int)) != cudaSuccess ||
+                        cudaMemset(c->d_sm_slots, 0, kXyloSlotWords * sizeof(unsigned int)) != cudaSuccess))
+                rc = set_error(MICLOC_ERR_CUDA, "cudaMalloc(sm_slots) failed");
+            cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+        }
+    }
     if (rc) { micloc_xylo_destroy(c); return rc; }
     *out = c;
     return MICLOC_OK;
@@ -434,16 +529,17 @@ static int launch_lif(micloc_xylo *c, const int8_t *spikes, long long B, long lo
     const int N = c->N;
     const int nchunks = (N + 479) / 480;                       // <= 480 neurons (15 warps) per CTA
     const int npb = (N + nchunks - 1) / nchunks;
-    const int threads = (npb + 31) & ~31;
+    const int threads = ((npb + 31) & ~31) + 32;             // neuron warps + the producer warp
     const int W = (c->N_in + 31) / 32;
     const int npb_pad = (npb + 7) & ~7;
     const int row = SIGNED_IN ? c->CT : c->N_in;
-    const size_t smem = (((size_t)c->N_in * npb_pad * 2 + 15) & ~(size_t)15) + (size_t)kLifTile * W * 4 + (size_t)kLifTile * row + 16;
+    const size_t smem = (((size_t)c->N_in * npb_pad * 2 + 15) & ~(size_t)15) + (size_t)2 * kLifTile * W * 4 + (size_t)kLifTile * row + 16;
     if (smem > 227 * 1024) return set_error(MICLOC_ERR_UNSUPPORTED, "LIF kernel needs %zu B of shared memory", smem);
     dim3 grid((unsigned)B, (unsigned)nchunks);
 #define MICLOC_LIF_CASE(WW)                                                                                       \
     case WW: {                                                                                                    \
-        auto kern = k_xylo_lif<SIGNED_IN, WW>;                                                                    \
+        auto kern = raster ? (c->sat_isyn ? k_xylo_lif<SIGNED_IN, WW, true, true> : k_xylo_lif<SIGNED_IN, WW, false, true>)   \
+                           : (c->sat_isyn ? k_xylo_lif<SIGNED_IN, WW, true, false> : k_xylo_lif<SIGNED_IN, WW, false, false>); \
         MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         kern<<<grid, threads, smem, st>>>(spikes, c->CT, c->p.bipolar, c->N_in, c->d_w, c->d_thr, c->d_ds, c->d_dm, \
                                           c->d_bias, c->max_spikes, N, npb, T, raster, counts);                   \
@@ -499,9 +595,8 @@ extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int
     if (exact) {
         MICLOC_TRY(c->qd.reserve((size_t)chunk * T * p.M * sizeof(double)));
         MICLOC_TRY(c->zd.reserve((size_t)chunk * T * CT * sizeof(double)));
-    } else {
-        MICLOC_TRY(c->q.reserve((size_t)chunk * T * p.M * sizeof(float)));
     }
+    bool fused_front = !exact && c->use_fused && !getenv("MICLOC_XYLO_STAGED_FRONT");
     const size_t esz = dtype == MICLOC_I16 ? 2 : 4;
     for (long long b0 = 0; b0 < B; b0 += chunk) {
         const long long nb = B - b0 < chunk ? B - b0 : chunk;
@@ -528,8 +623,19 @@ extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int
             MICLOC_CUDA(cudaGetLastError());
             MICLOC_TRY(micloc_rzcc_encode_f64((const double *)c->zd.ptr, nb, T, CT, p.w, p.bipolar, sgn, c->device, st));
         } else {
-            MICLOC_TRY(launch_stht_any(p, c->d_taps, a, dtype, (float *)c->q.ptr, nb, T, st));
-            MICLOC_TRY(launch_chain_any(p, a, dtype, (const float *)c->q.ptr, c->d_band_sos, c->F, nullptr, sgn, flg + b0, nb, T, st));
+            bool done = false;
+            if (fused_front) {
+                const int rcf = launch_fused(c->pf, c->d_taps, c->d_Wd1, a, dtype, nb, T, sgn, nullptr, nullptr, flg + b0,
+                                             c->d_sm_slots, c->sm_count, st);
+                if (rcf == MICLOC_OK) done = true;
+                else if (rcf != MICLOC_ERR_UNSUPPORTED) return rcf;
+                else fused_front = c->use_fused = false;   // e.g. a robust_width beyond the fused kernel's spike ring
+            }
+            if (!done) {
+                MICLOC_TRY(c->q.reserve((size_t)chunk * T * p.M * sizeof(float)));
+                MICLOC_TRY(launch_stht_any(p, c->d_taps, a, dtype, (float *)c->q.ptr, nb, T, st));
+                MICLOC_TRY(launch_chain_any(p, a, dtype, (const float *)c->q.ptr, c->d_band_sos, c->F, nullptr, sgn, flg + b0, nb, T, st));
+            }
         }
         if (spikes_in_dev) {
             const long long rows = nb * T;
