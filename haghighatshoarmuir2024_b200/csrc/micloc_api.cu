@@ -43,8 +43,6 @@ extern "C" int64_t micloc_launch_count(void) { return g_launches.load(); }
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
-static constexpr size_t kSlotWords = 320 + 16 * 1024;
-
 struct micloc_snn {
     int device = 0;
     ChainParams p{};
@@ -105,6 +103,7 @@ int micloc::setup_stht(ChainParams &p, const double *h, int K, float **d_taps) {
     p.K = K; p.half = K / 2;
     p.tap_stride = stride; p.tap_first = first; p.n_taps = npad;
     p.span = first + stride * (npad - 1);
+    p.fir_split = ((npad / kFirJB + 5) / 6 * 6) / 2;      // half of the block count rounded up to a multiple of 6
     MICLOC_CUDA(cudaMalloc(d_taps, npad * sizeof(float)));
     MICLOC_CUDA(cudaMemcpy(*d_taps, taps.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
     return MICLOC_OK;
@@ -192,21 +191,21 @@ extern "C" int micloc_snn_set_bf(micloc_snn *c, const double *bf, int32_t G) {
 // Debug: busy cycles per warp role of the fused kernel (FIR slot 0, FIR slot 1, front, neuron) and
 // the number of warps that reported, summed since the previous call; all zero unless the library
 // was built with -DMICLOC_ROLE_TIMING.
-extern "C" int micloc_snn_debug_counters(micloc_snn *c, uint64_t out[16]) {
+extern "C" int micloc_snn_debug_counters(micloc_snn *c, uint64_t out[32]) {
     if (!c || !out) return set_error(MICLOC_ERR_CONFIG, "null argument");
     MICLOC_CUDA(cudaSetDevice(c->device));
     MICLOC_CUDA(cudaDeviceSynchronize());
-    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + 256, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    MICLOC_CUDA(cudaMemset(c->d_sm_slots + 256, 0, 16 * sizeof(uint64_t)));
+    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + kSlotDbg, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    MICLOC_CUDA(cudaMemset(c->d_sm_slots + kSlotDbg, 0, 32 * sizeof(uint64_t)));
     return MICLOC_OK;
 }
 
 // Debug: (start ns, end ns, SM id, role rotation, busy cycles of the 4 roles) of the first `n` CTAs of the last fused launch (MICLOC_ROLE_TIMING builds).
 extern "C" int micloc_snn_debug_cta_times(micloc_snn *c, uint64_t *out, int32_t n) {
-    if (!c || !out || n < 1 || n > 1024) return set_error(MICLOC_ERR_CONFIG, "bad argument");
+    if (!c || !out || n < 1 || n > 512) return set_error(MICLOC_ERR_CONFIG, "bad argument");
     MICLOC_CUDA(cudaSetDevice(c->device));
     MICLOC_CUDA(cudaDeviceSynchronize());
-    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + 320, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    MICLOC_CUDA(cudaMemcpy(out, c->d_sm_slots + kSlotCta, (size_t)n * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return MICLOC_OK;
 }
 

@@ -43,6 +43,18 @@ struct DevBuf {
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
 };
 
+// Layout of the fused kernel's per-context counter block (32-bit words, device memory):
+//   [0, 1024)            FIR warps placed per (SM, sub-partition): word 4*smid + smsp   (reset per launch)
+//   [kSlotPair]          dynamic clip-pair counter                                      (reset per launch)
+//   (kSlotPair, kSlotDbg) CTAs arrived per SM                                            (reset per launch)
+//   [kSlotDbg, +64)      32 x 64-bit debug counters (MICLOC_ROLE_TIMING builds)
+//   [kSlotCta, ...)      16 x 64-bit words per CTA for the first 512 CTAs (MICLOC_ROLE_TIMING builds)
+constexpr int kSlotPair = 1024;
+constexpr int kSlotDbg = 1280;
+constexpr int kSlotCta = 1536;
+constexpr size_t kSlotWords = kSlotCta + 2 * 16 * 512;
+constexpr int kSlotResetWords = kSlotDbg;
+
 int setup_stht(ChainParams &p, const double *h, int K, float **d_taps);
 int sos_to_f32(const double *sos, int nsec, float *out);
 int launch_stht_any(const ChainParams &p, const float *d_taps, const void *audio, int dtype, float *q,

@@ -4,25 +4,33 @@
 // Reference sites: micloc/snn_beamformer.py:283-370 and the callers' power/argmax
 // paper_plots/target_snn_localization.py:462-464.
 //
-// One persistent CTA of four warps owns kSlots = 2 clips at a time and walks them
-// in time tiles of kTile = 64 samples.  The warps are specialised and run as a
-// software pipeline, one barrier per tile (iteration k):
+// One persistent CTA of eight warps owns kSlots = 2 clips at a time and walks them in time tiles
+// of kTile = 64 samples.  The warps are specialised BY FUNCTION (every role serves both clips with
+// all its lanes, so that the serial depth of each role per tile is short) and run as a software
+// pipeline, one barrier per tile (iteration k):
 //
-//   FIR warps   tile k+1   audio (HBM) -> mic-major ring in shared memory (each warp its own clip)
-//               tile k     STHT quadrature FIR: every lane owns 16 consecutive outputs of one
-//                          microphone and walks the 240 non-zero Hilbert taps in blocks of 8 with
-//                          a sliding register window; the multiply-adds are packed FFMA2
-//                          (fma.rn.f32x2)
-//               tile k-4   Gram accumulation C += v v^T of the membrane tile the neuron warp
-//                          finished in this step (named barrier), FFMA2 on 4x4 blocks
-//   front warp  tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
-//                          sign / zero bit masks; every 32 samples the masks are turned into RZCC
-//                          candidates and resolved (find_peaks distance rule) into a bit-packed
-//                          spike ring
-//   neuron warp tile k-4   (the latency of the exact find_peaks decision) one lane per (clip,
-//                          channel): alpha-kernel neuron recurrences driven by the final spike
-//                          bits -> membrane tile, and the int8 spike raster of the tile -> HBM
-//   clip end               power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
+//   FIR warps x4 tile k+1   audio (HBM) -> mic-major ring in shared memory (two warps per clip, 32
+//                           samples each)
+//                tile k     STHT quadrature FIR: every lane owns 16 consecutive outputs of one
+//                           microphone and walks HALF of the 240 non-zero Hilbert taps (the two warps
+//                           of a clip split the tap range; the band-pass warp adds the two partial
+//                           sums) in blocks of 8 with a sliding register window; the multiply-adds
+//                           are packed FFMA2 (fma.rn.f32x2)
+//   band-pass    tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
+//                           sign / zero bit masks of every 32-sample segment -> shared memory
+//   RZCC         tile k-2   one lane per (clip, channel): the masks are turned into RZCC
+//                           candidates and resolved (find_peaks distance rule) into a bit-packed
+//                           spike ring
+//   neuron       tile k-d   (d = the latency of the exact find_peaks decision) one lane per (clip,
+//                           channel): alpha-kernel neuron recurrences driven by the final spike
+//                           bits -> membrane tile + int8 spike tile in shared memory
+//   Gram         tile k-d-1 C += v v^T of the membrane tile (FFMA2 on 4x4 blocks), int8 spike
+//                           raster of the tile -> HBM
+//   clip end                power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
+//
+// Two CTAs are resident per SM; the FIR roles go to the warps whose SM sub-partition holds the
+// fewest FIR warps so far, so that every sub-partition's FMA pipe always has two FIR warps to
+// keep it busy (one alone leaves it idle whenever it loses an issue slot to another warp).
 #include <cuda_runtime.h>
 
 #include "micloc_common.h"
@@ -34,17 +42,20 @@ constexpr int kSlots = 2;      // clips per CTA
 constexpr int kRows = 8;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmPitch = 32;   // floats per time step in the membrane tile: [slot][16]
-constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
+constexpr int kRingWords = 32; // spike-bit ring: 32 words of 32 samples per channel and polarity
+constexpr int kWarps = 8;      // 4 x FIR (clip slot x tap half), band-pass, RZCC, neuron, Gram
+constexpr int kFirWarps = 4;
+constexpr int kThreads = kWarps * 32;
 constexpr int kGramFlush = 8;  // tiles of float32 Gram accumulation between two folds into float64
 
 struct FusedGeom {
     int ring_x;      // audio ring length in samples (multiple of 32)
     int pitch_x;     // floats per ring row; pitch_x / 4 is odd (conflict-free LDS.128 across microphones)
     int shift;       // ring coordinate of sample t is (t + shift) mod ring_x
-    int nblk;        // FIR tap blocks of 8 (multiple of 3)
-    int dtile;       // the back warp runs dtile tiles behind the pipeline step (RZCC decision latency)
+    int nblk;        // FIR tap blocks of 8 (multiple of 6: two halves walked in groups of three)
+    int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
-    int off_x, off_q, off_vm, off_is, off_cs, off_clus, off_bits, off_stage, off_gacc;   // byte offsets in dynamic smem
+    int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_gacc, off_zero;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
@@ -95,8 +106,9 @@ __device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Ch
 // All four warps meet here once per pipeline step (the roles run different code).
 __device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// Optional role timing (MICLOC_ROLE_TIMING): busy cycles of each warp role between barriers,
-// summed into sm_slots[256 + 2*role] (64-bit) by lane 0; read back by micloc_snn_debug_counters.
+// Optional role timing (MICLOC_ROLE_TIMING): busy cycles of each warp role between barriers, summed into
+// the 64-bit counters at sm_slots[kSlotDbg] (busy of roles 0..7, then the number of warps that reported
+// each) by lane 0; read back by micloc_snn_debug_counters.
 #ifdef MICLOC_ROLE_TIMING
 __device__ __forceinline__ long long rt_clock() {
     long long t;
@@ -117,44 +129,40 @@ struct RoleTimer {
     }
     __device__ __forceinline__ void flush(unsigned int *sm_slots, int role, int lane) {
         if (lane == 0) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + 256) + role, (unsigned long long)busy);
-            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + 256) + 4 + role, 1ull);
-            if (blockIdx.x < 1024)
-                (reinterpret_cast<unsigned long long *>(sm_slots + 320) + 8 * blockIdx.x)[4 + role] = (unsigned long long)busy;
+            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg) + role, (unsigned long long)busy);
+            atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg) + 8 + role, 1ull);
+            if (blockIdx.x < 512)
+                (reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * blockIdx.x)[4 + role] = (unsigned long long)busy;
         }
     }
 };
 #define ROLE_TIMER_DECL RoleTimer rt_; rt_.start()
 #define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(); rt_.after_barrier(); } while (0)
 #define ROLE_TIMER_FLUSH(role) rt_.flush(sm.dbg, role, lane)
-#define PHASE_DECL long long ph_[6] = {0, 0, 0, 0, 0, 0}, pht_ = rt_clock()
-#define PHASE_MARK(i) do { const long long n_ = rt_clock(); ph_[i] += n_ - pht_; pht_ = n_; } while (0)
-#define PHASE_FLUSH() do { if (lane == 0) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(reinterpret_cast<unsigned long long *>(sm.dbg + 256) + 8 + i_, (unsigned long long)ph_[i_]); } while (0)
 #else
-#define PHASE_DECL
-#define PHASE_MARK(i)
-#define PHASE_FLUSH()
 #define ROLE_TIMER_DECL
 #define ROLE_BARRIER() tile_barrier()
 #define ROLE_TIMER_FLUSH(role)
 #endif
 
 struct FusedSmem {
-    float *taps, *xs, *qs, *vms, *is_s, *cs;
+    float *taps, *xs, *qs, *vms, *is_s, *cs, *zero;
+    unsigned int *seg;      // [2 tiles][kTile/kSeg][3: neg mask, zero mask, carry][32 lanes]: band-pass -> RZCC hand-over
     int *clus;
     unsigned int *bits;     // [2 polarities][kRingWords][32 lanes]
-    int8_t *stage;          // [kSlots][kTile][C2]
+    int8_t *stage;          // [2 tiles][kSlots][kTile][C2]
     double *gram;           // [kSlots][16][16], clip epilogue only (reuses the audio rings)
     double *gacc;           // [kSlots][10 block pairs][16] float64 Gram accumulators
     unsigned int *dbg;      // sm_slots (debug counters behind the first 256 entries)
 };
+constexpr int kSegsPerTile = kTile / kSeg;
 
 // ======= FIR warp (one per clip slot): audio tile k+1 -> ring, STHT FIR of tile k =======
 
 template <typename IN_T, int MM>
 __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
                                          const IN_T *__restrict__ audio, long long clip, bool clip_ok, long long T64,
-                                         int slot, int lane, int NT, int k_last) {
+                                         int slot, int half, int lane, int NT, int k_last) {
     const int M = MM ? MM : p.M;
     const int T = (int)T64;
     const int f_chunk = lane >> 3, f_mic = lane & 7;     // FIR lanes: lane = chunk * 8 + mic
@@ -162,94 +170,80 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
     const float *row = sm.xs + (slot * M + f_mic) * g.pitch_x;
     const IN_T *src = audio + (clip_ok ? clip : 0) * T64 * M;
     float *rows_w = sm.xs + slot * M * g.pitch_x;
-    // this lane's first sample of the tile being filled (tile 0 at k = -1): time, frame, ring coordinate
-    int fill_t = lane;
-    const IN_T *fill_src = src + (lane < T ? lane * M : 0);
-    int fill_c = (lane + g.shift) % g.ring_x;
+    const int nb2 = g.nblk / 2;                          // tap blocks of this warp: [half * nb2, (half + 1) * nb2)
+    // this lane's sample of the tile being filled (tile 0 at k = -1): the warp fills samples [32*half, 32*half + 32)
+    int fill_t = lane + 32 * half;
+    const IN_T *fill_src = src + (fill_t < T ? fill_t * M : 0);
+    int fill_c = (fill_t + g.shift) % g.ring_x;
+    // ring coordinate of this lane's window of the warp's first tap block at tile 0, kept incrementally
+    int c0 = ((16 * f_chunk - p.tap_first - 14 + g.shift - 16 * half * nb2) % g.ring_x + g.ring_x) % g.ring_x;
     ROLE_TIMER_DECL;
-    PHASE_DECL;
-    unsigned long long a2[8];       // float32 Gram partial sums of this lane's block pair and time slice
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a2[i] = 0ull;
 
     for (int k = -1; k <= k_last; ++k) {
-        // (a) audio tile k+1 -> mic-major ring: every lane moves whole frames (all microphones of one
+        // (a) audio tile k+1 -> mic-major ring: every lane moves one whole frame (all microphones of one
         //     sample); the loads are issued here and stored after the FIR so that their latency is hidden
         const int kf = k + 1;
         const bool filling = kf < NT && clip_ok;
-        float v[kTile / 32][kRows];
+        float v[kRows];
         if (filling) {
+            const bool ok = fill_t < T;
 #pragma unroll
-            for (int h = 0; h < kTile / 32; ++h) {
-                const bool ok = fill_t + 32 * h < T;
-                const IN_T *fr = fill_src + (ok ? 32 * h * M : 0);
-#pragma unroll
-                for (int m = 0; m < kRows; ++m) v[h][m] = (ok && m < M) ? to_f32<IN_T>(fr[m]) : 0.f;
-            }
+            for (int m = 0; m < kRows; ++m) v[m] = (ok && m < M) ? to_f32<IN_T>(fill_src[m]) : 0.f;
         }
-        PHASE_MARK(0);
-        // (b) STHT quadrature FIR of tile k
-        if (work && k >= 0 && k < NT) {
-            unsigned long long acc[8];
+        // (b) this warp's half of the STHT quadrature FIR of tile k
+        if (k >= 0 && k < NT) {
+            if (work) {
+                unsigned long long acc[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0ull;
-            // ring coordinate of the window of tap block 0 (a multiple of 16 by the choice of shift)
-            const int c0 = (k * kTile + 16 * f_chunk - p.tap_first - 14 + g.shift + 2 * g.ring_x) % g.ring_x;
-            Chunk A, Bq, Cq;
-            { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
-            load_chunk(A, row, c0);
-            int cn = c0 - 16; if (cn < 0) cn += g.ring_x;
-            // window chunks and taps are fetched one block ahead of their use
-            const float *tp = sm.taps;
-            Taps8 t0, t1;
-            load_taps(t0, tp);
+                for (int i = 0; i < 8; ++i) acc[i] = 0ull;
+                Chunk A, Bq, Cq;
+                { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
+                load_chunk(A, row, c0);
+                int cn = c0 - 16; if (cn < 0) cn += g.ring_x;
+                // window chunks and taps are fetched one block ahead of their use
+                const float *tp = sm.taps + 8 * half * nb2;
+                Taps8 t0, t1;
+                load_taps(t0, tp);
 #pragma unroll 1
-            for (int jb = 0; jb < g.nblk; jb += 3) {
-                load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                load_taps(t1, tp + 8);
-                fir_block(acc, A, Bq, t0);
-                load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                load_taps(t0, tp + 16);
-                fir_block(acc, Cq, A, t1);
-                load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
-                load_taps(t1, tp + 24);                 // first block of the next round (zero padding behind the last)
-                fir_block(acc, Bq, Cq, t0);
-                t0 = t1;
-                tp += 24;
-            }
-            float *dst = sm.qs + (((k & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
+                for (int jb = 0; jb < nb2; jb += 3) {
+                    load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                    load_taps(t1, tp + 8);
+                    fir_block(acc, A, Bq, t0);
+                    load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                    load_taps(t0, tp + 16);
+                    fir_block(acc, Cq, A, t1);
+                    load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                    load_taps(t1, tp + 24);             // first block of the next round (zero padding behind the last)
+                    fir_block(acc, Bq, Cq, t0);
+                    t0 = t1;
+                    tp += 24;
+                }
+                float *dst = sm.qs + ((((k & 1) * 2 + half) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                float4 o;
-                unpack2(acc[2 * v], o.x, o.y);
-                unpack2(acc[2 * v + 1], o.z, o.w);
-                reinterpret_cast<float4 *>(dst)[v] = o;
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    float4 o;
+                    unpack2(acc[2 * v4], o.x, o.y);
+                    unpack2(acc[2 * v4 + 1], o.z, o.w);
+                    reinterpret_cast<float4 *>(dst)[v4] = o;
+                }
             }
+            c0 += kTile; if (c0 >= g.ring_x) c0 -= g.ring_x;
         }
-        PHASE_MARK(1);
         if (filling) {
 #pragma unroll
-            for (int h = 0; h < kTile / 32; ++h) {
-                int c = fill_c + 32 * h; if (c >= g.ring_x) c -= g.ring_x;
-#pragma unroll
-                for (int m = 0; m < kRows; ++m)
-                    if (m < M) rows_w[m * g.pitch_x + c] = v[h][m];
-            }
-            // next tile: time, source frame and ring coordinate of this lane's first sample
+            for (int m = 0; m < kRows; ++m)
+                if (m < M) rows_w[m * g.pitch_x + fill_c] = v[m];
+            // next tile: time, source frame and ring coordinate of this lane's sample
             fill_t += kTile;
             fill_src += (fill_t < T ? kTile * M : 0);
             fill_c += kTile; if (fill_c >= g.ring_x) fill_c -= g.ring_x;
         }
-        PHASE_MARK(2);
-        PHASE_MARK(4);
         ROLE_BARRIER();
-        PHASE_MARK(5);
     }
-    ROLE_TIMER_FLUSH(slot);
-    PHASE_FLUSH();
+    ROLE_TIMER_FLUSH(2 * slot + half);
 }
 
-// ============ front warp: band-pass + RZCC -> spike bits, lane = slot*16 + channel ============
+// ============ band-pass warp: SOS cascade + running sum + sign / zero masks, lane = slot*16 + channel ============
 // two biquads, direct form II transposed, coefficients in registers
 struct Sos2 { float b0[2], b1[2], b2[2], a1[2], a2[2]; };
 __device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, float x) {
@@ -264,25 +258,16 @@ __device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, fl
 }
 
 template <typename IN_T, int MM>
-__device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                           const IN_T *__restrict__ audio, int32_t *__restrict__ flags,
-                                           long long clip0, long long B, long long T64, int lane, int k_last) {
+__device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                              const IN_T *__restrict__ audio, long long clip0, long long B,
+                                              long long T64, int lane, int k_last) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
     const int c_slot = lane >> 4, c_ch = lane & 15;
     const bool slot_ok = clip0 + c_slot < B;
     const bool c_valid = c_ch < C2 && slot_ok;
     const bool c_inphase = c_ch < M;
-    const int w = p.w, bipolar = p.bipolar;
-    const RzccStore store{sm.clus + lane, reinterpret_cast<float *>(sm.clus + 2 * kClusterMax * 32) + lane, 32};
-    unsigned int *bits = sm.bits + lane;
-    // a final spike: set its bit in this channel's ring word (only this lane ever writes these words)
-    auto emit = [&](int pos, int sign) {
-        unsigned int *wd = bits + ((sign > 0 ? kRingWords : 0) + ((pos >> 5) & (kRingWords - 1))) * 32;
-        *wd |= 1u << (pos & 31);
-    };
     const IN_T *clip_audio = audio + (slot_ok ? clip0 + c_slot : clip0) * T64 * M;
-    float *cs = sm.cs + lane;
     Sos2 sos;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -290,7 +275,9 @@ __device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParam
         sos.a1[k] = p.sos[k][3]; sos.a2[k] = p.sos[k][4];
     }
     BiquadState bq; biquad_reset(bq);
-    RzccState rz; rzcc_reset(rz);
+    float csum = 0.f;
+    // ring coordinate of the in-phase sample x[ts - K/2] of the next segment (warp-uniform, kept incrementally)
+    int cin_u = ((g.shift - p.half) % g.ring_x + g.ring_x) % g.ring_x;
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
@@ -315,120 +302,138 @@ __device__ __forceinline__ void front_role(const FusedSmem &sm, const ChainParam
                 }
                 __syncwarp();
             }
-            if (c_valid) {
 #pragma unroll 1
-                for (int sg = 0; sg < kTile / kSeg; ++sg) {
-                    const int ts = t0 + sg * kSeg;            // first sample of this segment
-                    if (ts >= T) break;
-                    const float *xp;
-                    int stride = 1, wrap_at = kSeg;
-                    if (!c_inphase) {
-                        xp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
-                    } else if (from_is) {
-                        xp = sm.is_s + c_slot * kTile * M + sg * kSeg * M + c_ch;
-                        stride = M;
-                    } else {
-                        const int cin = (ts - p.half + g.shift) % g.ring_x;
-                        xp = sm.xs + (c_slot * M + c_ch) * g.pitch_x + cin;
-                        wrap_at = g.ring_x - cin;
-                    }
-                    // this segment's words of the spike-bit ring start empty
-                    bits[((ts >> 5) & (kRingWords - 1)) * 32] = 0u;
-                    bits[(kRingWords + ((ts >> 5) & (kRingWords - 1))) * 32] = 0u;
-                    // (warp-uniform) no lane wraps around the audio ring inside this segment
-                    const int cin_u = (ts - p.half + g.shift + g.ring_x) % g.ring_x;
-                    const bool fast = !from_is && ts + kSeg <= T && cin_u + kSeg <= g.ring_x;
-                    const float carry = rz.csum;
-                    unsigned int neg = 0u, zero = 0u;
-                    float csum = carry;
-                    int nvalid = kSeg;
-                    if (fast) {
-                        float xn[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) xn[i] = xp[i];
-#pragma unroll 1
-                        for (int o = 0; o < kSeg / 8; ++o) {
-                            float xc[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) xc[i] = xn[i];
-                            if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i];
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float z = biquad2_step(sos, bq, xc[i]);
-                                csum += z;
-                                cs[(8 * o + i) * 32] = csum;
-                                neg = __funnelshift_l(__float_as_uint(z), neg, 1);
-                                zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
-                            }
-                        }
-                    } else {
-                        nvalid = T - ts < kSeg ? T - ts : kSeg;
-#pragma unroll 1
-                        for (int i = 0; i < nvalid; ++i) {
-                            if (i == wrap_at) xp -= g.ring_x;
-                            const float z = biquad2_step(sos, bq, xp[i * stride]);
-                            csum += z;
-                            cs[i * 32] = csum;
-                            neg |= (__float_as_uint(z) >> 31) << (31 - i);
-                            zero |= (z == 0.f ? 1u : 0u) << (31 - i);
-                        }
-                    }
-                    rz.csum = csum;
-                    rzcc_segment_masks(rz, store, bipolar, w, ts, nvalid, neg, zero, cs, 32, carry, emit);
-                    const bool last = ts + kSeg >= T;
-                    rzcc_close(rz, store, w, last ? T - 1 : ts + kSeg - 1, last, emit);
+            for (int sg = 0; sg < kSegsPerTile; ++sg) {
+                const int ts = t0 + sg * kSeg;            // first sample of this segment
+                float *cs = sm.cs + ((kc & 1) * kSegsPerTile + sg) * kSeg * 32 + lane;
+                unsigned int *sgm = sm.seg + ((kc & 1) * kSegsPerTile + sg) * 3 * 32 + lane;
+                const int cin = cin_u;                    // ring coordinate of x[ts - K/2]
+                cin_u += kSeg; if (cin_u >= g.ring_x) cin_u -= g.ring_x;
+                if (ts >= T || !c_valid) continue;
+                const float *xp, *xp2 = sm.zero;         // quadrature = sum of the two FIR warps' partial sums
+                int stride = 1, wrap_at = kSeg;
+                if (!c_inphase) {
+                    xp = sm.qs + ((((kc & 1) * 2 + 0) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
+                    xp2 = sm.qs + ((((kc & 1) * 2 + 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
+                } else if (from_is) {
+                    xp = sm.is_s + c_slot * kTile * M + sg * kSeg * M + c_ch;
+                    stride = M;
+                } else {
+                    xp = sm.xs + (c_slot * M + c_ch) * g.pitch_x + cin;
+                    wrap_at = g.ring_x - cin;
                 }
+                // (warp-uniform) no lane wraps around the audio ring inside this segment
+                const bool fast = !from_is && ts + kSeg <= T && cin + kSeg <= g.ring_x;
+                const float carry = csum;
+                unsigned int neg = 0u, zero = 0u;
+                if (fast) {
+                    float xn[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xn[i] = xp[i] + xp2[i];
+#pragma unroll 1
+                    for (int o = 0; o < kSeg / 8; ++o) {
+                        float xc[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xc[i] = xn[i];
+                        if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i] + xp2[8 * (o + 1) + i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float z = biquad2_step(sos, bq, xc[i]);
+                            csum += z;
+                            cs[(8 * o + i) * 32] = csum;
+                            neg = __funnelshift_l(__float_as_uint(z), neg, 1);
+                            zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
+                        }
+                    }
+                } else {
+                    const int nvalid = T - ts < kSeg ? T - ts : kSeg;
+#pragma unroll 1
+                    for (int i = 0; i < nvalid; ++i) {
+                        if (i == wrap_at) xp -= g.ring_x;
+                        const float z = biquad2_step(sos, bq, xp[i * stride] + xp2[i]);
+                        csum += z;
+                        cs[i * 32] = csum;
+                        neg |= (__float_as_uint(z) >> 31) << (31 - i);
+                        zero |= (z == 0.f ? 1u : 0u) << (31 - i);
+                    }
+                }
+                sgm[0] = neg; sgm[32] = zero; sgm[64] = __float_as_uint(carry);
             }
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(2);
+    ROLE_TIMER_FLUSH(4);
+}
+
+// ============ RZCC warp: masks of tile k-2 -> candidates -> clusters -> spike bits, lane = slot*16 + channel ============
+__device__ __forceinline__ void rzcc_role(const FusedSmem &sm, const ChainParams &p, int32_t *__restrict__ flags,
+                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
+    const int C2 = 2 * MMv;
+    const int T = (int)T64;
+    const int c_slot = lane >> 4, c_ch = lane & 15;
+    const bool c_valid = c_ch < C2 && clip0 + c_slot < B;
+    const int w = p.w, bipolar = p.bipolar;
+    const RzccStore store{sm.clus + lane, reinterpret_cast<float *>(sm.clus + 2 * kClusterMax * 32) + lane, 32};
+    unsigned int *bits = sm.bits + lane;
+    // a final spike: set its bit in this channel's ring word (only this lane ever writes these words)
+    auto emit = [&](int pos, int sign) {
+        unsigned int *wd = bits + ((sign > 0 ? kRingWords : 0) + ((pos >> 5) & (kRingWords - 1))) * 32;
+        *wd |= 1u << (pos & 31);
+    };
+    RzccState rz; rzcc_reset(rz);
+    ROLE_TIMER_DECL;
+
+    for (int k = -1; k <= k_last; ++k) {
+        const int kr = k - 2;
+        const int t0 = kr * kTile;
+        if (kr >= 0 && t0 < T && c_valid) {
+#pragma unroll 1
+            for (int sg = 0; sg < kSegsPerTile; ++sg) {
+                const int ts = t0 + sg * kSeg;
+                if (ts >= T) break;
+                // this segment's words of the spike-bit ring start empty
+                bits[((ts >> 5) & (kRingWords - 1)) * 32] = 0u;
+                bits[(kRingWords + ((ts >> 5) & (kRingWords - 1))) * 32] = 0u;
+                const float *cs = sm.cs + ((kr & 1) * kSegsPerTile + sg) * kSeg * 32 + lane;
+                const unsigned int *sgm = sm.seg + ((kr & 1) * kSegsPerTile + sg) * 3 * 32 + lane;
+                const unsigned int neg = sgm[0], zero = sgm[32];
+                const float carry = __uint_as_float(sgm[64]);
+                const int nvalid = T - ts < kSeg ? T - ts : kSeg;
+                rzcc_segment_masks(rz, store, bipolar, w, ts, nvalid, neg, zero, cs, 32, carry, emit);
+                const bool last = ts + kSeg >= T;
+                rzcc_close(rz, store, w, last ? T - 1 : ts + kSeg - 1, last, emit);
+            }
+        }
+        ROLE_BARRIER();
+    }
+    ROLE_TIMER_FLUSH(5);
     if (c_valid && rz.overflow && flags) atomicOr(flags + clip0 + c_slot, 1);
 }
 
-// ==== neuron warp: alpha-kernel recurrences + int8 spike write-out of tile k - dtile, lane = slot*16 + channel ====
-template <int MM>
+// ==== neuron warp: alpha-kernel recurrences of tile k - dtile -> membrane tile + int8 spike tile, lane = slot*16 + channel ====
 __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                            int8_t *__restrict__ spikes, long long clip0, long long B, long long T64,
-                                            int lane, int k_last) {
-    const int M = MM ? MM : p.M, C2 = 2 * M;
+                                            long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
+    const int C2 = 2 * MMv;
     const int T = (int)T64;
     const int c_slot = lane >> 4, c_ch = lane & 15;
     const bool c_valid = c_ch < C2 && clip0 + c_slot < B;
     const unsigned int *bits = sm.bits + lane;
-    int8_t *stg = sm.stage + c_slot * kTile * C2 + c_ch;
-    float *vmo = sm.vms + lane;
     const float na = p.na, nc = p.nc, ncT = p.ncT, nLf = p.nLf;
     const int nL = p.nL;
     NeuronState nr; neuron_reset(nr);
-    // Gram lanes: lane = slot * 10 + upper-triangular 4x4 block pair of the slot's 16x16 matrix
-    const int g_slot = lane / 10;
-    int g_bi = 0, g_bj = 0;
-    {
-        int pr = lane % 10;
-        for (int r = 0; r < 4; ++r) {
-            const int len = 4 - r;
-            if (pr < len) { g_bi = r; g_bj = r + pr; break; }
-            pr -= len;
-        }
-    }
-    const bool g_lane = lane < 10 * kSlots;
-    double *gacc = sm.gacc + lane * 16;
-    unsigned long long a2[8];       // float32 Gram partial sums of this lane's block pair
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a2[i] = 0ull;
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
         const int j = k - g.dtile;
         const int u0 = j * kTile;
-        const bool live = j >= 0 && u0 < T;
-        if (live && c_valid) {
+        if (j >= 0 && u0 < T && c_valid) {
+            int8_t *stg = sm.stage + ((j & 1) * kSlots + c_slot) * kTile * C2 + c_ch;
+            float *vmo = sm.vms + (j & 1) * kTile * kVmPitch + lane;
 #pragma unroll 1
-            for (int sg = 0; sg < kTile / kSeg; ++sg) {
+            for (int sg = 0; sg < kSegsPerTile; ++sg) {
                 const int us = u0 + sg * kSeg;
                 const int wi = (us >> 5) & (kRingWords - 1);
                 unsigned int P = bits[(kRingWords + wi) * 32], Nn = bits[wi * 32];
@@ -474,11 +479,42 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                 }
             }
         }
-        __syncwarp();
-        // Gram of the membrane tile: C += v v^T on 4x4 blocks with FFMA2, float32 partial sums in
-        // registers, folded into the float64 accumulators every kGramFlush tiles
+        ROLE_BARRIER();
+    }
+    ROLE_TIMER_FLUSH(6);
+}
+
+// ==== Gram warp: C += v v^T of the membrane tile k - dtile - 1, then that tile's int8 spike raster -> HBM ====
+__device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &g, int8_t *__restrict__ spikes,
+                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
+    const int C2 = 2 * MMv;
+    const int T = (int)T64;
+    // Gram lanes: lane = slot * 10 + upper-triangular 4x4 block pair of the slot's 16x16 matrix
+    const int g_slot = lane / 10;
+    int g_bi = 0, g_bj = 0;
+    {
+        int pr = lane % 10;
+        for (int r = 0; r < 4; ++r) {
+            const int len = 4 - r;
+            if (pr < len) { g_bi = r; g_bj = r + pr; break; }
+            pr -= len;
+        }
+    }
+    const bool g_lane = lane < 10 * kSlots;
+    double *gacc = sm.gacc + lane * 16;
+    unsigned long long a2[8];       // float32 Gram partial sums of this lane's block pair
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a2[i] = 0ull;
+    ROLE_TIMER_DECL;
+
+    for (int k = -1; k <= k_last; ++k) {
+        const int j = k - g.dtile - 1;
+        const int u0 = j * kTile;
+        const bool live = j >= 0 && u0 < T;
+        // C += v v^T on 4x4 blocks with FFMA2, float32 partial sums in registers, folded into the float64
+        // accumulators every kGramFlush tiles
         if (live && g_lane) {
-            const float *vm = sm.vms + g_slot * 16;
+            const float *vm = sm.vms + (j & 1) * kTile * kVmPitch + g_slot * 16;
 #pragma unroll 8
             for (int i = 0; i < kTile; ++i) {
                 const float4 a = *reinterpret_cast<const float4 *>(vm + i * kVmPitch + 4 * g_bi);
@@ -502,16 +538,16 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                 }
             }
         }
-        __syncwarp();
         // int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
         if (live && spikes) {
             const int nrow = T - u0 < kTile ? T - u0 : kTile;
             for (int s = 0; s < kSlots; ++s) {
                 if (clip0 + s >= B) continue;
-                const int8_t *src = sm.stage + s * kTile * C2;
+                const int8_t *src = sm.stage + ((j & 1) * kSlots + s) * kTile * C2;
                 int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
                 const int nbytes = nrow * C2;
-                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0) {
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0 &&
+                    ((kTile * C2) & 15) == 0) {
                     for (int v = lane; v < nbytes / 16; v += 32)
                         reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
                 } else {
@@ -521,11 +557,11 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(3);
+    ROLE_TIMER_FLUSH(7);
 }
 
 template <typename IN_T, int MM>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
         int8_t *__restrict__ spikes, float *__restrict__ power, int32_t *__restrict__ doa,
         int32_t *__restrict__ flags, unsigned int *__restrict__ sm_slots,
@@ -534,19 +570,21 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     FusedSmem sm;
     sm.taps = reinterpret_cast<float *>(smem_raw);
     sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
-    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2][kSlots*M][kQPitch]
-    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [kTile][kVmPitch]
+    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2 tiles][2 tap halves][kSlots*M][kQPitch]
+    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [2][kTile][kVmPitch]
     sm.is_s = reinterpret_cast<float *>(smem_raw + g.off_is);    // [kSlots][kTile][M]
-    sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [kSeg][32] running sums of the open segment
+    sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [2][kSegsPerTile][kSeg][32] running sums
+    sm.seg = reinterpret_cast<unsigned int *>(smem_raw + g.off_seg);     // [2][kSegsPerTile][3][32]
     sm.clus = reinterpret_cast<int *>(smem_raw + g.off_clus);    // RZCC cluster buffers, interleaved over 32 lanes
     sm.bits = reinterpret_cast<unsigned int *>(smem_raw + g.off_bits);   // [2][kRingWords][32]
-    sm.stage = reinterpret_cast<int8_t *>(smem_raw + g.off_stage);       // [kSlots][kTile][C2]
+    sm.stage = reinterpret_cast<int8_t *>(smem_raw + g.off_stage);       // [2][kSlots][kTile][C2]
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
     sm.gacc = reinterpret_cast<double *>(smem_raw + g.off_gacc);
+    sm.zero = reinterpret_cast<float *>(smem_raw + g.off_zero);  // [64] zeros
     sm.dbg = sm_slots;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
-    __shared__ unsigned int s_rot;
+    __shared__ int s_smsp[kWarps], s_role[kWarps];
     __shared__ long long s_pair;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -557,27 +595,54 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
 #endif
 
-    // Warp w of a CTA lands on SM sub-partition w % 4; rotate the roles per co-resident
-    // CTA so that every sub-partition gets its share of FIR warps.
+    // Role assignment.  A hardware warp slot w belongs to SM sub-partition w % 4, and the FMA pipe of a
+    // sub-partition is what the FIR warps compete for: the four FIR roles go to the warps of this CTA whose
+    // sub-partition holds the fewest FIR warps of the CTAs already resident on this SM (counters per SM in
+    // sm_slots[4*smid + smsp], reset per launch); the other four roles follow in warp order, rotated by two
+    // for every second CTA of an SM so that the band-pass / Gram warps (the ones with FMA work) spread out.
+    if (lane == 0) {
+        unsigned int wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        s_smsp[warp] = (int)(wid & 3u);
+    }
+    for (int i = tid; i < 8 * g.nblk + 8; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
+    for (int i = tid; i < 64; i += blockDim.x) sm.zero[i] = 0.f;
+    __syncthreads();
     if (tid == 0) {
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const unsigned int k = atomicAdd(sm_slots + (smid & 255u), 1u) & 3u;
-        s_rot = (0x3120u >> (4 * k)) & 3u;   // 0, 2, 1, 3 for the 1st .. 4th CTA that lands on this SM
+        unsigned int *fir_cnt = sm_slots + 4 * (smid & 255u);
+        const unsigned int arrival = atomicAdd(sm_slots + kSlotPair + 1 + (smid & 255u) % 254u, 1u);
+        bool taken[kWarps];
+        for (int w = 0; w < kWarps; ++w) { taken[w] = false; s_role[w] = -1; }
+        for (int r = 0; r < kFirWarps; ++r) {
+            int best = -1; unsigned int bestc = 0xffffffffu;
+            for (int w = 0; w < kWarps; ++w) {
+                if (taken[w]) continue;
+                const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
+                if (c < bestc) { bestc = c; best = w; }
+            }
+            taken[best] = true;
+            s_role[best] = r;
+            atomicAdd(fir_cnt + s_smsp[best], 1u);
+        }
+        int next = (int)(2u * (arrival & 1u));
+        for (int w = 0; w < kWarps; ++w)
+            if (!taken[w]) { s_role[w] = kFirWarps + (next & 3); ++next; }
     }
-    for (int i = tid; i < 8 * g.nblk + 8; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
     __syncthreads();
-    const int role = (warp + (int)s_rot) & 3;     // 0, 1: FIR (+ fill, Gram) of clip slot 0 / 1; 2: front; 3: neuron
+    // 0..3: FIR (+ fill) of clip slot role >> 1, tap half role & 1; 4: band-pass; 5: RZCC; 6: neuron; 7: Gram
+    const int role = s_role[warp];
 
     const int NT = (int)((T + kTile - 1) / kTile);
-    const int k_last = NT - 1 + g.dtile;
+    const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 tiles behind
     const long long npairs = (B + kSlots - 1) / kSlots;
 
-    // Clip pairs are handed out dynamically: co-resident CTAs do not run at the same speed (the warp
-    // scheduler favours the youngest CTA of an SM), so a static split would wait for the slowest one.
+    // Clip pairs are handed out dynamically: co-resident CTAs do not run at the same speed, so a static
+    // split would wait for the slowest one.
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_pair = (long long)atomicAdd(sm_slots + 255, 1u);
+        if (tid == 0) s_pair = (long long)atomicAdd(sm_slots + kSlotPair, 1u);
         __syncthreads();
         const long long pair = s_pair;
         if (pair >= npairs) break;
@@ -588,14 +653,18 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             for (int i = tid; i < n4; i += blockDim.x) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             // no spikes before the clip start; membrane columns of unused lanes stay zero
             for (int i = tid; i < 2 * kRingWords * 32; i += blockDim.x) sm.bits[i] = 0u;
-            for (int i = tid; i < kTile * kVmPitch; i += blockDim.x) sm.vms[i] = 0.f;
+            for (int i = tid; i < 2 * kTile * kVmPitch; i += blockDim.x) sm.vms[i] = 0.f;
             for (int i = tid; i < kSlots * 160; i += blockDim.x) sm.gacc[i] = 0.0;
         }
         __syncthreads();
 
-        if (role < 2) fir_role<IN_T, MM>(sm, p, g, audio, clip0 + role, clip0 + role < B, T, role, lane, NT, k_last);
-        else if (role == 2) front_role<IN_T, MM>(sm, p, g, audio, flags, clip0, B, T, lane, k_last);
-        else neuron_role<MM>(sm, p, g, spikes, clip0, B, T, lane, k_last);
+        if (role < kFirWarps)
+            fir_role<IN_T, MM>(sm, p, g, audio, clip0 + (role >> 1), clip0 + (role >> 1) < B, T, role >> 1, role & 1, lane,
+                               NT, k_last);
+        else if (role == 4) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
+        else if (role == 5) rzcc_role(sm, p, flags, clip0, B, T, M, lane, k_last);
+        else if (role == 6) neuron_role(sm, p, g, clip0, B, T, M, lane, k_last);
+        else gram_role(sm, g, spikes, clip0, B, T, M, lane, k_last);
         __syncthreads();
         // unpack the block-pair accumulators into full symmetric matrices (the audio rings are dead now)
         for (int e = tid; e < kSlots * 160; e += blockDim.x) {
@@ -613,29 +682,31 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         }
         __syncthreads();
 
-        // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
+        // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax (threads 0..127) ----
         const double inv_T = 1.0 / (double)T;
         for (int s = 0; s < kSlots; ++s) {
             const long long clip = clip0 + s;
             if (clip >= B) break;
             const double *Cd = sm.gram + s * 256;
             double best = -1.0; int besti = 0x7fffffff;
-            for (int gg = tid; gg < p.G; gg += blockDim.x) {
-                double accp = 0.0;
+            if (tid < 128) {
+                for (int gg = tid; gg < p.G; gg += 128) {
+                    double accp = 0.0;
 #pragma unroll 1
-                for (int r = 0; r < C2; ++r) {
-                    double rr = 0.0;
+                    for (int r = 0; r < C2; ++r) {
+                        double rr = 0.0;
 #pragma unroll 2
-                    for (int c = 0; c < C2; ++c) rr = fma(Cd[r * 16 + c], Wd[(long long)c * p.G + gg], rr);
-                    accp = fma(Wd[(long long)r * p.G + gg], rr, accp);
+                        for (int c = 0; c < C2; ++c) rr = fma(Cd[r * 16 + c], Wd[(long long)c * p.G + gg], rr);
+                        accp = fma(Wd[(long long)r * p.G + gg], rr, accp);
+                    }
+                    accp *= inv_T;
+                    if (power) power[clip * p.G + gg] = (float)accp;
+                    if (accp > best) { best = accp; besti = gg; }
                 }
-                accp *= inv_T;
-                if (power) power[clip * p.G + gg] = (float)accp;
-                if (accp > best) { best = accp; besti = gg; }
+                red_v[tid] = best; red_i[tid] = besti;
             }
-            red_v[tid] = best; red_i[tid] = besti;
             __syncthreads();
-            for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+            for (int st = 64; st > 0; st >>= 1) {
                 if (tid < st) {
                     const double ov = red_v[tid + st]; const int oi = red_i[tid + st];
                     if (ov > red_v[tid] || (ov == red_v[tid] && oi < red_i[tid])) { red_v[tid] = ov; red_i[tid] = oi; }
@@ -650,17 +721,19 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     if (blockIdx.x == 0 && tid == 0) {
         unsigned long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + 256);
-        d[14] = (unsigned long long)(rt_clock() - dbg_c0);
-        d[15] = g1 - dbg_g0;
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg);
+        d[16] = (unsigned long long)(rt_clock() - dbg_c0);
+        d[17] = g1 - dbg_g0;
     }
-    if (tid == 0 && blockIdx.x < 1024) {
+    if (tid == 0 && blockIdx.x < 512) {
         unsigned long long g1;
         unsigned int smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + 320) + 8 * blockIdx.x;
-        d[0] = dbg_g0; d[1] = g1; d[2] = smid; d[3] = s_rot;
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * blockIdx.x;
+        unsigned long long map = 0;
+        for (int w = 0; w < kWarps; ++w) map |= (unsigned long long)((s_role[w] & 7) | ((s_smsp[w] & 3) << 3)) << (8 * w);
+        d[0] = dbg_g0; d[1] = g1; d[2] = smid; d[3] = map;     // d[4..11]: busy cycles per role
     }
 #endif
 }
@@ -675,16 +748,17 @@ static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float 
                           int32_t *flags, unsigned int *sm_slots, int sm_count, cudaStream_t st) {
     auto kern = k_fused<IN_T, MM>;
     MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-    // all of the SM's L1/shared array as shared memory: three CTAs of ~71 KB must be resident together
+    // all of the SM's L1/shared array as shared memory: two CTAs of ~100 KB must be resident together
     MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
-    MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, g.smem_bytes));
+    MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, g.smem_bytes));
+    if (per_sm > 2) per_sm = 2;     // the role placement balances two CTAs per SM
     if (per_sm < 1) return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel does not fit (smem %d B)", g.smem_bytes);
     long long grid = (long long)sm_count * per_sm;
     const long long npairs = (B + kSlots - 1) / kSlots;
     if (grid > npairs) grid = npairs;
-    MICLOC_CUDA(cudaMemsetAsync(sm_slots, 0, 256 * sizeof(unsigned int), st));   // role rotation restarts per launch
-    kern<<<(unsigned)grid, 128, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
+    MICLOC_CUDA(cudaMemsetAsync(sm_slots, 0, kSlotResetWords * sizeof(unsigned int), st));   // FIR placement counters + pair counter restart per launch
+    kern<<<(unsigned)grid, kThreads, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
     count_launch(1);
     MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
@@ -698,33 +772,36 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
                          "fused kernel covers Hilbert-type STHT kernels (every other tap zero), a 2-section band-pass "
                          "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
-    // FIR tap blocks: groups of three blocks of 8 (zero taps appended by setup_stht up to a multiple of 8)
-    g.nblk = (p.n_taps / 8 + 2) / 3 * 3;
+    // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
+    g.nblk = 2 * p.fir_split;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
     g.ring_x = ((lookback + 2 * kTile) + 31) / 32 * 32;             // history + current tile + tile being filled
     g.pitch_x = g.ring_x + 4;
     g.shift = ((p.tap_first + 14) % 16 + 16) % 16;
-    // a spike at p is final once the front warp passed p + rzcc_lag(w) - 1; the back warp works on
-    // tile k - dtile while the front warp has completed tile k - 2
-    g.dtile = 1 + (rzcc_lag(p.w) + 63 + kTile - 1) / kTile;
+    // a spike at p is final once the RZCC warp passed p + rzcc_lag(w) - 1; the neuron warp works on
+    // tile k - dtile while the RZCC warp has completed tile k - 3
+    g.dtile = 3 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
     g.tiles_is = (p.half + kTile - 1) / kTile;
     int off = ((8 * g.nblk + 8) * (int)sizeof(float) + 15) & ~15;
     g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
-    g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
-    g.off_vm = off; off += kTile * kVmPitch * (int)sizeof(float);
+    g.off_q = off; off += 2 * 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
+    g.off_vm = off; off += 2 * kTile * kVmPitch * (int)sizeof(float);
     g.off_is = off; off += kSlots * kTile * p.M * (int)sizeof(float);
-    g.off_cs = off; off += kSeg * 32 * (int)sizeof(float);
+    g.off_cs = off; off += 2 * kSegsPerTile * kSeg * 32 * (int)sizeof(float);
+    g.off_seg = off; off += 2 * kSegsPerTile * 3 * 32 * (int)sizeof(int);
     g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
-    g.off_stage = off; off += (kSlots * kTile * p.C2 + 15) & ~15;
+    g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.off_gacc = off; off += kSlots * 160 * (int)sizeof(double);
+    g.off_zero = off; off += 64 * (int)sizeof(float);
     g.smem_bytes = off;
     // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
-    if (kTile * (g.dtile + 1) + p.nL + kSeg > kRingWords * 32)
+    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 2)
+    if (kTile * (g.dtile - 1) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
     if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
-        128 * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
+        128 * 12 > 4 * kSlots * p.M * kQPitch * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);

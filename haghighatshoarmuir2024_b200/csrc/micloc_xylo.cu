@@ -401,7 +401,7 @@ struct micloc_xylo {
     unsigned int *d_sm_slots = nullptr;
     int sm_count = 148;
 };
-static constexpr size_t kXyloSlotWords = 320 + 16 * 1024;
+static constexpr size_t kXyloSlotWords = kSlotWords;
 
 extern "C" int micloc_xylo_destroy(micloc_xylo *c) {
     if (!c) return MICLOC_OK;

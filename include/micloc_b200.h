@@ -183,14 +183,13 @@ int64_t micloc_launch_count(void);
  * runs summed in n_runs, then forgets them. */
 int micloc_snn_last_kernel_ms(micloc_snn *ctx, float *ms, int32_t *n_runs);
 int micloc_snn_enable_timing(micloc_snn *ctx, int enable);
-/* Debug counters of the fused kernel (busy cycles per warp role: FIR slot 0, FIR slot 1, front,
- * neuron; then the number of warps that reported each; then six sub-phase sums of the FIR warps);
- * zeros unless the library was built with
- * -DMICLOC_ROLE_TIMING.  Synchronises the device. */
-int micloc_snn_debug_counters(micloc_snn *ctx, uint64_t out[16]);
-/* Debug: out[8*i .. 8*i+7] = (start ns, end ns, SM id, role rotation, busy cycles of FIR0, FIR1, front,
- * neuron) of CTA i of the last fused launch, i < n <= 1024
- * (MICLOC_ROLE_TIMING builds only). */
+/* Debug counters of the fused kernel (MICLOC_ROLE_TIMING builds only, zeros otherwise): out[0..7] = busy
+ * cycles summed per warp role (FIR clip 0 half 0/1, FIR clip 1 half 0/1, band-pass, RZCC, neuron, Gram),
+ * out[8..15] = number of warps that reported each, out[16] / out[17] = clock64 cycles / nanoseconds of CTA 0.
+ * Synchronises the device. */
+int micloc_snn_debug_counters(micloc_snn *ctx, uint64_t out[32]);
+/* Debug: out[16*i .. 16*i+15] = (start ns, end ns, SM id, role map: byte w = role | smsp << 3 of warp w, busy
+ * cycles of the eight roles, unused) of CTA i of the last fused launch, i < n <= 512 (MICLOC_ROLE_TIMING builds only). */
 int micloc_snn_debug_cta_times(micloc_snn *ctx, uint64_t *out, int32_t n);
 /* FP32 FMA-pipe micro-benchmark on `device` (the measured denominator of the
  * roofline in bench.py): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */

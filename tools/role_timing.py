@@ -21,7 +21,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 888
 audio, _, _ = sweep.synthesize(0, B, seed=1, snr_db_grid=Bn.SNR_GRID)
 eng = sweep.engines[0]
 lib = N.lib()
-out = (ctypes.c_uint64 * 16)()
+out = (ctypes.c_uint64 * 32)()
 for rep in range(3):
     lib.micloc_snn_debug_counters(eng._h, out)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,25 +32,29 @@ for rep in range(3):
     ms = ev0.elapsed_time(ev1)
     lib.micloc_snn_debug_counters(eng._h, out)
     v = list(out)
-    names = ["fir0", "fir1", "front", "neuron"]
-    iters = (Bn.T_CLIP // 64) + 5
+    names = ["fir0a", "fir0b", "fir1a", "fir1b", "bandpass", "rzcc", "neuron", "gram"]
+    iters = (Bn.T_CLIP // 64) + 8
     print(f"rep {rep}: {ms:.3f} ms, {B / ms:.1f} clips/ms; " + ", ".join(
-        f"{n}: {v[i] / max(v[4 + i], 1) / iters:.0f} busy cyc/tile ({v[4 + i]} warps)" for i, n in enumerate(names)))
-    nf = max(v[4] + v[5], 1)
-    print("   FIR warp phases (cyc/tile): " + ", ".join(f"{n}: {v[8 + i] / nf / iters:.0f}" for i, n in enumerate(
-        ["fill-load", "fir", "fill-store", "-", "post", "tile-barrier"])))
-    print(f"   CTA 0: {v[14]} clock64 cycles in {v[15]} ns -> {v[14] / max(v[15], 1) * 1e3:.0f} MHz")
+        f"{n}: {v[i] / max(v[8 + i], 1) / iters:.0f}" for i, n in enumerate(names)) + " busy cyc/tile")
+    print(f"   CTA 0: {v[16]} clock64 cycles in {v[17]} ns -> {v[16] / max(v[17], 1) * 1e3:.0f} MHz")
 
-n = min(444, (B + 1) // 2)  # CTAs of the launch (148 SMs x 3)
-buf = (ctypes.c_uint64 * (8 * n))()
+n = min(296, (B + 1) // 2)  # CTAs of the launch (148 SMs x 2)
+buf = (ctypes.c_uint64 * (16 * n))()
 lib.micloc_snn_debug_cta_times(eng._h, buf, n)
-a = np.array(list(buf), dtype=np.float64).reshape(n, 8)
+a = np.array(list(buf), dtype=np.float64).reshape(n, 16)
+raw = np.array(list(buf), dtype=np.uint64).reshape(n, 16)
 t0 = a[:, 0].min()
-start, end, smid, rot = (a[:, 0] - t0) / 1e6, (a[:, 1] - t0) / 1e6, a[:, 2].astype(int), a[:, 3].astype(int)
+start, end, smid = (a[:, 0] - t0) / 1e6, (a[:, 1] - t0) / 1e6, a[:, 2].astype(int)
 print("CTA start ms: max %.3f; end ms: min %.3f median %.3f max %.3f; CTAs per SM: %s" % (
     start.max(), end.min(), np.median(end), end.max(), np.bincount(np.bincount(smid))))
-iters = Bn.T_CLIP // 64 + 5
-for r in sorted(set(rot)):
-    m = rot == r
-    print(f"rot {r}: {m.sum()} CTAs, end ms mean {end[m].mean():.2f} (min {end[m].min():.2f} max {end[m].max():.2f}); busy cyc/tile "
-          + ", ".join(f"{nm} {a[m, 4 + i].mean() / iters:.0f}" for i, nm in enumerate(["fir0", "fir1", "front", "neuron"])))
+# FIR warps per (SM, sub-partition)
+fir = {}
+for i in range(n):
+    for w in range(8):
+        byte = (int(raw[i, 3]) >> (8 * w)) & 0xff
+        role, smsp = byte & 7, (byte >> 3) & 3
+        if role < 4:
+            fir[(smid[i], smsp)] = fir.get((smid[i], smsp), 0) + 1
+print("FIR warps per (SM, sub-partition) histogram:", np.bincount(list(fir.values())), "of", 4 * len(set(smid)), "sub-partitions")
+iters = Bn.T_CLIP // 64 + 8
+print("mean busy cyc/tile per role over CTAs:", ", ".join(f"{nm} {a[:, 4 + i].mean() / iters:.0f}" for i, nm in enumerate(names)))
