@@ -33,6 +33,8 @@
 // keep it busy (one alone leaves it idle whenever it loses an issue slot to another warp).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "micloc_common.h"
 
 namespace micloc {
@@ -55,6 +57,7 @@ struct FusedGeom {
     int nblk;        // FIR tap blocks of 8 (multiple of 6: two halves walked in groups of three)
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
+    int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
     int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_gacc, off_zero;   // byte offsets in dynamic smem
     int smem_bytes;
 };
@@ -658,7 +661,9 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         }
         __syncthreads();
 
-        if (role < kFirWarps)
+        if ((g.skip >> role) & 1) {
+            for (int k = -1; k <= k_last; ++k) tile_barrier();
+        } else if (role < kFirWarps)
             fir_role<IN_T, MM>(sm, p, g, audio, clip0 + (role >> 1), clip0 + (role >> 1) < B, T, role >> 1, role & 1, lane,
                                NT, k_last);
         else if (role == 4) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
@@ -772,6 +777,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
                          "fused kernel covers Hilbert-type STHT kernels (every other tap zero), a 2-section band-pass "
                          "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
+    if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
     g.nblk = 2 * p.fir_split;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load

@@ -192,7 +192,8 @@ int micloc_snn_debug_counters(micloc_snn *ctx, uint64_t out[32]);
  * cycles of the eight roles, unused) of CTA i of the last fused launch, i < n <= 512 (MICLOC_ROLE_TIMING builds only). */
 int micloc_snn_debug_cta_times(micloc_snn *ctx, uint64_t *out, int32_t n);
 /* FP32 FMA-pipe micro-benchmark on `device` (the measured denominator of the
- * roofline in bench.py): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
+ * roofline in bench.py): variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2; diagnostics: 2 = FP64 DFMA
+ * (FP64 TFLOP/s), 3 = FFMA2 with one DFMA per two FFMA2 in the same warps (FP32 TFLOP/s of the FFMA2 part). */
 int micloc_fp32_peak(int device, int variant, double *tflops);
 
 #ifdef __cplusplus

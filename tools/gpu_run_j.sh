@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 TAG=${1:-j}
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -rs 2>&1 | tail -15 > gpurun_out/tests_$TAG.log
+python -m pytest tests -m gpu -x -q -rs 2>&1 | tail -15 > gpurun_out/tests_$TAG.log
 cat gpurun_out/tests_$TAG.log
 python bench.py --steps 4 --warmup 3 --clips-per-band 3552 --no-cpu > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -3 gpurun_out/bench_${TAG}.err
 python -c "
