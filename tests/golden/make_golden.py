@@ -19,14 +19,19 @@ import os
 import sys
 import types
 
-for m in ("matplotlib", "matplotlib.pyplot"):
+for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.gridspec"):
     sys.modules[m] = types.ModuleType(m)
+sys.modules["matplotlib"].gridspec = sys.modules["matplotlib.gridspec"]
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["matplotlib"].use = lambda *a, **k: None           # multiple_targets_snn.py calls use_latex() at import
+sys.modules["matplotlib"].rcParams = {}
+sys.modules["matplotlib.pyplot"].rc = lambda *a, **k: None
 sys.path.insert(0, "/root/reference")
 
 import numpy as np
 from scipy.signal import butter, lfilter
 
-from micloc.array_geometry import CenterCircularArray, LinearArray
+from micloc.array_geometry import CenterCircularArray, LinearArray, Random2DArray
 from micloc.beamformer import Beamformer
 from micloc.snn_beamformer import SNNBeamformer
 from micloc.spike_encoder import ZeroCrossingSpikeEncoder
@@ -42,7 +47,8 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-def snn_case(name, geometry, band, bipolar, G, T, source, snr_db, seed, kernel_duration=10e-3, int16=False):
+def snn_case(name, geometry, band, bipolar, G, T, source, snr_db, seed, kernel_duration=10e-3, int16=False,
+             multi_targets=None, dec=DEC):
     np.random.seed(seed)
     f_mid = float(np.mean(band))
     tau = 1 / (2 * np.pi * f_mid)
@@ -61,12 +67,25 @@ def snn_case(name, geometry, band, bipolar, G, T, source, snr_db, seed, kernel_d
     else:
         src = chirp
     doa = float(np.random.rand() * 2 * np.pi)
-    # array signal exactly as apply_to_template builds it (snn_beamformer.py:243-275)
-    delays = np.asarray([geometry.delays(theta=doa, normalized=False) for _ in t]).T
-    delays = delays - delays.min()
-    td = t.reshape(1, -1) - delays
-    td[td < t.min()] = t.min()
-    x = np.interp(td.ravel(), t, src).reshape(td.shape).T
+    if multi_targets is not None:
+        # several simultaneous sources through the reference's own signal_multiple_targets
+        # (paper_plots/multiple_targets_snn.py:87-159), speech-shaped source: white noise tilted by -6 dB/oct, band-passed
+        sys.path.insert(0, "/root/reference/paper_plots")
+        from multiple_targets_snn import signal_multiple_targets
+        tilt = lfilter([1.0], [1.0, -0.95], np.random.randn(T))
+        b_, a_ = butter(2, band, btype="bandpass", fs=FS)
+        src = lfilter(b_, a_, tilt)
+        doas, powers = multi_targets
+        x = signal_multiple_targets(geometry, t, src, np.tile(np.asarray(doas, float), (T, 1)),
+                                    np.tile(np.asarray(powers, float), (T, 1)))
+        doa = float(doas[0])
+    else:
+        # array signal exactly as apply_to_template builds it (snn_beamformer.py:243-275)
+        delays = np.asarray([geometry.delays(theta=doa, normalized=False) for _ in t]).T
+        delays = delays - delays.min()
+        td = t.reshape(1, -1) - delays
+        td[td < t.min()] = t.min()
+        x = np.interp(td.ravel(), t, src).reshape(td.shape).T
     snr = 10 ** (snr_db / 10)
     x = x + np.sqrt(np.mean(x ** 2)) / np.sqrt(snr) * np.random.randn(*x.shape)
     if int16:
@@ -92,7 +111,7 @@ def snn_case(name, geometry, band, bipolar, G, T, source, snr_db, seed, kernel_d
     nir = nir[: np.sum(np.cumsum(nir) < 0.999)]
     vmem = lfilter(nir, [1], spikes, axis=0)
     assert np.array_equal(vmem @ bf_mat, y), "stage taps diverge from apply_to_signal"
-    rows = np.arange(0, T, DEC)
+    rows = np.arange(0, T, dec)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
         kind="snn", fs=FS, band=np.asarray(band, float), bipolar=bipolar, tau=tau, kernel_duration=kernel_duration,
@@ -157,7 +176,25 @@ def utils_case():
     print("utils", idx.shape)
 
 
+def extra_cases():
+    """BASELINE configs 4 and 5 at fixture size."""
+    circ = CenterCircularArray(radius=4.5e-2, num_mic=7)
+    # config 4: two simultaneous speech-shaped sources at +-pi/3 (multiple_targets_snn.py:307-308), 360-angle grid
+    snn_case("snn_c4_multi", circ, [1500, 2500], True, 360, 4800, "noise", 15.0, 17,
+             multi_targets=([np.pi / 3, -np.pi / 3], [1.0, 1.0]), dec=32)
+    # config 5: 64-microphone linear and random arrays (array_resolution_linear_snn.py:126-136,
+    # array_resolution_random_snn.py:114-121 with np.random.seed(1)), 512-angle grid
+    lin64 = LinearArray(spacing=2 * 4.5e-2 / 64, num_mic=64, radius=4.5e-2)
+    snn_case("snn_c5_linear64", lin64, [1600, 2000], True, 512, 1600, "chirp", 10.0, 18, dec=64)
+    np.random.seed(1)
+    rnd64 = Random2DArray(radius=4.5e-2, num_mic=64)
+    snn_case("snn_c5_random64", rnd64, [1600, 2000], False, 512, 1600, "noise", 10.0, 19, dec=64)
+
+
 if __name__ == "__main__":
+    if "--new-only" in sys.argv:
+        extra_cases()
+        sys.exit(0)
     circ = CenterCircularArray(radius=4.5e-2, num_mic=7)
     snn_case("snn_c1_bipolar", circ, [1600, 2000], True, 64, 4800, "noise", 20.0, 11)
     snn_case("snn_c1_unipolar", circ, [1600, 2000], False, 64, 4800, "noise", 20.0, 12)
@@ -166,6 +203,8 @@ if __name__ == "__main__":
     lin = LinearArray(spacing=2 * 4.5e-2 / 16, num_mic=16, radius=4.5e-2)
     snn_case("snn_linear16", lin, [1600, 2000], True, 40, 2400, "chirp", 10.0, 15)
     snn_case("snn_k20ms", circ, [2300, 2600], False, 24, 2400, "noise", 10.0, 16, kernel_duration=20e-3)
-    rzcc_case()
-    beamformer_case()
-    utils_case()
+    extra_cases()
+    if "--new-only" not in sys.argv:
+        rzcc_case()
+        beamformer_case()
+        utils_case()

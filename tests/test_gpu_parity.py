@@ -123,6 +123,56 @@ def test_full_size_clip_config1():
             assert pos.size < 2 or np.diff(pos).min() >= int(g["robust_width"])
 
 
+def test_full_size_config4_multi_source_360_grid():
+    """Config 4 size: 1 s clips with two simultaneous sources, G = 360, fused kernel vs oracle."""
+    g = H.load("snn_c4_multi")
+    T = 48000
+    rng = np.random.default_rng(41)
+    fs = float(g["fs"]); t = np.arange(T) / fs
+    from scipy.signal import butter, lfilter
+    from haghighatshoarmuir2024_b200.array_geometry import ArrayGeometry
+    geo = ArrayGeometry(g["r_vec"], g["theta_vec"])
+    b_, a_ = butter(2, g["band"], btype="bandpass", fs=fs)
+    xs = []
+    for i in range(3):
+        src = lfilter(b_, a_, lfilter([1.0], [1.0, -0.95], rng.standard_normal(T)))
+        x = 0.0
+        for doa in (np.pi / 3, -np.pi / 3 + 0.2 * i):          # multiple_targets_snn.py:87-159: delays added, np.interp
+            x = x + np.interp((t[:, None] + geo.delays_batch(np.full(T, doa))).ravel(), t, src).reshape(T, -1)
+        xs.append(x + 0.05 * np.std(x) * rng.standard_normal(x.shape))
+    x = np.stack(xs).astype(np.float32)
+    eng = engine_for(g, T)
+    out = eng.run(to_dev(x), want_spikes=True, fused=True)
+    st = eng.run(to_dev(x), want_spikes=True, fused=False)
+    assert torch.equal(out["spikes"], st["spikes"]) and torch.equal(out["doa"], st["doa"])
+    cfg = H.oracle_cfg(g)
+    cfg.nir = O.neuron_kernel(t, float(g["tau"]), float(g["tau"]))
+    ref = O.snn_run_batch(cfg, x, nthreads=3, want_spikes=True)
+    assert H.spike_agreement(out["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
+    assert np.array_equal(out["doa"].cpu().numpy(), ref["doa"])
+    assert H.rel_err(out["power"].cpu().numpy(), ref["power"]) < 2e-3
+    assert int(out["flags"].sum()) == 0
+
+
+def test_full_size_config5_64_mics_10s_512_grid():
+    """Config 5 size: one 10 s clip (T = 480 000) on the 64-microphone random array, G = 512 (staged path:
+    the fused kernel covers up to 8 microphones) against the oracle."""
+    g = H.load("snn_c5_random64")
+    T = 480_000
+    x, _ = H.synth_clips(g, 1, T, seed=51, snrs_db=(10.0,))
+    eng = engine_for(g, T)
+    out = eng.run(to_dev(x), want_spikes=True, fused=False)
+    torch.cuda.synchronize()
+    cfg = H.oracle_cfg(g)
+    cfg.nir = O.neuron_kernel(np.arange(T) / float(g["fs"]), float(g["tau"]), float(g["tau"]))
+    ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
+    assert H.spike_agreement(out["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
+    assert int(out["doa"][0]) == int(ref["doa"][0])
+    assert H.rel_err(out["power"].cpu().numpy(), ref["power"]) < 2e-3
+    with pytest.raises(Exception):
+        eng.run(to_dev(x[:, :4096]), fused=True)               # 64 microphones: the fused kernel says so loudly
+
+
 def test_stht_linearity_and_zero_input():
     g = H.load("snn_c1_bipolar")
     eng = engine_for(g, 2048)
