@@ -103,7 +103,6 @@ int micloc::setup_stht(ChainParams &p, const double *h, int K, float **d_taps) {
     p.K = K; p.half = K / 2;
     p.tap_stride = stride; p.tap_first = first; p.n_taps = npad;
     p.span = first + stride * (npad - 1);
-    p.fir_split = ((npad / kFirJB + 5) / 6 * 6) / 2;      // half of the block count rounded up to a multiple of 6
     MICLOC_CUDA(cudaMalloc(d_taps, npad * sizeof(float)));
     MICLOC_CUDA(cudaMemcpy(*d_taps, taps.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
     return MICLOC_OK;

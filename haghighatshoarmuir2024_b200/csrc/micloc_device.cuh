@@ -27,7 +27,6 @@ struct ChainParams {
     int tap_first;    // index k0 of the first kept tap
     int n_taps;       // kept taps, padded with zeros to a multiple of kFirJB
     int span;         // largest look-back = tap_first + tap_stride*(n_taps-1)
-    int fir_split;    // tap blocks (of kFirJB) in the first of the two partial sums the FIR is accumulated in
     int nsec;         // biquad sections
     float sos[kMaxSections][5];  // b0 b1 b2 a1 a2
     int w;            // RZCC distance (>=1)
@@ -66,24 +65,18 @@ __host__ __device__ inline int fir_row_pitch(int TT, int span) {
 
 template <int STRIDE>
 __device__ __forceinline__ void fir_accumulate(const float *__restrict__ row, const float *__restrict__ taps_s,
-                                               int n_taps, int span, int k0, int chunk, int split,
+                                               int n_taps, int span, int k0, int chunk,
                                                float (&acc)[kFirR]) {
     constexpr int WIN = FirGeom<STRIDE>::WIN;
     constexpr int NV = FirGeom<STRIDE>::NV;
 #pragma unroll
     for (int i = 0; i < kFirR; ++i) acc[i] = 0.f;
     const int nblk = n_taps / kFirJB;
-    // The sum over the taps is formed as two partial sums (blocks [0, split) and [split, nblk)) that are
-    // added at the end: the fused kernel gives the two halves to two warps, and both paths must round alike.
-    float acc_lo[kFirR];
     // l index of the window start for tap block 0; it moves back by STRIDE*JB per block
     int lmin = span + kFirR * chunk - k0 - STRIDE * (kFirJB - 1);
 #pragma unroll 1
     for (int jb = 0; jb < nblk; ++jb, lmin -= STRIDE * kFirJB) {
-        if (jb == split) {
-#pragma unroll
-            for (int i = 0; i < kFirR; ++i) { acc_lo[i] = acc[i]; acc[i] = 0.f; }
-        }
+
         float g[kFirJB];
         {
             const float4 g0 = *reinterpret_cast<const float4 *>(taps_s + jb * kFirJB);
@@ -103,10 +96,6 @@ __device__ __forceinline__ void fir_accumulate(const float *__restrict__ row, co
             for (int i = 0; i < kFirR; ++i)
                 acc[i] = fmaf(g[jj], wv[i + STRIDE * (kFirJB - 1 - jj)], acc[i]);
         (void)WIN;
-    }
-    if (split < nblk) {
-#pragma unroll
-        for (int i = 0; i < kFirR; ++i) acc[i] = acc_lo[i] + acc[i];
     }
 }
 

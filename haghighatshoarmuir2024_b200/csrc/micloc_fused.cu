@@ -11,14 +11,16 @@
 //
 //   FIR warps x4 tile k+1   audio (HBM) -> mic-major ring in shared memory (two warps per clip, 32
 //                           samples each)
-//                tile k     STHT quadrature FIR: every lane owns 16 consecutive outputs of one
-//                           microphone and walks HALF of the 240 non-zero Hilbert taps (the two warps
-//                           of a clip split the tap range; the band-pass warp adds the two partial
-//                           sums) in blocks of 8 with a sliding register window; the multiply-adds
-//                           are packed FFMA2 (fma.rn.f32x2)
-//   band-pass    tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
+//                tile k     STHT quadrature FIR, first half of the taps: every lane owns 16
+//                           consecutive outputs of one microphone and walks 120 of the 240 non-zero
+//                           Hilbert taps in blocks of 8 with a sliding register window; the
+//                           multiply-adds are packed FFMA2 (fma.rn.f32x2)
+//                tile k-1   second warp of the clip: continues the SAME running sums (handed over
+//                           in shared memory) through the other 120 taps: the summation order is
+//                           that of one warp walking all taps
+//   band-pass    tile k-2   one lane per (clip, channel): SOS band-pass recurrence, running sum,
 //                           sign / zero bit masks of every 32-sample segment -> shared memory
-//   RZCC         tile k-2   one lane per (clip, channel): the masks are turned into RZCC
+//   RZCC         tile k-3   one lane per (clip, channel): the masks are turned into RZCC
 //                           candidates and resolved (find_peaks distance rule) into a bit-packed
 //                           spike ring
 //   neuron       tile k-d   (d = the latency of the exact find_peaks decision) one lane per (clip,
@@ -57,8 +59,9 @@ struct FusedGeom {
     int nblk;        // FIR tap blocks of 8 (multiple of 6: two halves walked in groups of three)
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
+    int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
-    int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_gacc, off_zero;   // byte offsets in dynamic smem
+    int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_gacc, off_qa;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
@@ -149,7 +152,7 @@ struct RoleTimer {
 #endif
 
 struct FusedSmem {
-    float *taps, *xs, *qs, *vms, *is_s, *cs, *zero;
+    float *taps, *xs, *qs, *qa, *vms, *is_s, *cs;
     unsigned int *seg;      // [2 tiles][kTile/kSeg][3: neg mask, zero mask, carry][32 lanes]: band-pass -> RZCC hand-over
     int *clus;
     unsigned int *bits;     // [2 polarities][kRingWords][32 lanes]
@@ -193,12 +196,24 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
 #pragma unroll
             for (int m = 0; m < kRows; ++m) v[m] = (ok && m < M) ? to_f32<IN_T>(fill_src[m]) : 0.f;
         }
-        // (b) this warp's half of the STHT quadrature FIR of tile k
-        if (k >= 0 && k < NT) {
+        // (b) this warp's half of the taps of the STHT quadrature FIR: half 0 starts the running sums of tile k,
+        //     half 1 picks up those of tile k - 1 and finishes them
+        const int kk = k - half;
+        if (kk >= 0 && kk < NT) {
             if (work) {
                 unsigned long long acc[8];
+                float *part = sm.qa + (((kk & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
+                if (half == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = 0ull;
+                    for (int i = 0; i < 8; ++i) acc[i] = 0ull;
+                } else {
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const float4 o = reinterpret_cast<const float4 *>(part)[v4];
+                        acc[2 * v4] = pack2(o.x, o.y);
+                        acc[2 * v4 + 1] = pack2(o.z, o.w);
+                    }
+                }
                 Chunk A, Bq, Cq;
                 { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
                 load_chunk(A, row, c0);
@@ -208,7 +223,7 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
                 Taps8 t0, t1;
                 load_taps(t0, tp);
 #pragma unroll 1
-                for (int jb = 0; jb < nb2; jb += 3) {
+                for (int jb = 0; jb < (g.fir_blocks ? g.fir_blocks : nb2); jb += 3) {
                     load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
                     load_taps(t1, tp + 8);
                     fir_block(acc, A, Bq, t0);
@@ -221,7 +236,7 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
                     t0 = t1;
                     tp += 24;
                 }
-                float *dst = sm.qs + ((((k & 1) * 2 + half) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
+                float *dst = half == 0 ? part : sm.qs + (((kk & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
                     float4 o;
@@ -284,7 +299,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kc = k - 1;
+        const int kc = k - 2;
         const int t0 = kc * kTile;
         if (kc >= 0 && t0 < T) {
             const bool from_is = kc < g.tiles_is;
@@ -313,11 +328,10 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                 const int cin = cin_u;                    // ring coordinate of x[ts - K/2]
                 cin_u += kSeg; if (cin_u >= g.ring_x) cin_u -= g.ring_x;
                 if (ts >= T || !c_valid) continue;
-                const float *xp, *xp2 = sm.zero;         // quadrature = sum of the two FIR warps' partial sums
+                const float *xp;
                 int stride = 1, wrap_at = kSeg;
                 if (!c_inphase) {
-                    xp = sm.qs + ((((kc & 1) * 2 + 0) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
-                    xp2 = sm.qs + ((((kc & 1) * 2 + 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
+                    xp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
                 } else if (from_is) {
                     xp = sm.is_s + c_slot * kTile * M + sg * kSeg * M + c_ch;
                     stride = M;
@@ -332,7 +346,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                 if (fast) {
                     float xn[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) xn[i] = xp[i] + xp2[i];
+                    for (int i = 0; i < 8; ++i) xn[i] = xp[i];
 #pragma unroll 1
                     for (int o = 0; o < kSeg / 8; ++o) {
                         float xc[8];
@@ -340,7 +354,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                         for (int i = 0; i < 8; ++i) xc[i] = xn[i];
                         if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i] + xp2[8 * (o + 1) + i];
+                            for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i];
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -356,7 +370,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
 #pragma unroll 1
                     for (int i = 0; i < nvalid; ++i) {
                         if (i == wrap_at) xp -= g.ring_x;
-                        const float z = biquad2_step(sos, bq, xp[i * stride] + xp2[i]);
+                        const float z = biquad2_step(sos, bq, xp[i * stride]);
                         csum += z;
                         cs[i * 32] = csum;
                         neg |= (__float_as_uint(z) >> 31) << (31 - i);
@@ -390,7 +404,7 @@ __device__ __forceinline__ void rzcc_role(const FusedSmem &sm, const ChainParams
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kr = k - 2;
+        const int kr = k - 3;
         const int t0 = kr * kTile;
         if (kr >= 0 && t0 < T && c_valid) {
 #pragma unroll 1
@@ -573,7 +587,8 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     FusedSmem sm;
     sm.taps = reinterpret_cast<float *>(smem_raw);
     sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
-    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2 tiles][2 tap halves][kSlots*M][kQPitch]
+    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2 tiles][kSlots*M][kQPitch]: finished quadrature tiles
+    sm.qa = reinterpret_cast<float *>(smem_raw + g.off_qa);      // [2 tiles][kSlots*M][kQPitch]: running sums after the first tap half
     sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [2][kTile][kVmPitch]
     sm.is_s = reinterpret_cast<float *>(smem_raw + g.off_is);    // [kSlots][kTile][M]
     sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [2][kSegsPerTile][kSeg][32] running sums
@@ -583,7 +598,6 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.stage = reinterpret_cast<int8_t *>(smem_raw + g.off_stage);       // [2][kSlots][kTile][C2]
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
     sm.gacc = reinterpret_cast<double *>(smem_raw + g.off_gacc);
-    sm.zero = reinterpret_cast<float *>(smem_raw + g.off_zero);  // [64] zeros
     sm.dbg = sm_slots;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
@@ -609,7 +623,6 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         s_smsp[warp] = (int)(wid & 3u);
     }
     for (int i = tid; i < 8 * g.nblk + 8; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
-    for (int i = tid; i < 64; i += blockDim.x) sm.zero[i] = 0.f;
     __syncthreads();
     if (tid == 0) {
         unsigned int smid;
@@ -623,7 +636,11 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             for (int w = 0; w < kWarps; ++w) {
                 if (taken[w]) continue;
                 const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
+#ifdef MICLOC_FIR_HIGH_WARPS
+                if (c <= bestc) { bestc = c; best = w; }     // experiment: ties go to the highest warp slot
+#else
                 if (c < bestc) { bestc = c; best = w; }
+#endif
             }
             taken[best] = true;
             s_role[best] = r;
@@ -778,19 +795,21 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
                          "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
+    if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
     // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
-    g.nblk = 2 * p.fir_split;
+    g.nblk = (p.n_taps / 8 + 5) / 6 * 6;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
-    g.ring_x = ((lookback + 2 * kTile) + 31) / 32 * 32;             // history + current tile + tile being filled
+    g.ring_x = ((lookback + 3 * kTile) + 31) / 32 * 32;             // history + the two tiles in the FIR + tile being filled
     g.pitch_x = g.ring_x + 4;
     g.shift = ((p.tap_first + 14) % 16 + 16) % 16;
     // a spike at p is final once the RZCC warp passed p + rzcc_lag(w) - 1; the neuron warp works on
-    // tile k - dtile while the RZCC warp has completed tile k - 3
-    g.dtile = 3 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
+    // tile k - dtile while the RZCC warp has completed tile k - 4
+    g.dtile = 4 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
     g.tiles_is = (p.half + kTile - 1) / kTile;
     int off = ((8 * g.nblk + 8) * (int)sizeof(float) + 15) & ~15;
     g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
-    g.off_q = off; off += 2 * 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
+    g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
+    g.off_qa = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
     g.off_vm = off; off += 2 * kTile * kVmPitch * (int)sizeof(float);
     g.off_is = off; off += kSlots * kTile * p.M * (int)sizeof(float);
     g.off_cs = off; off += 2 * kSegsPerTile * kSeg * 32 * (int)sizeof(float);
@@ -799,15 +818,14 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.off_gacc = off; off += kSlots * 160 * (int)sizeof(double);
-    g.off_zero = off; off += 64 * (int)sizeof(float);
     g.smem_bytes = off;
     // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
-    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 2)
-    if (kTile * (g.dtile - 1) + p.nL + kSeg > kRingWords * 32)
+    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 3)
+    if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
     if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
-        128 * 12 > 4 * kSlots * p.M * kQPitch * (int)sizeof(float))
+        128 * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);

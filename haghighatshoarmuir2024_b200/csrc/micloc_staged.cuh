@@ -38,7 +38,7 @@ k_stht(const IN_T *__restrict__ audio, float *__restrict__ q, const float *__res
     for (int item = threadIdx.x; item < mg * chunks; item += blockDim.x) {
         const int mm = item / chunks, chunk = item % chunks;
         float acc[kFirR];
-        fir_accumulate<STRIDE>(rows + mm * pitch, taps_s, p.n_taps, p.span, p.tap_first, chunk, p.fir_split, acc);
+        fir_accumulate<STRIDE>(rows + mm * pitch, taps_s, p.n_taps, p.span, p.tap_first, chunk, acc);
         float *dst = q + (b * T + t0 + (long long)chunk * kFirR) * p.M + m0 + mm;
 #pragma unroll
         for (int i = 0; i < kFirR; ++i)

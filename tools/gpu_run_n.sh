@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-for m in 0x00 0xF0 0x0F 0xE0 0xD0 0xB0 0x70 0x0A 0x05; do
-MICLOC_FUSED_SKIP=$m python bench.py --steps 3 --warmup 2 --clips-per-band 1184 --no-cpu > gpurun_out/skip_$m.json 2>/dev/null
-python -c "
-import json
-d=json.load(open('gpurun_out/skip_$m.json'))
-print('skip $m', round(d['value']), 'clips/s', round(d['ms_per_step'],2),'ms/step')
-"
-done
+run() { python bench.py --steps 3 --warmup 2 --clips-per-band 1184 --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$1', round(d['value']), 'clips/s', round(d['ms_per_step'],2),'ms/step')"; }
+MICLOC_FUSED_FIRBLOCKS=3 run "firblocks=3 (all roles)"
+MICLOC_FUSED_FIRBLOCKS=3 MICLOC_FUSED_SKIP=0xE0 run "firblocks=3 + bandpass only"
+MICLOC_FUSED_FIRBLOCKS=3 MICLOC_FUSED_SKIP=0x80 run "firblocks=3, no gram"
+MICLOC_FUSED_FIRBLOCKS=3 MICLOC_FUSED_SKIP=0xC0 run "firblocks=3, no neuron/gram"
+MICLOC_FUSED_FIRBLOCKS=9 run "firblocks=9 (all roles)"
+run "full"
