@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmicloc_b200.so")
+# MICLOC_B200_LIB points the loader at an instrumented build of the same library (tools/role_timing.py)
+LIB_PATH = os.environ.get("MICLOC_B200_LIB") or os.path.join(CSRC, "libmicloc_b200.so")
 
 F32, I16 = 0, 1
 ERR_SHAPE, ERR_CONFIG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = -1, -2, -3, -4, -5
@@ -70,6 +71,7 @@ SYMBOLS = {
     "micloc_snn_debug_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "micloc_snn_debug_cta_times": (C.c_int, [_vp, C.POINTER(C.c_uint64), _i32]),
     "micloc_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "micloc_sched_probe": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

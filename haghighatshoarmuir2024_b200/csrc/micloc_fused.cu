@@ -60,6 +60,7 @@ struct FusedGeom {
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
+    int stagger;     // cycles by which clip-pair group 1 of a CTA starts behind group 0 (see k_fused)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
     int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_gacc, off_qa;   // byte offsets in dynamic smem
     int smem_bytes;
@@ -109,8 +110,9 @@ __device__ __forceinline__ void fir_block(unsigned long long (&acc)[8], const Ch
     }
 }
 
-// All four warps meet here once per pipeline step (the roles run different code).
-__device__ __forceinline__ void tile_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+// The eight warps of one clip-pair group meet here once per pipeline step (the roles run different code);
+// every group of a CTA owns one named barrier.
+__device__ __forceinline__ void tile_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
 
 // Optional role timing (MICLOC_ROLE_TIMING): busy cycles of each warp role between barriers, summed into
 // the 64-bit counters at sm_slots[kSlotDbg] (busy of roles 0..7, then the number of warps that reported
@@ -133,21 +135,21 @@ struct RoleTimer {
         asm volatile("{ .reg .u32 d; mov.u32 d, %1; mov.u64 %0, %%clock64; }" : "=l"(t) : "r"(v));
         t0 = t;
     }
-    __device__ __forceinline__ void flush(unsigned int *sm_slots, int role, int lane) {
+    __device__ __forceinline__ void flush(unsigned int *sm_slots, int role, int lane, int rec) {
         if (lane == 0) {
             atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg) + role, (unsigned long long)busy);
             atomicAdd(reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg) + 8 + role, 1ull);
-            if (blockIdx.x < 512)
-                (reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * blockIdx.x)[4 + role] = (unsigned long long)busy;
+            if (rec < 512)
+                (reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * rec)[4 + role] = (unsigned long long)busy;
         }
     }
 };
 #define ROLE_TIMER_DECL RoleTimer rt_; rt_.start()
-#define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(); rt_.after_barrier(); } while (0)
-#define ROLE_TIMER_FLUSH(role) rt_.flush(sm.dbg, role, lane)
+#define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(sm.bar_id); rt_.after_barrier(); } while (0)
+#define ROLE_TIMER_FLUSH(role) rt_.flush(sm.dbg, role, lane, sm.rec)
 #else
 #define ROLE_TIMER_DECL
-#define ROLE_BARRIER() tile_barrier()
+#define ROLE_BARRIER() tile_barrier(sm.bar_id)
 #define ROLE_TIMER_FLUSH(role)
 #endif
 
@@ -160,6 +162,8 @@ struct FusedSmem {
     double *gram;           // [kSlots][16][16], clip epilogue only (reuses the audio rings)
     double *gacc;           // [kSlots][10 block pairs][16] float64 Gram accumulators
     unsigned int *dbg;      // sm_slots (debug counters behind the first 256 entries)
+    int bar_id;             // named barrier of this clip-pair group
+    int rec;                // index of this group's debug record (MICLOC_ROLE_TIMING builds)
 };
 constexpr int kSegsPerTile = kTile / kSeg;
 
@@ -577,13 +581,101 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
     ROLE_TIMER_FLUSH(7);
 }
 
-template <typename IN_T, int MM>
-__global__ void __launch_bounds__(kThreads, 2)
+// GROUPS = 1: a CTA is one clip-pair group of eight warps, two CTAs per SM, FIR roles placed per SM
+//             sub-partition at run time (hardware warp slots of a second CTA are not known in advance).
+// GROUPS = 2: ONE CTA of sixteen warps per SM holding two independent clip-pair groups (own named barrier,
+//             own shared-memory region, own clip pairs).  The warp slots are then known: warps 0..7 are the
+//             FIR warps (two per sub-partition, one of each group), warps 8..15 the serial roles.  The
+//             scheduler of a sub-partition prefers the eligible warp with the highest warp id, so the
+//             latency-bound serial roles (a chain of dependent instructions per sample) always win their few
+//             issue slots and run at their dependency-chain pace, while the FIR warps fill every remaining
+//             FMA-pipe cycle; with the FIR warps in front the serial roles starve behind a stream of
+//             independent FFMA2s and FIR and serial phases alternate instead of overlapping.
+template <typename IN_T, int MM, int GROUPS>
+__global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 2 : 1)
 k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
         int8_t *__restrict__ spikes, float *__restrict__ power, int32_t *__restrict__ doa,
         int32_t *__restrict__ flags, unsigned int *__restrict__ sm_slots,
         const __grid_constant__ ChainParams p, const __grid_constant__ FusedGeom g, long long B, long long T) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    __shared__ int s_smsp[kWarps * GROUPS], s_role[kWarps * GROUPS];
+    __shared__ long long s_pair[GROUPS];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = MM ? MM : p.M, C2 = 2 * M;
+#ifdef MICLOC_ROLE_TIMING
+    long long dbg_c0 = rt_clock();
+    unsigned long long dbg_g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+#endif
+
+    // ---- which group and role this warp serves ----
+    int group = 0, role;
+    if (GROUPS == 1) {
+        // A hardware warp slot w belongs to SM sub-partition w % 4, and the FMA pipe of a sub-partition is
+        // what the FIR warps compete for: the four FIR roles go to the warps of this CTA whose sub-partition
+        // holds the fewest FIR warps of the CTAs already resident on this SM (counters per SM in
+        // sm_slots[4*smid + smsp], reset per launch); the other four roles follow in warp order, rotated by
+        // two for every second CTA of an SM so that the band-pass / Gram warps (the ones with FMA work)
+        // spread out.
+        if (lane == 0) {
+            unsigned int wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            s_smsp[warp] = (int)(wid & 3u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned int *fir_cnt = sm_slots + 4 * (smid & 255u);
+            const unsigned int arrival = atomicAdd(sm_slots + kSlotPair + 1 + (smid & 255u) % 254u, 1u);
+            bool taken[kWarps];
+            for (int w = 0; w < kWarps; ++w) { taken[w] = false; s_role[w] = -1; }
+            for (int r = 0; r < kFirWarps; ++r) {
+                int best = -1; unsigned int bestc = 0xffffffffu;
+                for (int w = 0; w < kWarps; ++w) {
+                    if (taken[w]) continue;
+                    const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
+#ifdef MICLOC_FIR_HIGH_WARPS
+                    if (c <= bestc) { bestc = c; best = w; }     // experiment: ties go to the highest warp slot
+#else
+                    if (c < bestc) { bestc = c; best = w; }
+#endif
+                }
+                taken[best] = true;
+                s_role[best] = r;
+                atomicAdd(fir_cnt + s_smsp[best], 1u);
+            }
+            int next = (int)(2u * (arrival & 1u));
+            for (int w = 0; w < kWarps; ++w)
+                if (!taken[w]) { s_role[w] = kFirWarps + (next & 3); ++next; }
+        }
+        __syncthreads();
+        role = s_role[warp];
+    } else {
+        // warps 0..3: FIR of group 0, 4..7: FIR of group 1 (one per sub-partition each); warps 8..11 / 12..15:
+        // band-pass, RZCC, neuron, Gram of group 0 / 1, rotated by two between the groups so that the two
+        // roles with FMA work (band-pass, Gram) of a sub-partition are of different kinds
+        if (warp < 2 * kFirWarps) {
+            group = warp >> 2;
+            role = warp & 3;
+        } else {
+            group = (warp - 2 * kFirWarps) >> 2;
+            role = kFirWarps + (((warp & 3) + 2 * group) & 3);
+        }
+        if (lane == 0) {
+            unsigned int wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            s_smsp[warp] = (int)(wid & 3u);
+            s_role[warp] = role;
+        }
+    }
+    // 0..3: FIR (+ fill) of clip slot role >> 1, tap half role & 1; 4: band-pass; 5: RZCC; 6: neuron; 7: Gram
+    const int tid = role * 32 + lane;       // thread index inside the group
+    const int bar_id = 1 + group;
+    auto group_sync = [&]() { tile_barrier(bar_id); };
+
+    unsigned char *smem_raw = smem_all + (size_t)group * g.smem_bytes;
     FusedSmem sm;
     sm.taps = reinterpret_cast<float *>(smem_raw);
     sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
@@ -599,87 +691,50 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
     sm.gacc = reinterpret_cast<double *>(smem_raw + g.off_gacc);
     sm.dbg = sm_slots;
-    double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [128], clip epilogue only
-    int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + 128 * sizeof(double));
-    __shared__ int s_smsp[kWarps], s_role[kWarps];
-    __shared__ long long s_pair;
+    sm.bar_id = bar_id;
+    sm.rec = GROUPS * (int)blockIdx.x + group;
+    double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [kThreads], clip epilogue only
+    int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + kThreads * sizeof(double));
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = MM ? MM : p.M, C2 = 2 * M;
-#ifdef MICLOC_ROLE_TIMING
-    long long dbg_c0 = rt_clock();
-    unsigned long long dbg_g0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
-#endif
-
-    // Role assignment.  A hardware warp slot w belongs to SM sub-partition w % 4, and the FMA pipe of a
-    // sub-partition is what the FIR warps compete for: the four FIR roles go to the warps of this CTA whose
-    // sub-partition holds the fewest FIR warps of the CTAs already resident on this SM (counters per SM in
-    // sm_slots[4*smid + smsp], reset per launch); the other four roles follow in warp order, rotated by two
-    // for every second CTA of an SM so that the band-pass / Gram warps (the ones with FMA work) spread out.
-    if (lane == 0) {
-        unsigned int wid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        s_smsp[warp] = (int)(wid & 3u);
-    }
-    for (int i = tid; i < 8 * g.nblk + 8; i += blockDim.x) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned int *fir_cnt = sm_slots + 4 * (smid & 255u);
-        const unsigned int arrival = atomicAdd(sm_slots + kSlotPair + 1 + (smid & 255u) % 254u, 1u);
-        bool taken[kWarps];
-        for (int w = 0; w < kWarps; ++w) { taken[w] = false; s_role[w] = -1; }
-        for (int r = 0; r < kFirWarps; ++r) {
-            int best = -1; unsigned int bestc = 0xffffffffu;
-            for (int w = 0; w < kWarps; ++w) {
-                if (taken[w]) continue;
-                const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
-#ifdef MICLOC_FIR_HIGH_WARPS
-                if (c <= bestc) { bestc = c; best = w; }     // experiment: ties go to the highest warp slot
-#else
-                if (c < bestc) { bestc = c; best = w; }
-#endif
-            }
-            taken[best] = true;
-            s_role[best] = r;
-            atomicAdd(fir_cnt + s_smsp[best], 1u);
-        }
-        int next = (int)(2u * (arrival & 1u));
-        for (int w = 0; w < kWarps; ++w)
-            if (!taken[w]) { s_role[w] = kFirWarps + (next & 3); ++next; }
-    }
-    __syncthreads();
-    // 0..3: FIR (+ fill) of clip slot role >> 1, tap half role & 1; 4: band-pass; 5: RZCC; 6: neuron; 7: Gram
-    const int role = s_role[warp];
+    for (int i = tid; i < 8 * g.nblk + 8; i += kThreads) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
 
     const int NT = (int)((T + kTile - 1) / kTile);
     const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 tiles behind
     const long long npairs = (B + kSlots - 1) / kSlots;
 
-    // Clip pairs are handed out dynamically: co-resident CTAs do not run at the same speed, so a static
+    // The two FIR warps of a sub-partition (one per group) share its FMA pipe.  Started together they stay
+    // in phase for the whole launch (equal work per tile): both are inside their tap loop at the same time,
+    // and both are outside it (tile hand-over, audio fill, barrier) at the same time, when the pipe idles.
+    // Group 1 therefore starts a fraction of a tile period late; the offset is neutrally stable, and one
+    // group's hand-over then hides behind the other's tap loop.
+    if (GROUPS == 2 && group == 1 && g.stagger > 0) {
+        long long t0, t1;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
+        do { asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1)); } while (t1 - t0 < (long long)g.stagger);
+    }
+
+    // Clip pairs are handed out dynamically: co-resident groups do not run at the same speed, so a static
     // split would wait for the slowest one.
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_pair = (long long)atomicAdd(sm_slots + kSlotPair, 1u);
-        __syncthreads();
-        const long long pair = s_pair;
+        group_sync();
+        if (tid == 0) s_pair[group] = (long long)atomicAdd(sm_slots + kSlotPair, 1u);
+        group_sync();
+        const long long pair = s_pair[group];
         if (pair >= npairs) break;
         const long long clip0 = pair * kSlots;
         {   // zero the audio rings: samples before the clip start are zeros (lfilter's zero state)
             float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
             const int n4 = kSlots * M * g.pitch_x / 4;
-            for (int i = tid; i < n4; i += blockDim.x) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < n4; i += kThreads) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             // no spikes before the clip start; membrane columns of unused lanes stay zero
-            for (int i = tid; i < 2 * kRingWords * 32; i += blockDim.x) sm.bits[i] = 0u;
-            for (int i = tid; i < 2 * kTile * kVmPitch; i += blockDim.x) sm.vms[i] = 0.f;
-            for (int i = tid; i < kSlots * 160; i += blockDim.x) sm.gacc[i] = 0.0;
+            for (int i = tid; i < 2 * kRingWords * 32; i += kThreads) sm.bits[i] = 0u;
+            for (int i = tid; i < 2 * kTile * kVmPitch; i += kThreads) sm.vms[i] = 0.f;
+            for (int i = tid; i < kSlots * 160; i += kThreads) sm.gacc[i] = 0.0;
         }
-        __syncthreads();
+        group_sync();
 
         if ((g.skip >> role) & 1) {
-            for (int k = -1; k <= k_last; ++k) tile_barrier();
+            for (int k = -1; k <= k_last; ++k) tile_barrier(bar_id);
         } else if (role < kFirWarps)
             fir_role<IN_T, MM>(sm, p, g, audio, clip0 + (role >> 1), clip0 + (role >> 1) < B, T, role >> 1, role & 1, lane,
                                NT, k_last);
@@ -687,9 +742,9 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         else if (role == 5) rzcc_role(sm, p, flags, clip0, B, T, M, lane, k_last);
         else if (role == 6) neuron_role(sm, p, g, clip0, B, T, M, lane, k_last);
         else gram_role(sm, g, spikes, clip0, B, T, M, lane, k_last);
-        __syncthreads();
+        group_sync();
         // unpack the block-pair accumulators into full symmetric matrices (the audio rings are dead now)
-        for (int e = tid; e < kSlots * 160; e += blockDim.x) {
+        for (int e = tid; e < kSlots * 160; e += kThreads) {
             const int sl = e / 160, pr0 = (e % 160) / 16, kk = e % 16;
             int bi = 0, bj = 0, pr = pr0;
             for (int r = 0; r < 4; ++r) {
@@ -702,59 +757,70 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             sm.gram[sl * 256 + row * 16 + col] = v;
             if (bi != bj) sm.gram[sl * 256 + col * 16 + row] = v;
         }
-        __syncthreads();
+        group_sync();
 
-        // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax (threads 0..127) ----
+        // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
+        // one DoA column per thread and pass: its 2M weights are fetched first (independent loads, one
+        // memory latency), then the quadratic form runs from registers and shared memory
         const double inv_T = 1.0 / (double)T;
         for (int s = 0; s < kSlots; ++s) {
             const long long clip = clip0 + s;
             if (clip >= B) break;
             const double *Cd = sm.gram + s * 256;
             double best = -1.0; int besti = 0x7fffffff;
-            if (tid < 128) {
-                for (int gg = tid; gg < p.G; gg += 128) {
-                    double accp = 0.0;
-#pragma unroll 1
-                    for (int r = 0; r < C2; ++r) {
-                        double rr = 0.0;
+            for (int gg = tid; gg < p.G; gg += kThreads) {
+                double w[2 * kRows];
+#pragma unroll
+                for (int c = 0; c < 2 * kRows; ++c) w[c] = c < C2 ? Wd[(long long)c * p.G + gg] : 0.0;
+                double accp = 0.0;
 #pragma unroll 2
-                        for (int c = 0; c < C2; ++c) rr = fma(Cd[r * 16 + c], Wd[(long long)c * p.G + gg], rr);
-                        accp = fma(Wd[(long long)r * p.G + gg], rr, accp);
-                    }
-                    accp *= inv_T;
-                    if (power) power[clip * p.G + gg] = (float)accp;
-                    if (accp > best) { best = accp; besti = gg; }
+                for (int r = 0; r < C2; ++r) {
+                    double rr = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 2 * kRows; ++c)
+                        if (c < C2) rr = fma(Cd[r * 16 + c], w[c], rr);
+                    double wr = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 2 * kRows; ++c) wr = c == r ? w[c] : wr;
+                    accp = fma(wr, rr, accp);
                 }
-                red_v[tid] = best; red_i[tid] = besti;
+                accp *= inv_T;
+                if (power) power[clip * p.G + gg] = (float)accp;
+                if (accp > best) { best = accp; besti = gg; }
             }
-            __syncthreads();
-            for (int st = 64; st > 0; st >>= 1) {
+            red_v[tid] = best; red_i[tid] = besti;
+            group_sync();
+            for (int st = kThreads / 2; st > 0; st >>= 1) {
                 if (tid < st) {
                     const double ov = red_v[tid + st]; const int oi = red_i[tid + st];
                     if (ov > red_v[tid] || (ov == red_v[tid] && oi < red_i[tid])) { red_v[tid] = ov; red_i[tid] = oi; }
                 }
-                __syncthreads();
+                group_sync();
             }
             if (tid == 0 && doa) doa[clip] = red_i[0];
-            __syncthreads();
+            group_sync();
         }
     }
 #ifdef MICLOC_ROLE_TIMING
-    if (blockIdx.x == 0 && tid == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long g1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotDbg);
         d[16] = (unsigned long long)(rt_clock() - dbg_c0);
         d[17] = g1 - dbg_g0;
     }
-    if (tid == 0 && blockIdx.x < 512) {
+    if (tid == 0 && GROUPS * blockIdx.x + group < 512) {
         unsigned long long g1;
         unsigned int smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * blockIdx.x;
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * (GROUPS * blockIdx.x + group);
         unsigned long long map = 0;
-        for (int w = 0; w < kWarps; ++w) map |= (unsigned long long)((s_role[w] & 7) | ((s_smsp[w] & 3) << 3)) << (8 * w);
+        for (int w = 0; w < kWarps * GROUPS; ++w)
+            if (GROUPS == 1 || ((w < 2 * kFirWarps ? w >> 2 : (w - 2 * kFirWarps) >> 2) == group)) {
+                const int r = s_role[w] & 7;
+                map |= (unsigned long long)(r | ((s_smsp[w] & 3) << 3)) << (8 * r);
+            }
         d[0] = dbg_g0; d[1] = g1; d[2] = smid; d[3] = map;     // d[4..11]: busy cycles per role
     }
 #endif
@@ -764,23 +830,25 @@ bool fused_supported(const ChainParams &p) {
     return p.tap_stride == 2 && p.M <= kRows && p.nsec == 2 && (p.n_taps % 8) == 0;
 }
 
-template <typename IN_T, int MM>
+template <typename IN_T, int MM, int GROUPS>
 static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float *d_taps, const double *d_Wd,
                           const IN_T *audio, long long B, long long T, int8_t *spikes, float *power, int32_t *doa,
                           int32_t *flags, unsigned int *sm_slots, int sm_count, cudaStream_t st) {
-    auto kern = k_fused<IN_T, MM>;
-    MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-    // all of the SM's L1/shared array as shared memory: two CTAs of ~100 KB must be resident together
+    auto kern = k_fused<IN_T, MM, GROUPS>;
+    const int smem = GROUPS * g.smem_bytes;
+    MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // all of the SM's L1/shared array as shared memory: two clip-pair groups of ~100 KB must be resident together
     MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 1;
-    MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, g.smem_bytes));
-    if (per_sm > 2) per_sm = 2;     // the role placement balances two CTAs per SM
-    if (per_sm < 1) return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel does not fit (smem %d B)", g.smem_bytes);
+    MICLOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads * GROUPS, smem));
+    if (per_sm > 2 / GROUPS) per_sm = 2 / GROUPS;     // two groups per SM: the role placement balances exactly two
+    if (per_sm < 1) return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel does not fit (smem %d B)", smem);
     long long grid = (long long)sm_count * per_sm;
     const long long npairs = (B + kSlots - 1) / kSlots;
-    if (grid > npairs) grid = npairs;
+    const long long want = (npairs + GROUPS - 1) / GROUPS;
+    if (grid > want) grid = want;
     MICLOC_CUDA(cudaMemsetAsync(sm_slots, 0, kSlotResetWords * sizeof(unsigned int), st));   // FIR placement counters + pair counter restart per launch
-    kern<<<(unsigned)grid, kThreads, g.smem_bytes, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
+    kern<<<(unsigned)grid, kThreads * GROUPS, smem, st>>>(audio, d_taps, d_Wd, spikes, power, doa, flags, sm_slots, p, g, B, T);
     count_launch(1);
     MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
@@ -796,6 +864,8 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
+    g.stagger = 0;
+    if (const char *e = getenv("MICLOC_FUSED_STAGGER")) g.stagger = (int)strtol(e, nullptr, 0);
     // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
     g.nblk = (p.n_taps / 8 + 5) / 6 * 6;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
@@ -818,21 +888,30 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.off_gacc = off; off += kSlots * 160 * (int)sizeof(double);
-    g.smem_bytes = off;
+    g.smem_bytes = (off + 15) & ~15;
     // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
     // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 3)
     if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
     if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
-        128 * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
+        kThreads * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);
     if (T + 16 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
-#define MICLOC_FUSED_CASE(IN, MMV)                                                                        \
-    return launch_fused_t<IN, MMV>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa, flags, \
-                                   sm_slots, sm_count, st)
+    // one CTA of two clip-pair groups per SM when both fit its shared memory (the usual case), else the
+    // single-group CTA twice per SM; MICLOC_FUSED_GROUPS=1 forces the latter (A/B measurements)
+    int groups = 2 * g.smem_bytes <= 227 * 1024 ? 2 : 1;
+    if (const char *e = getenv("MICLOC_FUSED_GROUPS")) { if (atoi(e) == 1) groups = 1; }
+#define MICLOC_FUSED_CASE(IN, MMV)                                                                                \
+    do {                                                                                                          \
+        if (groups == 2)                                                                                          \
+            return launch_fused_t<IN, MMV, 2>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa,    \
+                                              flags, sm_slots, sm_count, st);                                     \
+        return launch_fused_t<IN, MMV, 1>(p, g, d_taps, d_Wd, (const IN *)audio, B, T, spikes, power, doa, flags, \
+                                          sm_slots, sm_count, st);                                                \
+    } while (0)
     const bool i16 = dtype == MICLOC_I16;
     if (p.M == 7) { if (i16) MICLOC_FUSED_CASE(int16_t, 7); else MICLOC_FUSED_CASE(float, 7); }
     if (i16) MICLOC_FUSED_CASE(int16_t, 0); else MICLOC_FUSED_CASE(float, 0);

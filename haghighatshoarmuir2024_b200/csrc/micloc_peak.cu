@@ -100,6 +100,154 @@ k_peak_mixed(float *out, int iters, float a, float b, double da, double db) {
     if (s == 123.456f) out[0] = s;
 }
 
+
+// ---------------------------------------------------------------------------
+// Scheduler probe (diagnostics for the warp-specialised fused kernel): one CTA of up to 16 warps per SM,
+// every warp runs one instruction stream chosen by roles[warp] for iters x 1000 cycles (all warps run side
+// by side for the whole measurement) and reports its clock64 cycles and the instructions it got through.  Hardware warp slot w belongs to SM sub-partition w % 4.
+//   0 idle   1 FFMA2 stream (8 independent accumulators)   2 dependent scalar FFMA chain
+//   3 independent ALU stream (8 chains of LOP3/IADD3)       4 independent scalar FFMA stream (16 accumulators)
+//   5 dependent chain alternating FFMA and ALU               6 FFMA2 stream, 64 per round then 8 ALU ops
+//   7 dependent DFMA chain                                    8 independent DFMA stream (8 accumulators)
+// out[warp] = cycles of CTA 0's warp, out[16 + warp] = instructions of the measured kind it issued.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsigned long long *out, float *sink) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int role = roles[warp];
+    __syncthreads();
+    long long t0, t1;
+    unsigned long long n_inst = 0;
+    float res = 0.f;
+    int rounds_done = 0;
+    auto probe_running = [&](long long start, int kcyc, int it) {
+        long long now;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now));
+        rounds_done = it;
+        return now - start < 1000ll * kcyc;
+    };
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
+    if (role == 1 || role == 6) {
+        unsigned long long acc[8], av, bv;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(lo), "f"(hi));
+        }
+        unsigned int x = threadIdx.x;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(av), "l"(bv));
+            if (role == 6) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(it), "r"(i));
+            }
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+            res += lo + hi;
+        }
+        res += (float)x;
+    } else if (role == 2) {
+        float x = (float)threadIdx.x;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(a), "f"(b));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+        res = x;
+    } else if (role == 3) {
+        unsigned int x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(it), "r"(r));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res += (float)x[i];
+    } else if (role == 4) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+        const float ar = a + (float)lane * 1e-9f, br = b + (float)lane * 1e-9f;   // register operands, not constants
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(ar), "f"(br));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) res += acc[i];
+    } else if (role == 5) {
+        float x = (float)threadIdx.x;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(a), "f"(b));
+                unsigned int u = __float_as_uint(x);
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u) : "r"(it), "r"(i));
+                x = __uint_as_float(u);
+            }
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+        res = x;
+    }
+    else if (role == 7) {
+        double x = (double)threadIdx.x;
+        const double da = (double)a, db = (double)b;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(da), "d"(db));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+        res = (float)x;
+    } else if (role == 8) {
+        double acc[8];
+        const double da = (double)a, db = (double)b;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = (double)(threadIdx.x + i);
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(da), "d"(db));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res += (float)acc[i];
+    }
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
+    if (res == 123.456f) sink[0] = res;
+    if (blockIdx.x == 0 && lane == 0) { out[warp] = (unsigned long long)(t1 - t0); out[16 + warp] = n_inst; }
+}
+
 }  // namespace micloc
 
 using namespace micloc;
@@ -136,5 +284,30 @@ extern "C" int micloc_fp32_peak(int device, int variant, double *tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     MICLOC_CUDA(cudaGetLastError());
     *tflops = best;
+    return MICLOC_OK;
+}
+
+extern "C" int micloc_sched_probe(int device, const int32_t roles[16], int iters, uint64_t out[32]) {
+    if (!roles || !out || iters <= 0) return set_error(MICLOC_ERR_CONFIG, "bad arguments");
+    MICLOC_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    MICLOC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int nw = 0;
+    for (int w = 0; w < 16; ++w) if (roles[w]) nw = w + 1;
+    if (nw == 0) return set_error(MICLOC_ERR_CONFIG, "no active warp");
+    int *d_roles = nullptr; unsigned long long *d_out = nullptr; float *d_sink = nullptr;
+    MICLOC_CUDA(cudaMalloc(&d_roles, 16 * sizeof(int)));
+    MICLOC_CUDA(cudaMalloc(&d_out, 32 * sizeof(unsigned long long)));
+    MICLOC_CUDA(cudaMalloc(&d_sink, sizeof(float)));
+    MICLOC_CUDA(cudaMemcpy(d_roles, roles, 16 * sizeof(int), cudaMemcpyHostToDevice));
+    MICLOC_CUDA(cudaMemset(d_out, 0, 32 * sizeof(unsigned long long)));
+    for (int rep = 0; rep < 2; ++rep) {     // the second run is the one reported (warm instruction cache)
+        k_sched_probe<<<sms, 32 * nw>>>(d_roles, iters, 0.999f, 0.001f, d_out, d_sink);
+        count_launch(1);
+        MICLOC_CUDA(cudaDeviceSynchronize());
+    }
+    MICLOC_CUDA(cudaMemcpy(out, d_out, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_roles); cudaFree(d_out); cudaFree(d_sink);
+    MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
 }
