@@ -109,6 +109,8 @@ k_peak_mixed(float *out, int iters, float a, float b, double da, double db) {
 //   3 independent ALU stream (8 chains of LOP3/IADD3)       4 independent scalar FFMA stream (16 accumulators)
 //   5 dependent chain alternating FFMA and ALU               6 FFMA2 stream, 64 per round then 8 ALU ops
 //   7 dependent DFMA chain                                    8 independent DFMA stream (8 accumulators)
+//   9 / 11 FFMA2 with the FIR operand pattern (all operands in non-uniform registers; tap scalar / tap pair)
+//   10 scalar FFMA with the FIR operand pattern
 // out[warp] = cycles of CTA 0's warp, out[16 + warp] = instructions of the measured kind it issued.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1)
@@ -242,6 +244,69 @@ k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsign
         n_inst = 1024ull * (unsigned long long)rounds_done;
 #pragma unroll
         for (int i = 0; i < 8; ++i) res += (float)acc[i];
+    }
+    else if (role == 9 || role == 11) {
+        // the FIR's operand pattern: accumulator pair += window pair * tap, all from (non-uniform) registers;
+        // role 9: the tap is one scalar register broadcast to both halves, role 11: the tap is a register pair
+        unsigned long long acc[8], win[16], tap2[8];
+        float tap[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(lo), "f"(hi));
+            tap[i] = a + 1e-6f * (float)(lane + i);
+            const float tl = tap[i], th = tap[i] + 1e-7f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(tap2[i]) : "f"(tl), "f"(th));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float lo = b + 1e-6f * (float)(lane + i), hi = lo + 1e-7f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(win[i]) : "f"(lo), "f"(hi));
+        }
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (role == 9) {
+                        unsigned long long t2;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(t2) : "f"(tap[j]));
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(win[i + 7 - j]), "l"(t2));
+                    } else {
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(win[i + 7 - j]), "l"(tap2[j]));
+                    }
+                }
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+            res += lo + hi;
+        }
+    } else if (role == 10) {
+        // scalar FFMA with the FIR's operand pattern: 16 accumulators, 23 window values, 8 taps, all registers
+        float acc[16], win[24], tap[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) win[i] = b + 1e-6f * (float)(lane + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tap[i] = a + 1e-6f * (float)(lane + i);
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 8; ++sub) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc[i]) : "f"(win[i + 7 - j]), "f"(tap[j]));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) res += acc[i];
     }
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
     if (res == 123.456f) sink[0] = res;

@@ -55,8 +55,8 @@ def test_staged_taps_match_reference_golden(name):
 def test_fused_matches_reference_golden(name):
     g = H.load(name)
     eng = engine_for(g)
-    if eng.M > 8:
-        pytest.skip("fused kernel covers up to 8 microphones; larger arrays take the staged path")
+    if eng.M > 7:
+        pytest.skip("fused kernel covers up to 7 microphones; larger arrays take the staged path")
     out = eng.run(to_dev(g["x"]), want_spikes=True, fused=True)
     torch.cuda.synchronize()
     spikes = out["spikes"][0].cpu().numpy()
@@ -68,7 +68,8 @@ def test_fused_matches_reference_golden(name):
 
 
 # ---------------------------------------------------------------------------
-# batches against the oracle: fused == staged bit for bit, both within tolerance
+# batches against the oracle: fused (fast-FIR STHT) and staged (direct-form STHT) agree within the
+# reference tolerance with each other and with the oracle
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("name,T,int16", [("snn_c1_bipolar", 4800, False), ("snn_c1_unipolar", 3000, False),
                                           ("snn_band2_sine", 4801, True), ("snn_band3_i16", 1000, True),
@@ -82,10 +83,13 @@ def test_batch_fused_vs_staged_vs_oracle(name, T, int16):
     st = eng.run(xd, want_spikes=True, fused=False)
     fu = eng.run(xd, want_spikes=True, fused=True)
     torch.cuda.synchronize()
-    # the two device paths run the same arithmetic in the same order for spikes
-    assert torch.equal(st["spikes"], fu["spikes"])
-    assert torch.equal(st["doa"], fu["doa"])
-    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < 1e-5
+    # the fused kernel's STHT is a fast FIR (three half-length sub-filters), the staged one the direct form:
+    # float32 rounding differs, so the two are compared at the tolerance both owe the reference
+    assert H.spike_agreement(fu["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= SPIKE_AGREE
+    assert (st["doa"] == fu["doa"]).float().mean().item() >= DOA_AGREE
+    same_spk = (st["spikes"] == fu["spikes"]).flatten(1).all(dim=1).cpu().numpy()
+    if same_spk.any():
+        assert H.rel_err(fu["power"].cpu().numpy()[same_spk], st["power"].cpu().numpy()[same_spk]) < 1e-5
     cfg = H.oracle_cfg(g)
     fs = float(g["fs"]); tau = float(g["tau"])
     cfg.nir = O.neuron_kernel(np.arange(T) / fs, tau, tau)
@@ -144,7 +148,8 @@ def test_full_size_config4_multi_source_360_grid():
     eng = engine_for(g, T)
     out = eng.run(to_dev(x), want_spikes=True, fused=True)
     st = eng.run(to_dev(x), want_spikes=True, fused=False)
-    assert torch.equal(out["spikes"], st["spikes"]) and torch.equal(out["doa"], st["doa"])
+    assert H.spike_agreement(out["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= SPIKE_AGREE
+    assert torch.equal(out["doa"], st["doa"])
     cfg = H.oracle_cfg(g)
     cfg.nir = O.neuron_kernel(t, float(g["tau"]), float(g["tau"]))
     ref = O.snn_run_batch(cfg, x, nthreads=3, want_spikes=True)
@@ -156,7 +161,7 @@ def test_full_size_config4_multi_source_360_grid():
 
 def test_full_size_config5_64_mics_10s_512_grid():
     """Config 5 size: one 10 s clip (T = 480 000) on the 64-microphone random array, G = 512 (staged path:
-    the fused kernel covers up to 8 microphones) against the oracle."""
+    the fused kernel covers up to 7 microphones) against the oracle."""
     g = H.load("snn_c5_random64")
     T = 480_000
     x, _ = H.synth_clips(g, 1, T, seed=51, snrs_db=(10.0,))
@@ -195,7 +200,7 @@ def test_ragged_and_tiny_clips():
         fu = eng.run(to_dev(x), want_spikes=True, fused=True)
         st = eng.run(to_dev(x), want_spikes=True, fused=False)
         torch.cuda.synchronize()
-        assert torch.equal(fu["spikes"], st["spikes"]), T
+        assert H.spike_agreement(fu["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= 0.99, T
         ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
         assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= 0.99, T
 

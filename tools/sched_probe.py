@@ -5,7 +5,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from haghighatshoarmuir2024_b200 import _native as N
 lib = N.lib()
-NAMES = {0: "-", 1: "ffma2", 2: "chain", 3: "alu", 4: "ffma", 5: "chainmix", 6: "ffma2+alu", 7: "dchain", 8: "dfma"}
+NAMES = {0: "-", 1: "ffma2", 2: "chain", 3: "alu", 4: "ffma", 5: "chainmix", 6: "ffma2+alu", 7: "dchain", 8: "dfma", 9: "fir2", 10: "fir1", 11: "fir2p"}
 
 def run(title, placement, iters=4000):
     roles = (ctypes.c_int32 * 16)(*([0] * 16))
@@ -54,3 +54,13 @@ run("ffma2 x2 + dchain", {0: 1, 4: 1, 8: 7})
 run("ffma2 x2 + dchain x2", {0: 1, 4: 1, 8: 7, 12: 7})
 run("ffma x2 + dchain x2", {0: 4, 4: 4, 8: 7, 12: 7})
 run("ffma2 x2 + dchain + chainmix", {0: 1, 4: 1, 8: 7, 12: 5})
+run("FIR-pattern ffma2 (scalar tap) x1", {0: 9})
+run("FIR-pattern ffma2 (scalar tap) x2", {0: 9, 4: 9})
+run("FIR-pattern ffma2 (scalar tap) x3", {0: 9, 4: 9, 8: 9})
+run("FIR-pattern ffma2 (pair tap) x1", {0: 11})
+run("FIR-pattern ffma2 (pair tap) x2", {0: 11, 4: 11})
+run("FIR-pattern ffma2 (pair tap) x3", {0: 11, 4: 11, 8: 11})
+run("FIR-pattern ffma x1", {0: 10})
+run("FIR-pattern ffma x2", {0: 10, 4: 10})
+run("FIR-pattern ffma x3", {0: 10, 4: 10, 8: 10})
+run("FIR-pattern ffma2 x3, all 4 SMSPs", {w: 9 for w in range(12)})
