@@ -398,7 +398,23 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                 const bool fast = ts + kSeg <= T && src0 + kSeg <= T;
                 const float carry = csum;
                 unsigned int neg = 0u, zero = 0u;
+                // sample by sample with explicit sign / zero masks (ragged segments, wrapping in-phase source, exact zeros)
+                auto slow_segment = [&](int nvalid) {
+                    int src = src0;
+#pragma unroll 1
+                    for (int i = 0; i < nvalid; ++i) {
+                        const float x = c_inphase ? to_f32<IN_T>(clip_audio[(long long)src * M + c_ch]) : qp[i];
+                        if (++src >= T) src = 0;
+                        const float z = biquad2_step(sos, bq, x);
+                        csum += z;
+                        cs[i * 32] = csum;
+                        neg |= (__float_as_uint(z) >> 31) << (31 - i);
+                        zero |= (z == 0.f ? 1u : 0u) << (31 - i);
+                    }
+                };
                 if (fast) {
+                    const BiquadState bq0 = bq;
+                    float zmin = 1.f;                   // smallest |z| of the segment: exact zeros are rare (silence)
                     float xn[8];
                     const bool pre = pre_ok && pre_src == src0;     // (warp-uniform) this segment's first in-phase group is here already
 #pragma unroll
@@ -427,23 +443,16 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                             csum += z;
                             cs[(8 * o + i) * 32] = csum;
                             neg = __funnelshift_l(__float_as_uint(z), neg, 1);
-                            zero = __funnelshift_l(z == 0.f ? 0x80000000u : 0u, zero, 1);
+                            zmin = fminf(zmin, fabsf(z));
                         }
+                    }
+                    if (zmin == 0.f) {                  // redo this lane's segment for its zero mask (same arithmetic)
+                        bq = bq0; csum = carry; neg = 0u;
+                        slow_segment(kSeg);
                     }
                 } else {
                     pre_ok = false;
-                    const int nvalid = T - ts < kSeg ? T - ts : kSeg;
-                    int src = src0;
-#pragma unroll 1
-                    for (int i = 0; i < nvalid; ++i) {
-                        const float x = c_inphase ? to_f32<IN_T>(clip_audio[(long long)src * M + c_ch]) : qp[i];
-                        if (++src >= T) src = 0;
-                        const float z = biquad2_step(sos, bq, x);
-                        csum += z;
-                        cs[i * 32] = csum;
-                        neg |= (__float_as_uint(z) >> 31) << (31 - i);
-                        zero |= (z == 0.f ? 1u : 0u) << (31 - i);
-                    }
+                    slow_segment(T - ts < kSeg ? T - ts : kSeg);
                 }
                 sgm[0] = neg; sgm[32] = zero; sgm[64] = __float_as_uint(carry);
             }
@@ -544,20 +553,20 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                     float vq[4];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        // neuron_step with s, sd in {-1, 0, +1} given as bits
-                        nr.p2 = na * (nr.p2 + nr.p1);
+                        // neuron_step with s, sd in {-1, 0, +1} given as bits; a (p2 + p1) as a p2 + (a p1): the
+                        // product a p1 is needed for p1 anyway
                         float a1 = na * nr.p1;
+                        nr.p2 = fmaf(na, nr.p2, a1);
                         if (P & (1u << i)) a1 += 1.f;
                         if (Nn & (1u << i)) a1 -= 1.f;
                         nr.p1 = a1;
-                        nr.q2 = na * (nr.q2 + nr.q1);
                         float b1 = na * nr.q1;
+                        nr.q2 = fmaf(na, nr.q2, b1);
                         if (PD & (1u << i)) b1 += 1.f;
                         if (ND & (1u << i)) b1 -= 1.f;
                         nr.q1 = b1;
                         const float tail = fmaf(nLf, nr.q1, nr.q2);
-                        float v = fmaf(-ncT, tail, nc * nr.p2);
-                        if (8 * o + i >= nvalid) v = 0.f;
+                        const float v = fmaf(-ncT, tail, nc * nr.p2);
                         vq[i & 3] = v;
                         if ((i & 3) == 3)
                             *reinterpret_cast<float4 *>(vseg + 8 * o + i - 3) = make_float4(vq[0], vq[1], vq[2], vq[3]);
@@ -565,6 +574,8 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                     }
                     P >>= 8; Nn >>= 8; PD >>= 8; ND >>= 8;
                 }
+                // the membrane potential behind the clip end does not count (ragged last segment)
+                for (int i = nvalid; i < kSeg; ++i) vseg[i] = 0.f;
             }
         }
         ROLE_BARRIER();
@@ -685,7 +696,7 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
 //             (~5500 slots per tile).
 // GROUPS = 1: a CTA is one group of eight warps (two CTAs per SM), role = warp; the fallback when two
 //             groups do not fit the shared memory of one CTA (long STHT kernels).
-static const unsigned char kRoleMaps[3][16] = {
+static const unsigned char kRoleMaps[4][16] = {
     // layout 0 (mixed): (group << 3 | role) of warp 4 i + sub-partition
     {0 << 3 | 0, 0 << 3 | 1, 0 << 3 | 2, 1 << 3 | 2,
      1 << 3 | 0, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
@@ -700,7 +711,12 @@ static const unsigned char kRoleMaps[3][16] = {
     {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
      0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
      1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
-     1 << 3 | kRoleGram, 0 << 3 | kRoleGram, 0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader}};
+     1 << 3 | kRoleGram, 0 << 3 | kRoleGram, 0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader},
+    // layout 3: FIR 0, 1 + RZCC + loader | FIR 2 + band-pass + neuron + Gram
+    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
+     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
+     1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
+     1 << 3 | kRoleLoader, 0 << 3 | kRoleLoader, 0 << 3 | kRoleGram, 1 << 3 | kRoleGram}};
 
 template <typename IN_T, int MM, int GROUPS>
 __global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 2 : 1)
@@ -916,7 +932,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     {
         int layout = 2;
         if (const char *e = getenv("MICLOC_FUSED_LAYOUT")) layout = atoi(e);     // role placement experiments
-        for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[layout >= 0 && layout < 3 ? layout : 2][w];
+        for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[layout >= 0 && layout < 4 ? layout : 2][w];
     }
     // sub-filters of n_taps / 2 taps in blocks of 8, walked in groups of three (zero taps appended)
     const int sub_taps = (p.n_taps + 1) / 2;
