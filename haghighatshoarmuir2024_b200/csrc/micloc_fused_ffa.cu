@@ -1,26 +1,25 @@
-// micloc_fused.cu -- the fused hot-path kernel: raw audio in, spikes + per-DoA
+// micloc_fused_ffa.cu -- fast-FIR variant of the fused hot-path kernel (MICLOC_FUSED_FIR=ffa; micloc_fused.cu is the default): raw audio in, spikes + per-DoA
 // power + DoA index out; nothing else touches HBM.
 //
 // Reference sites: micloc/snn_beamformer.py:283-370 and the callers' power/argmax
 // paper_plots/target_snn_localization.py:462-464.
 //
-// One persistent CTA of eight warps owns kSlots = 2 clips at a time and walks them in time tiles
-// of kTile = 64 samples.  The warps are specialised BY FUNCTION (every role serves both clips with
-// all its lanes, so that the serial depth of each role per tile is short) and run as a software
-// pipeline, one barrier per tile (iteration k):
+// A clip-pair GROUP of eight warps owns kSlots = 2 clips at a time and walks them in time tiles of
+// kTile = 64 samples.  The warps are specialised BY FUNCTION (every role serves both clips with all its
+// lanes, so that the serial depth of each role per tile is short) and run as a software pipeline, one
+// named barrier per tile (iteration k):
 //
-//   FIR warps x4 tile k+1   audio (HBM) -> mic-major ring in shared memory (two warps per clip, 32
-//                           samples each)
-//                tile k     STHT quadrature FIR, first half of the taps: every lane owns 16
-//                           consecutive outputs of one microphone and walks 120 of the 240 non-zero
-//                           Hilbert taps in blocks of 8 with a sliding register window; the
-//                           multiply-adds are packed FFMA2 (fma.rn.f32x2)
-//                tile k-1   second warp of the clip: continues the SAME running sums (handed over
-//                           in shared memory) through the other 120 taps: the summation order is
-//                           that of one warp walking all taps
-//   band-pass    tile k-2   one lane per (clip, channel): SOS band-pass recurrence, running sum,
-//                           sign / zero bit masks of every 32-sample segment -> shared memory
-//   RZCC         tile k-3   one lane per (clip, channel): the masks are turned into RZCC
+//   loader       tile k+1   audio (HBM) -> the three sub-sequence rings of every microphone in shared
+//                           memory (see "fast FIR" below)
+//   FIR warps x3 tile k     STHT quadrature FIR as three half-length sub-filters; every lane owns 8
+//                           consecutive output pairs of one (microphone, sub-filter) and walks its 120
+//                           taps in blocks of 8 with a sliding register window (packed FFMA2, see fir_block);
+//                           the three partial results are recombined inside the warp and the finished
+//                           quadrature tile goes to shared memory
+//   band-pass    tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
+//                           sign / zero bit masks of every 32-sample segment -> shared memory; the
+//                           in-phase input x[(t - K/2) mod T] (np.roll) is re-read from global memory (L2)
+//   RZCC         tile k-2   one lane per (clip, channel): the masks are turned into RZCC
 //                           candidates and resolved (find_peaks distance rule) into a bit-packed
 //                           spike ring
 //   neuron       tile k-d   (d = the latency of the exact find_peaks decision) one lane per (clip,
@@ -30,9 +29,22 @@
 //                           raster of the tile -> HBM
 //   clip end                power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 //
-// Two CTAs are resident per SM; the FIR roles go to the warps whose SM sub-partition holds the
-// fewest FIR warps so far, so that every sub-partition's FMA pipe always has two FIR warps to
-// keep it busy (one alone leaves it idle whenever it loses an issue slot to another warp).
+// Fast FIR.  The Hilbert kernel has taps only at every other lag, h[k0 + 2j] = c_j: on pairs of
+// consecutive samples r[i] = (x[2i-k0], x[2i+1-k0]) and output pairs Y[p] = (Q[2p], Q[2p+1]) it is the dense
+// FIR Y[p] = sum_j c_j r[p-j] (both samples of a pair take the same tap).  Splitting
+// taps and pairs by parity (A_n = c_2n, B_n = c_2n+1, R0[m] = r[2m], R1[m] = r[2m+1]) gives
+//      Y[2m]   = (A*R0)[m] + (B*R1)[m-1]
+//      Y[2m+1] = (A*R1)[m] + (B*R0)[m]  =  ((A+B)*(R0+R1))[m] - (A*R0)[m] - (B*R1)[m]
+// i.e. THREE convolutions of half length U = A*R0, V = B*R1, W = (A+B)*(R0+R1) instead of four: a quarter
+// of the multiply-adds of the direct form is never executed (a 2-parallel fast FIR algorithm; the float32
+// error against the float64 reference stays at the direct form's ~1e-6 relative).  The loader keeps R0, R1
+// and S = R0 + R1 of every microphone in three rings, so that each sub-filter is the same register-blocked
+// sliding-window loop on its own ring with its own tap array.
+//
+// Issue slots, not the FMA pipe alone, bound this kernel: an FFMA2 occupies two issue slots of its SM
+// sub-partition (tools/sched_probe.py), so every instruction of the serial roles displaces half an FFMA2.
+// One CTA holds two groups (GROUPS = 2, sixteen warps, one CTA per SM); the roles are laid out over the four
+// sub-partitions so that their instruction counts per tile balance (see k_fused).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -40,30 +52,36 @@
 #include "micloc_common.h"
 
 namespace micloc {
+namespace ffa {
 
 constexpr int kTile = 64;      // samples per pipeline step
-constexpr int kSlots = 2;      // clips per CTA
-constexpr int kRows = 8;       // most microphones per clip the lane maps cover
+constexpr int kSlots = 2;      // clips per group
+constexpr int kRows = 7;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmRows = 16 * kSlots;    // membrane tile rows: [slot][16 channels] (channels 14, 15 stay zero)
 constexpr int kVmPitch = kTile + 4;     // floats per row of the membrane tile (channel-major: ldmatrix rows of 4 samples)
-constexpr int kRingWords = 32; // spike-bit ring: 32 words of 32 samples per channel and polarity
-constexpr int kWarps = 8;      // 4 x FIR (clip slot x tap half), band-pass, RZCC, neuron, Gram
-constexpr int kFirWarps = 4;
+constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
+constexpr int kWarps = 8;      // 3 x FIR (sub-filter rows), loader, band-pass, RZCC, neuron, Gram
+constexpr int kFirWarps = 3;
+constexpr int kRoleLoader = 3, kRoleBandpass = 4, kRoleRzcc = 5, kRoleNeuron = 6, kRoleGram = 7;
 constexpr int kThreads = kWarps * 32;
 constexpr int kGramFlush = 2;  // tiles of float32 Gram accumulation (inside the tensor cores: truncating adds) between two folds into float64
+constexpr int kTileM = kTile / 4;      // groups of four samples (= one pair of each sub-sequence) per tile
+constexpr int kShiftP = 7;     // ring coordinate of pair m is (m + kShiftP) mod ring_p: window chunks start 8-aligned
+constexpr int kUvPitch = 2 * kTileM + 4;   // floats per row of the U / V hand-over scratch (+ one pair of the previous tile)
 
 struct FusedGeom {
-    int ring_x;      // audio ring length in samples (multiple of 32)
-    int pitch_x;     // floats per ring row; pitch_x / 4 is odd (conflict-free LDS.128 across microphones)
-    int shift;       // ring coordinate of sample t is (t + shift) mod ring_x
-    int nblk;        // FIR tap blocks of 8 (multiple of 6: two halves walked in groups of three)
+    int ring_p;      // pairs per sub-sequence ring (multiple of 8)
+    int pitch_x;     // floats per ring; pitch_x / 4 is odd (LDS.128 of consecutive rings hit distinct bank groups)
+    int nblk;        // tap blocks of 8 per sub-filter (multiple of 3: walked in groups of three)
+    int tap_pitch;   // floats per tap array (A, B, A+B)
+    int rows_per_warp;   // (clip, microphone) rows per FIR warp
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
-    int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
+    int stagger;     // debug (MICLOC_FUSED_STAGGER): cycles by which group 1 of a CTA starts behind group 0
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
-    int stagger;     // cycles by which clip-pair group 1 of a CTA starts behind group 0 (see k_fused)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
-    int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_qa;   // byte offsets in dynamic smem
+    unsigned char role_map[16];   // GROUPS = 2: (group << 3 | role) of warp w (sub-partition w % 4), see k_fused
+    int off_x, off_q, off_uv, off_vm, off_cs, off_seg, off_clus, off_bits, off_stage;   // byte offsets in dynamic smem
     int smem_bytes;
 };
 
@@ -80,7 +98,11 @@ __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long lon
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(g2));
 }
 
-struct Chunk { unsigned long long p[8]; };   // 16 consecutive samples as 8 float pairs
+// Packed FFMA2 (fma.rn.f32x2): one instruction per tap and output pair.  With three operands from non-uniform
+// registers (accumulator pair, window pair, tap) an FFMA2 issues every ~2.6 cycles per sub-partition in this
+// loop, not every 2 as with a uniform-register multiplier (the form the FP32 peak is measured with); the scalar
+// FFMA form of the same loop was measured 2 % slower end to end (tools/sched_probe.py roles 9-11).
+struct Chunk { unsigned long long p[8]; };   // 8 consecutive pairs of one sub-sequence ring
 
 __device__ __forceinline__ void load_chunk(Chunk &c, const float *row, int coord) {
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(row + coord);
@@ -91,7 +113,7 @@ __device__ __forceinline__ void load_chunk(Chunk &c, const float *row, int coord
     }
 }
 
-// 8 taps x 16 outputs: acc[ip] += g[jj] * W[ip + 7 - jj], W = lo pairs 0..7 | hi pairs 0..6
+// 8 taps x 8 output pairs: acc[ip] += g[jj] * W[ip + 7 - jj], W = lo pairs 0..7 | hi pairs 0..6
 struct Taps8 { float4 a, b; };
 __device__ __forceinline__ void load_taps(Taps8 &t, const float *__restrict__ taps8) {
     t.a = *reinterpret_cast<const float4 *>(taps8);
@@ -155,7 +177,12 @@ struct RoleTimer {
 #endif
 
 struct FusedSmem {
-    float *taps, *xs, *qs, *qa, *vms, *is_s, *cs;
+    float *taps;            // [3: A, B, A+B][tap_pitch]
+    float *xs;              // [kSlots*M rows][3: R0, R1, R0+R1][pitch_x] sub-sequence rings
+    float *qs;              // [2 tiles][kSlots*M][kQPitch]: finished quadrature tiles
+    float *uv;              // [2: U, V][kSlots*M][kUvPitch]: partial results handed over inside a FIR warp
+    float *vms;             // [2 tiles][kVmRows][kVmPitch] membrane tiles, channel-major
+    float *cs;
     unsigned int *seg;      // [2 tiles][kTile/kSeg][3: neg mask, zero mask, carry][32 lanes]: band-pass -> RZCC hand-over
     int *clus;
     unsigned int *bits;     // [2 polarities][kRingWords][32 lanes]
@@ -167,102 +194,149 @@ struct FusedSmem {
 };
 constexpr int kSegsPerTile = kTile / kSeg;
 
-// ======= FIR warp (one per clip slot): audio tile k+1 -> ring, STHT FIR of tile k =======
-
+// ======= loader warp: audio tile k+1 (HBM) -> sub-sequence rings R0, R1, S = R0 + R1 of every microphone =======
+// lane = slot * 16 + group of four consecutive samples u = 4m - k0 + e, e < 4 (one pair of R0, one of R1)
 template <typename IN_T, int MM>
-__device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                         const IN_T *__restrict__ audio, long long clip, bool clip_ok, long long T64,
-                                         int slot, int half, int lane, int NT, int k_last) {
+__device__ __forceinline__ void loader_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                            const IN_T *__restrict__ audio, long long clip0, long long B, long long T64,
+                                            int lane, int NT, int k_last) {
     const int M = MM ? MM : p.M;
     const int T = (int)T64;
-    const int f_chunk = lane >> 3, f_mic = lane & 7;     // FIR lanes: lane = chunk * 8 + mic
-    const bool work = clip_ok && f_mic < M;
-    const float *row = sm.xs + (slot * M + f_mic) * g.pitch_x;
-    const IN_T *src = audio + (clip_ok ? clip : 0) * T64 * M;
-    float *rows_w = sm.xs + slot * M * g.pitch_x;
-    const int nb2 = g.nblk / 2;                          // tap blocks of this warp: [half * nb2, (half + 1) * nb2)
-    // this lane's sample of the tile being filled (tile 0 at k = -1): the warp fills samples [32*half, 32*half + 32)
-    int fill_t = lane + 32 * half;
-    const IN_T *fill_src = src + (fill_t < T ? fill_t * M : 0);
-    int fill_c = (fill_t + g.shift) % g.ring_x;
-    // ring coordinate of this lane's window of the warp's first tap block at tile 0, kept incrementally
-    int c0 = ((16 * f_chunk - p.tap_first - 14 + g.shift - 16 * half * nb2) % g.ring_x + g.ring_x) % g.ring_x;
+    const int slot = lane >> 4, gi = lane & 15;
+    const bool clip_ok = clip0 + slot < B;
+    const IN_T *src = audio + (clip_ok ? clip0 + slot : clip0) * T64 * M;
+    float *rows = sm.xs + slot * M * 3 * g.pitch_x;
+    int m = gi;                                      // pair index of the tile being filled (tile 0 at k = -1)
+    int coord = (gi + kShiftP) % g.ring_p;           // its ring coordinate, kept incrementally
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        // (a) audio tile k+1 -> mic-major ring: every lane moves one whole frame (all microphones of one
-        //     sample); the loads are issued here and stored after the FIR so that their latency is hidden
-        const int kf = k + 1;
-        const bool filling = kf < NT && clip_ok;
-        float v[kRows];
-        if (filling) {
-            const bool ok = fill_t < T;
+        if (k + 1 < NT && clip_ok) {
+            const int u0 = 4 * m - p.tap_first;
+            float v[4][kRows];
 #pragma unroll
-            for (int m = 0; m < kRows; ++m) v[m] = (ok && m < M) ? to_f32<IN_T>(fill_src[m]) : 0.f;
-        }
-        // (b) this warp's half of the taps of the STHT quadrature FIR: half 0 starts the running sums of tile k,
-        //     half 1 picks up those of tile k - 1 and finishes them
-        const int kk = k - half;
-        if (kk >= 0 && kk < NT) {
-            if (work) {
-                unsigned long long acc[8];
-                float *part = sm.qa + (((kk & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
-                if (half == 0) {
+            for (int e = 0; e < 4; ++e) {
+                const int u = u0 + e;
+                const bool ok = u >= 0 && u < T;
+                const IN_T *fr = src + (ok ? (long long)u * M : 0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = 0ull;
-                } else {
+                for (int mm = 0; mm < kRows; ++mm) v[e][mm] = (ok && mm < M) ? to_f32<IN_T>(fr[mm]) : 0.f;
+            }
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        const float4 o = reinterpret_cast<const float4 *>(part)[v4];
-                        acc[2 * v4] = pack2(o.x, o.y);
-                        acc[2 * v4 + 1] = pack2(o.z, o.w);
-                    }
+            for (int mm = 0; mm < kRows; ++mm)
+                if (mm < M) {
+                    float *r = rows + mm * 3 * g.pitch_x + 2 * coord;
+                    *reinterpret_cast<float2 *>(r) = make_float2(v[0][mm], v[1][mm]);
+                    *reinterpret_cast<float2 *>(r + g.pitch_x) = make_float2(v[2][mm], v[3][mm]);
+                    *reinterpret_cast<float2 *>(r + 2 * g.pitch_x) = make_float2(v[0][mm] + v[2][mm], v[1][mm] + v[3][mm]);
                 }
+            m += kTileM;
+            coord += kTileM; if (coord >= g.ring_p) coord -= g.ring_p;
+        }
+        ROLE_BARRIER();
+    }
+    ROLE_TIMER_FLUSH(kRoleLoader);
+}
+
+// ======= FIR warps: STHT quadrature FIR of tile k as the three half-length sub-filters U, V, W =======
+// lane = chunk * 15 + local row * 3 + sub-filter (lanes 30, 31 idle); a lane owns the 8 output pairs
+// m = 16k + 8 chunk + i of its (row, sub-filter)
+template <int MM>
+__device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                         long long clip0, long long B, int warp_f, int lane, int NT, int k_last) {
+    const int M = MM ? MM : p.M;
+    const int f_chunk = lane >= 15 ? 1 : 0;
+    const int q = lane - 15 * f_chunk, rl = q / 3, f = q - 3 * rl;
+    const int rowi = warp_f * g.rows_per_warp + rl;             // (slot, microphone) row
+    const bool work = lane < 30 && rl < g.rows_per_warp && rowi < kSlots * M && clip0 + rowi / M < B;
+    const int ringf = 2 * g.ring_p;
+    const float *row = sm.xs + ((work ? rowi : 0) * 3 + f) * g.pitch_x;
+    const float *tp0 = sm.taps + f * g.tap_pitch;
+    float *uv_u = sm.uv + (work ? rowi : 0) * kUvPitch + 4;                         // U pairs of this row, pair j at 2j
+    float *uv_v = uv_u + kSlots * M * kUvPitch;                                     // V pairs (pair -1 = last of the previous tile)
+    // ring coordinate (floats) of this lane's window of tap block 0 at tile 0, kept incrementally
+    int c0 = 2 * ((8 * f_chunk) % g.ring_p);
+    ROLE_TIMER_DECL;
+
+    for (int k = -1; k <= k_last; ++k) {
+        if (k >= 0 && k < NT) {
+            unsigned long long acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0ull;
+            if (work) {
                 Chunk A, Bq, Cq;
-                { int ch = c0 + 16; if (ch >= g.ring_x) ch -= g.ring_x; load_chunk(Bq, row, ch); }
+                { int ch = c0 + 16; if (ch >= ringf) ch -= ringf; load_chunk(Bq, row, ch); }
                 load_chunk(A, row, c0);
-                int cn = c0 - 16; if (cn < 0) cn += g.ring_x;
+                int cn = c0 - 16; if (cn < 0) cn += ringf;
                 // window chunks and taps are fetched one block ahead of their use
-                const float *tp = sm.taps + 8 * half * nb2;
+                const float *tp = tp0;
                 Taps8 t0, t1;
                 load_taps(t0, tp);
 #pragma unroll 1
-                for (int jb = 0; jb < (g.fir_blocks ? g.fir_blocks : nb2); jb += 3) {
-                    load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                for (int jb = 0; jb < (g.fir_blocks ? g.fir_blocks : g.nblk); jb += 3) {
+                    load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += ringf;
                     load_taps(t1, tp + 8);
                     fir_block(acc, A, Bq, t0);
-                    load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                    load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += ringf;
                     load_taps(t0, tp + 16);
                     fir_block(acc, Cq, A, t1);
-                    load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
+                    load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += ringf;
                     load_taps(t1, tp + 24);             // first block of the next round (zero padding behind the last)
                     fir_block(acc, Bq, Cq, t0);
                     t0 = t1;
                     tp += 24;
                 }
-                float *dst = half == 0 ? part : sm.qs + (((kk & 1) * kSlots + slot) * M + f_mic) * kQPitch + 16 * f_chunk;
+                // U and V go through shared memory to the lanes that recombine them
+                if (f < 2) {
+                    float *dst = (f == 0 ? uv_u : uv_v) + 16 * f_chunk;
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) {
-                    float4 o;
-                    unpack2(acc[2 * v4], o.x, o.y);
-                    unpack2(acc[2 * v4 + 1], o.z, o.w);
-                    reinterpret_cast<float4 *>(dst)[v4] = o;
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        float4 o;
+                        unpack2(acc[2 * v4], o.x, o.y);
+                        unpack2(acc[2 * v4 + 1], o.z, o.w);
+                        reinterpret_cast<float4 *>(dst)[v4] = o;
+                    }
                 }
             }
-            c0 += kTile; if (c0 >= g.ring_x) c0 -= g.ring_x;
-        }
-        if (filling) {
+            __syncwarp();
+            if (work) {
+                float *qrow = sm.qs + ((k & 1) * kSlots * M + rowi) * kQPitch + 32 * f_chunk;
+                if (f == 0) {
+                    // Y[2m] = U[m] + V[m-1]
+                    const float *vp = uv_v + 16 * f_chunk - 2;
 #pragma unroll
-            for (int m = 0; m < kRows; ++m)
-                if (m < M) rows_w[m * g.pitch_x + fill_c] = v[m];
-            // next tile: time, source frame and ring coordinate of this lane's sample
-            fill_t += kTile;
-            fill_src += (fill_t < T ? kTile * M : 0);
-            fill_c += kTile; if (fill_c >= g.ring_x) fill_c -= g.ring_x;
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 vv = *reinterpret_cast<const float2 *>(vp + 2 * i);
+                        float ux, uy;
+                        unpack2(acc[i], ux, uy);
+                        *reinterpret_cast<float2 *>(qrow + 4 * i) = make_float2(ux + vv.x, uy + vv.y);
+                    }
+                } else if (f == 2) {
+                    // Y[2m+1] = W[m] - U[m] - V[m]
+                    const float *up = uv_u + 16 * f_chunk, *vp = uv_v + 16 * f_chunk;
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const float4 uu = reinterpret_cast<const float4 *>(up)[v4];
+                        const float4 vv = reinterpret_cast<const float4 *>(vp)[v4];
+                        float wx, wy;
+                        unpack2(acc[2 * v4], wx, wy);
+                        *reinterpret_cast<float2 *>(qrow + 8 * v4 + 2) = make_float2((wx - uu.x) - vv.x, (wy - uu.y) - vv.y);
+                        unpack2(acc[2 * v4 + 1], wx, wy);
+                        *reinterpret_cast<float2 *>(qrow + 8 * v4 + 6) = make_float2((wx - uu.z) - vv.z, (wy - uu.w) - vv.w);
+                    }
+                }
+            }
+            __syncwarp();
+            if (work && f == 1 && f_chunk == 1) {      // V[16k + 15] is the next tile's V[m-1]
+                float lx, ly;
+                unpack2(acc[7], lx, ly);
+                *reinterpret_cast<float2 *>(uv_v - 2) = make_float2(lx, ly);
+            }
+            c0 += 2 * kTileM; if (c0 >= ringf) c0 -= ringf;
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(2 * slot + half);
+    ROLE_TIMER_FLUSH(warp_f);
 }
 
 // ============ band-pass warp: SOS cascade + running sum + sign / zero masks, lane = slot*16 + channel ============
@@ -298,62 +372,41 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
     }
     BiquadState bq; biquad_reset(bq);
     float csum = 0.f;
-    // ring coordinate of the in-phase sample x[ts - K/2] of the next segment (warp-uniform, kept incrementally)
-    int cin_u = ((g.shift - p.half) % g.ring_x + g.ring_x) % g.ring_x;
+    float xpre[8];                      // in-phase samples fetched ahead for the next segment
+    bool pre_ok = false;
+    int pre_src = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xpre[i] = 0.f;
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kc = k - 2;
+        const int kc = k - 1;
         const int t0 = kc * kTile;
         if (kc >= 0 && t0 < T) {
-            const bool from_is = kc < g.tiles_is;
-            if (from_is) {
-                // in-phase input of the first K/2 samples is the clip's tail (np.roll, snn_beamformer.py:325)
-                if (slot_ok) {
-                    float *dsti = sm.is_s + c_slot * kTile * M;
-                    for (int e = c_ch; e < kTile * M; e += 16) {
-                        const int t = t0 + e / M;
-                        float v = 0.f;
-                        if (t < T) {
-                            int src = (t - p.half) % T;
-                            if (src < 0) src += T;
-                            v = to_f32<IN_T>(clip_audio[(long long)src * M + (e % M)]);
-                        }
-                        dsti[e] = v;
-                    }
-                }
-                __syncwarp();
-            }
 #pragma unroll 1
             for (int sg = 0; sg < kSegsPerTile; ++sg) {
                 const int ts = t0 + sg * kSeg;            // first sample of this segment
                 float *cs = sm.cs + ((kc & 1) * kSegsPerTile + sg) * kSeg * 32 + lane;
                 unsigned int *sgm = sm.seg + ((kc & 1) * kSegsPerTile + sg) * 3 * 32 + lane;
-                const int cin = cin_u;                    // ring coordinate of x[ts - K/2]
-                cin_u += kSeg; if (cin_u >= g.ring_x) cin_u -= g.ring_x;
                 if (ts >= T || !c_valid) continue;
-                const float *xp;
-                int stride = 1, wrap_at = kSeg;
-                if (!c_inphase) {
-                    xp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_ch - M)) * kQPitch + sg * kSeg;
-                } else if (from_is) {
-                    xp = sm.is_s + c_slot * kTile * M + sg * kSeg * M + c_ch;
-                    stride = M;
-                } else {
-                    xp = sm.xs + (c_slot * M + c_ch) * g.pitch_x + cin;
-                    wrap_at = g.ring_x - cin;
-                }
-                // (warp-uniform) no lane wraps around the audio ring inside this segment
-                const bool fast = !from_is && ts + kSeg <= T && cin + kSeg <= g.ring_x;
+                // in-phase input: x[(t - K/2) mod T] (np.roll, snn_beamformer.py:325), re-read from global memory
+                // (the loader fetched these frames a few tiles ago: L2 hits); quadrature input: the FIR warps' tile
+                int src0 = (ts - p.half) % T;             // (warp-uniform) source sample of the segment's first sample
+                if (src0 < 0) src0 += T;
+                const IN_T *gp = clip_audio + (long long)src0 * M + (c_inphase ? c_ch : 0);
+                const float *qp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_inphase ? 0 : c_ch - M)) * kQPitch + sg * kSeg;
+                // (warp-uniform) a whole segment inside the clip whose in-phase source does not wrap
+                const bool fast = ts + kSeg <= T && src0 + kSeg <= T;
                 const float carry = csum;
                 unsigned int neg = 0u, zero = 0u;
-                // sample by sample with explicit sign / zero masks (ragged segments, ring wrap, clip-tail input, exact zeros)
+                // sample by sample with explicit sign / zero masks (ragged segments, wrapping in-phase source, exact zeros)
                 auto slow_segment = [&](int nvalid) {
-                    const float *xq = xp;
+                    int src = src0;
 #pragma unroll 1
                     for (int i = 0; i < nvalid; ++i) {
-                        if (i == wrap_at) xq -= g.ring_x;
-                        const float z = biquad2_step(sos, bq, xq[i * stride]);
+                        const float x = c_inphase ? to_f32<IN_T>(clip_audio[(long long)src * M + c_ch]) : qp[i];
+                        if (++src >= T) src = 0;
+                        const float z = biquad2_step(sos, bq, x);
                         csum += z;
                         cs[i * 32] = csum;
                         neg |= (__float_as_uint(z) >> 31) << (31 - i);
@@ -364,8 +417,9 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                     const BiquadState bq0 = bq;
                     float zmin = 1.f;                   // smallest |z| of the segment: exact zeros are rare (silence)
                     float xn[8];
+                    const bool pre = pre_ok && pre_src == src0;     // (warp-uniform) this segment's first in-phase group is here already
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) xn[i] = xp[i];
+                    for (int i = 0; i < 8; ++i) xn[i] = c_inphase ? (pre ? xpre[i] : to_f32<IN_T>(gp[i * M])) : qp[i];
 #pragma unroll 1
                     for (int o = 0; o < kSeg / 8; ++o) {
                         float xc[8];
@@ -373,7 +427,16 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                         for (int i = 0; i < 8; ++i) xc[i] = xn[i];
                         if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) xn[i] = xp[8 * (o + 1) + i];
+                            for (int i = 0; i < 8; ++i)
+                                xn[i] = c_inphase ? to_f32<IN_T>(gp[(8 * (o + 1) + i) * M]) : qp[8 * (o + 1) + i];
+                        } else {
+                            // the next segment's first in-phase group (global memory: it does not wait for the tile barrier)
+                            pre_src = src0 + kSeg;
+                            pre_ok = pre_src + 8 <= T;
+                            if (pre_ok && c_inphase) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) xpre[i] = to_f32<IN_T>(gp[(kSeg + i) * M]);
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -389,6 +452,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                         slow_segment(kSeg);
                     }
                 } else {
+                    pre_ok = false;
                     slow_segment(T - ts < kSeg ? T - ts : kSeg);
                 }
                 sgm[0] = neg; sgm[32] = zero; sgm[64] = __float_as_uint(carry);
@@ -396,7 +460,7 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(4);
+    ROLE_TIMER_FLUSH(kRoleBandpass);
 }
 
 // ============ RZCC warp: masks of tile k-2 -> candidates -> clusters -> spike bits, lane = slot*16 + channel ============
@@ -418,7 +482,7 @@ __device__ __forceinline__ void rzcc_role(const FusedSmem &sm, const ChainParams
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kr = k - 3;
+        const int kr = k - 2;
         const int t0 = kr * kTile;
         if (kr >= 0 && t0 < T && c_valid) {
 #pragma unroll 1
@@ -440,7 +504,7 @@ __device__ __forceinline__ void rzcc_role(const FusedSmem &sm, const ChainParams
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(5);
+    ROLE_TIMER_FLUSH(kRoleRzcc);
     if (c_valid && rz.overflow && flags) atomicOr(flags + clip0 + c_slot, 1);
 }
 
@@ -517,7 +581,7 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(6);
+    ROLE_TIMER_FLUSH(kRoleNeuron);
 }
 
 // ==== Gram warp: C += V V^T of the membrane tile k - dtile - 1 on the tensor cores, then that tile's int8 spike
@@ -607,7 +671,7 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
         }
         ROLE_BARRIER();
     }
-    ROLE_TIMER_FLUSH(7);
+    ROLE_TIMER_FLUSH(kRoleGram);
     // the Gram matrices of the two clips -> shared memory for the clip epilogue (the audio rings are dead now):
     // accumulator fragment (m16n8): c0, c1 = row lane/4, columns 2 (lane%4) + {0, 1}; c2, c3 = row lane/4 + 8
 #pragma unroll
@@ -621,16 +685,40 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
             }
 }
 
-// GROUPS = 1: a CTA is one clip-pair group of eight warps, two CTAs per SM, FIR roles placed per SM
-//             sub-partition at run time (hardware warp slots of a second CTA are not known in advance).
 // GROUPS = 2: ONE CTA of sixteen warps per SM holding two independent clip-pair groups (own named barrier,
-//             own shared-memory region, own clip pairs).  The warp slots are then known: warps 0..7 are the
-//             FIR warps (two per sub-partition, one of each group), warps 8..15 the serial roles.  The
-//             scheduler of a sub-partition prefers the eligible warp with the highest warp id, so the
-//             latency-bound serial roles (a chain of dependent instructions per sample) always win their few
-//             issue slots and run at their dependency-chain pace, while the FIR warps fill every remaining
-//             FMA-pipe cycle; with the FIR warps in front the serial roles starve behind a stream of
-//             independent FFMA2s and FIR and serial phases alternate instead of overlapping.
+//             own shared-memory region, own clip pairs).  Hardware warp slot w belongs to sub-partition
+//             w % 4, whose single issue port all its warps share.  Streams and chains are kept apart:
+//                sub-partition 0 / 1: the three FIR warps and the loader of group 0 / 1
+//                sub-partition 2 / 3: band-pass, RZCC, neuron and Gram of group 0 / 1
+//             Three FIR warps saturate their sub-partition's issue port with independent FFMA2s (~2000 slots
+//             each per tile); the serial roles are chains of dependent instructions per sample, and a chain
+//             that shares a sub-partition with an FFMA2 stream runs three times slower per instruction
+//             (tools/sched_probe.py), while four chains side by side fill one another's latency gaps
+//             (~5500 slots per tile).
+// GROUPS = 1: a CTA is one group of eight warps (two CTAs per SM), role = warp; the fallback when two
+//             groups do not fit the shared memory of one CTA (long STHT kernels).
+static const unsigned char kRoleMaps[4][16] = {
+    // layout 0 (mixed): (group << 3 | role) of warp 4 i + sub-partition
+    {0 << 3 | 0, 0 << 3 | 1, 0 << 3 | 2, 1 << 3 | 2,
+     1 << 3 | 0, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
+     0 << 3 | kRoleGram, 1 << 3 | kRoleGram, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
+     1 << 3 | kRoleLoader, 0 << 3 | kRoleLoader, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleRzcc},
+    // layout 1 (streams and chains apart)
+    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
+     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleRzcc,
+     0 << 3 | 2, 1 << 3 | 2, 0 << 3 | kRoleNeuron, 1 << 3 | kRoleNeuron,
+     0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader, 0 << 3 | kRoleGram, 1 << 3 | kRoleGram},
+    // layout 2 (balanced for the tensor-core Gram: FIR 0, 1 + RZCC + Gram | FIR 2 + band-pass + neuron + loader)
+    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
+     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
+     1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
+     1 << 3 | kRoleGram, 0 << 3 | kRoleGram, 0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader},
+    // layout 3: FIR 0, 1 + RZCC + loader | FIR 2 + band-pass + neuron + Gram
+    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
+     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
+     1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
+     1 << 3 | kRoleLoader, 0 << 3 | kRoleLoader, 0 << 3 | kRoleGram, 1 << 3 | kRoleGram}};
+
 template <typename IN_T, int MM, int GROUPS>
 __global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 2 : 1)
 k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
@@ -650,67 +738,19 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
 #endif
 
     // ---- which group and role this warp serves ----
-    int group = 0, role;
-    if (GROUPS == 1) {
-        // A hardware warp slot w belongs to SM sub-partition w % 4, and the FMA pipe of a sub-partition is
-        // what the FIR warps compete for: the four FIR roles go to the warps of this CTA whose sub-partition
-        // holds the fewest FIR warps of the CTAs already resident on this SM (counters per SM in
-        // sm_slots[4*smid + smsp], reset per launch); the other four roles follow in warp order, rotated by
-        // two for every second CTA of an SM so that the band-pass / Gram warps (the ones with FMA work)
-        // spread out.
-        if (lane == 0) {
-            unsigned int wid;
-            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-            s_smsp[warp] = (int)(wid & 3u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            unsigned int *fir_cnt = sm_slots + 4 * (smid & 255u);
-            const unsigned int arrival = atomicAdd(sm_slots + kSlotPair + 1 + (smid & 255u) % 254u, 1u);
-            bool taken[kWarps];
-            for (int w = 0; w < kWarps; ++w) { taken[w] = false; s_role[w] = -1; }
-            for (int r = 0; r < kFirWarps; ++r) {
-                int best = -1; unsigned int bestc = 0xffffffffu;
-                for (int w = 0; w < kWarps; ++w) {
-                    if (taken[w]) continue;
-                    const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
-#ifdef MICLOC_FIR_HIGH_WARPS
-                    if (c <= bestc) { bestc = c; best = w; }     // experiment: ties go to the highest warp slot
-#else
-                    if (c < bestc) { bestc = c; best = w; }
-#endif
-                }
-                taken[best] = true;
-                s_role[best] = r;
-                atomicAdd(fir_cnt + s_smsp[best], 1u);
-            }
-            int next = (int)(2u * (arrival & 1u));
-            for (int w = 0; w < kWarps; ++w)
-                if (!taken[w]) { s_role[w] = kFirWarps + (next & 3); ++next; }
-        }
-        __syncthreads();
-        role = s_role[warp];
-    } else {
-        // warps 0..3: FIR of group 0, 4..7: FIR of group 1 (one per sub-partition each); warps 8..11 / 12..15:
-        // band-pass, RZCC, neuron, Gram of group 0 / 1, rotated by two between the groups so that the two
-        // roles with FMA work (band-pass, Gram) of a sub-partition are of different kinds
-        if (warp < 2 * kFirWarps) {
-            group = warp >> 2;
-            role = warp & 3;
-        } else {
-            group = (warp - 2 * kFirWarps) >> 2;
-            role = kFirWarps + (group == 0 ? (warp & 3) : 3 - (warp & 3));
-        }
-        if (lane == 0) {
-            unsigned int wid;
-            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-            s_smsp[warp] = (int)(wid & 3u);
-            s_role[warp] = role;
-        }
+    int group = 0, role = warp;
+    if (GROUPS == 2) {
+        const int gr = g.role_map[warp];
+        group = gr >> 3;
+        role = gr & 7;
     }
-    // 0..3: FIR (+ fill) of clip slot role >> 1, tap half role & 1; 4: band-pass; 5: RZCC; 6: neuron; 7: Gram
+    if (lane == 0) {
+        unsigned int wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        s_smsp[warp] = (int)(wid & 3u);
+        s_role[warp] = role | (group << 3);
+    }
+    // roles 0..2: FIR warps; 3: loader; 4: band-pass; 5: RZCC; 6: neuron; 7: Gram
     const int tid = role * 32 + lane;       // thread index inside the group
     const int bar_id = 1 + group;
     auto group_sync = [&]() { tile_barrier(bar_id); };
@@ -718,11 +758,10 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     unsigned char *smem_raw = smem_all + (size_t)group * g.smem_bytes;
     FusedSmem sm;
     sm.taps = reinterpret_cast<float *>(smem_raw);
-    sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);       // [kSlots*M][pitch_x]
-    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);       // [2 tiles][kSlots*M][kQPitch]: finished quadrature tiles
-    sm.qa = reinterpret_cast<float *>(smem_raw + g.off_qa);      // [2 tiles][kSlots*M][kQPitch]: running sums after the first tap half
-    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);     // [2 tiles][kVmRows][kVmPitch], channel-major
-    sm.is_s = reinterpret_cast<float *>(smem_raw + g.off_is);    // [kSlots][kTile][M]
+    sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);
+    sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);
+    sm.uv = reinterpret_cast<float *>(smem_raw + g.off_uv);
+    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);
     sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [2][kSegsPerTile][kSeg][32] running sums
     sm.seg = reinterpret_cast<unsigned int *>(smem_raw + g.off_seg);     // [2][kSegsPerTile][3][32]
     sm.clus = reinterpret_cast<int *>(smem_raw + g.off_clus);    // RZCC cluster buffers, interleaved over 32 lanes
@@ -735,17 +774,20 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [kThreads], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + kThreads * sizeof(double));
 
-    for (int i = tid; i < 8 * g.nblk + 8; i += kThreads) sm.taps[i] = i < p.n_taps ? taps[i] : 0.f;
+    // tap arrays of the three sub-filters: A_n = c_2n, B_n = c_2n+1, A + B (zero padded)
+    for (int i = tid; i < g.tap_pitch; i += kThreads) {
+        const float ta = 2 * i < p.n_taps ? taps[2 * i] : 0.f;
+        const float tb = 2 * i + 1 < p.n_taps ? taps[2 * i + 1] : 0.f;
+        sm.taps[i] = ta;
+        sm.taps[g.tap_pitch + i] = tb;
+        sm.taps[2 * g.tap_pitch + i] = ta + tb;
+    }
 
     const int NT = (int)((T + kTile - 1) / kTile);
     const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 tiles behind
     const long long npairs = (B + kSlots - 1) / kSlots;
 
-    // The two FIR warps of a sub-partition (one per group) share its FMA pipe.  Started together they stay
-    // in phase for the whole launch (equal work per tile): both are inside their tap loop at the same time,
-    // and both are outside it (tile hand-over, audio fill, barrier) at the same time, when the pipe idles.
-    // Group 1 therefore starts a fraction of a tile period late; the offset is neutrally stable, and one
-    // group's hand-over then hides behind the other's tap loop.
+    // experiment knob (MICLOC_FUSED_STAGGER): group 1 starts a number of cycles behind group 0 (no measured effect)
     if (GROUPS == 2 && group == 1 && g.stagger > 0) {
         long long t0, t1;
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
@@ -763,8 +805,9 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         const long long clip0 = pair * kSlots;
         {   // zero the audio rings: samples before the clip start are zeros (lfilter's zero state)
             float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
-            const int n4 = kSlots * M * g.pitch_x / 4;
+            const int n4 = kSlots * M * 3 * g.pitch_x / 4;
             for (int i = tid; i < n4; i += kThreads) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < 2 * kSlots * M * kUvPitch; i += kThreads) sm.uv[i] = 0.f;    // V[-1] = 0
             // no spikes before the clip start; membrane columns of unused lanes stay zero
             for (int i = tid; i < 2 * kRingWords * 32; i += kThreads) sm.bits[i] = 0u;
             for (int i = tid; i < 2 * kVmRows * kVmPitch; i += kThreads) sm.vms[i] = 0.f;
@@ -774,11 +817,11 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         if ((g.skip >> role) & 1) {
             for (int k = -1; k <= k_last; ++k) tile_barrier(bar_id);
         } else if (role < kFirWarps)
-            fir_role<IN_T, MM>(sm, p, g, audio, clip0 + (role >> 1), clip0 + (role >> 1) < B, T, role >> 1, role & 1, lane,
-                               NT, k_last);
-        else if (role == 4) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
-        else if (role == 5) rzcc_role(sm, p, flags, clip0, B, T, M, lane, k_last);
-        else if (role == 6) neuron_role(sm, p, g, clip0, B, T, M, lane, k_last);
+            fir_role<MM>(sm, p, g, clip0, B, role, lane, NT, k_last);
+        else if (role == kRoleLoader) loader_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, NT, k_last);
+        else if (role == kRoleBandpass) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
+        else if (role == kRoleRzcc) rzcc_role(sm, p, flags, clip0, B, T, M, lane, k_last);
+        else if (role == kRoleNeuron) neuron_role(sm, p, g, clip0, B, T, M, lane, k_last);
         else gram_role(sm, g, spikes, clip0, B, T, M, lane, k_last);
         group_sync();
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
@@ -839,7 +882,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         unsigned long long *d = reinterpret_cast<unsigned long long *>(sm_slots + kSlotCta) + 16 * (GROUPS * blockIdx.x + group);
         unsigned long long map = 0;
         for (int w = 0; w < kWarps * GROUPS; ++w)
-            if (GROUPS == 1 || ((w < 2 * kFirWarps ? w >> 2 : (w - 2 * kFirWarps) >> 2) == group)) {
+            if ((s_role[w] >> 3) == group) {
                 const int r = s_role[w] & 7;
                 map |= (unsigned long long)(r | ((s_smsp[w] & 3) << 3)) << (8 * r);
             }
@@ -879,53 +922,56 @@ static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float 
 int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
                  unsigned int *sm_slots, int sm_count, cudaStream_t st) {
-    // A/B switch: the fast-FIR variant (three half-length sub-filters, micloc_fused_ffa.cu) executes a quarter
-    // fewer multiply-adds but balances worse over the four sub-partitions; measured 4 % slower
-    if (const char *e = getenv("MICLOC_FUSED_FIR"))
-        if (e[0] == 'f' && ffa::fused_supported(p))
-            return ffa::launch_fused(p, d_taps, d_Wd, audio, dtype, B, T, spikes, power, doa, flags, sm_slots, sm_count, st);
-    if (!fused_supported(p))
+    if (!ffa::fused_supported(p))
         return set_error(MICLOC_ERR_UNSUPPORTED,
                          "fused kernel covers Hilbert-type STHT kernels (every other tap zero), a 2-section band-pass "
                          "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
-    g.stagger = 0;
     if (const char *e = getenv("MICLOC_FUSED_STAGGER")) g.stagger = (int)strtol(e, nullptr, 0);
-    // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
-    g.nblk = (p.n_taps / 8 + 5) / 6 * 6;
-    const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
-    g.ring_x = ((lookback + 3 * kTile) + 31) / 32 * 32;             // history + the two tiles in the FIR + tile being filled
-    g.pitch_x = g.ring_x + 4;
-    g.shift = ((p.tap_first + 14) % 16 + 16) % 16;
+    {
+        int layout = 2;
+        if (const char *e = getenv("MICLOC_FUSED_LAYOUT")) layout = atoi(e);     // role placement experiments
+        for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[layout >= 0 && layout < 4 ? layout : 2][w];
+    }
+    // sub-filters of n_taps / 2 taps in blocks of 8, walked in groups of three (zero taps appended)
+    const int sub_taps = (p.n_taps + 1) / 2;
+    g.nblk = ((sub_taps + 7) / 8 + 2) / 3 * 3;
+    g.tap_pitch = 8 * g.nblk + 8;                        // + the block the tap prefetch runs ahead
+    // a ring holds the oldest pair a tile's windows load (8 nblk - 1 back), the tile in the FIR and the tile being filled
+    g.ring_p = (8 * g.nblk + 2 * kTileM + 7) / 8 * 8;
+    g.pitch_x = 2 * g.ring_p + 4;
+    if ((g.pitch_x / 4) % 2 == 0) g.pitch_x += 4;
+    g.rows_per_warp = (kSlots * p.M + kFirWarps - 1) / kFirWarps;
     // a spike at p is final once the RZCC warp passed p + rzcc_lag(w) - 1; the neuron warp works on
-    // tile k - dtile while the RZCC warp has completed tile k - 4
-    g.dtile = 4 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
-    g.tiles_is = (p.half + kTile - 1) / kTile;
-    int off = ((8 * g.nblk + 8) * (int)sizeof(float) + 15) & ~15;
-    g.off_x = off; off += kSlots * p.M * g.pitch_x * (int)sizeof(float);
-    g.off_q = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
-    g.off_qa = off; off += 2 * kSlots * p.M * kQPitch * (int)sizeof(float);
+    // tile k - dtile while the RZCC warp has completed tile k - 3
+    g.dtile = 3 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
+    const int rows = kSlots * p.M;
+    int off = (3 * g.tap_pitch * (int)sizeof(float) + 15) & ~15;
+    g.off_x = off; off += rows * 3 * g.pitch_x * (int)sizeof(float);
+    g.off_q = off; off += 2 * rows * kQPitch * (int)sizeof(float);
+    g.off_uv = off; off += 2 * rows * kUvPitch * (int)sizeof(float);
     g.off_vm = off; off += 2 * kVmRows * kVmPitch * (int)sizeof(float);
-    g.off_is = off; off += kSlots * kTile * p.M * (int)sizeof(float);
     g.off_cs = off; off += 2 * kSegsPerTile * kSeg * 32 * (int)sizeof(float);
     g.off_seg = off; off += 2 * kSegsPerTile * 3 * 32 * (int)sizeof(int);
     g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.smem_bytes = (off + 15) & ~15;
-    // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
-    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 3)
-    if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
+    if (3 * g.rows_per_warp * 2 > 32)
+        return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel: %d microphones do not fit the FIR lane map", p.M);
+    // the spike-bit ring must hold the neuron warp's oldest read and the RZCC warp's newest write
+    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 2)
+    if (kTile * (g.dtile - 1) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
-    if (kSlots * 256 * (int)sizeof(double) > kSlots * p.M * g.pitch_x * (int)sizeof(float) ||
-        kThreads * 12 > 2 * kSlots * p.M * kQPitch * (int)sizeof(float))
+    if (kSlots * 256 * (int)sizeof(double) > rows * 3 * g.pitch_x * (int)sizeof(float) ||
+        kThreads * 12 > 2 * rows * kQPitch * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);
-    if (T + 16 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
+    if (T + 16 * kTile >= (1ll << 29)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
     // one CTA of two clip-pair groups per SM when both fit its shared memory (the usual case), else the
     // single-group CTA twice per SM; MICLOC_FUSED_GROUPS=1 forces the latter (A/B measurements)
     int groups = 2 * g.smem_bytes <= 227 * 1024 ? 2 : 1;
@@ -944,4 +990,5 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
 #undef MICLOC_FUSED_CASE
 }
 
+}  // namespace ffa
 }  // namespace micloc

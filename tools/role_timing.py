@@ -32,7 +32,7 @@ for rep in range(3):
     ms = ev0.elapsed_time(ev1)
     lib.micloc_snn_debug_counters(eng._h, out)
     v = list(out)
-    names = ["fir0", "fir1", "fir2", "loader", "bandpass", "rzcc", "neuron", "gram"]
+    names = os.environ.get("ROLE_NAMES", "fir0a,fir0b,fir1a,fir1b,bandpass,rzcc,neuron,gram").split(",")
     iters = (Bn.T_CLIP // 64) + 8
     print(f"rep {rep}: {ms:.3f} ms, {B / ms:.1f} clips/ms; " + ", ".join(
         f"{n}: {v[i] / max(v[8 + i], 1) / iters:.0f}" for i, n in enumerate(names)) + " busy cyc/tile")
@@ -53,7 +53,7 @@ for i in range(n):
     for w in range(8):
         byte = (int(raw[i, 3]) >> (8 * w)) & 0xff
         role, smsp = byte & 7, (byte >> 3) & 3
-        if role < 3:
+        if role < int(os.environ.get("FIR_ROLES", "4")):
             fir[(smid[i], smsp)] = fir.get((smid[i], smsp), 0) + 1
 print("FIR warps per (SM, sub-partition) histogram:", np.bincount(list(fir.values())), "of", 4 * len(set(smid)), "sub-partitions")
 iters = Bn.T_CLIP // 64 + 8
