@@ -362,7 +362,9 @@ def run_gpu(args):
     tfile = os.path.join(ROOT, "profiles", "fused_traffic.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+            tj = json.load(open(tfile))        # dram__bytes_read + write of one `ncu --set full` capture, per clip
+            if args.dtype == tj.get("input_dtype", "f32"):
+                traffic = float(tj["dram_bytes_per_clip"]) * Bb          # bytes per launch of Bb clips
         except Exception:
             pass
     roofline = {

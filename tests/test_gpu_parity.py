@@ -119,12 +119,11 @@ def test_batch_fused_vs_staged_vs_oracle(name, T, int16):
     st = eng.run(xd, want_spikes=True, fused=False)
     fu = eng.run(xd, want_spikes=True, fused=True)
     torch.cuda.synchronize()
-    # same STHT / band-pass / RZCC arithmetic in both device paths; the Gram sums differ (tensor cores vs FP64)
-    assert H.spike_agreement(fu["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= SPIKE_AGREE
+    # the two device paths run the same STHT / band-pass / RZCC arithmetic in the same order: identical spikes;
+    # the Gram sums differ (tensor cores with a TF32 x3 split vs FP64)
+    assert torch.equal(st["spikes"], fu["spikes"])
     assert (st["doa"] == fu["doa"]).float().mean().item() >= DOA_AGREE
-    same_spk = (st["spikes"] == fu["spikes"]).flatten(1).all(dim=1).cpu().numpy()
-    if same_spk.any():
-        assert H.rel_err(fu["power"].cpu().numpy()[same_spk], st["power"].cpu().numpy()[same_spk]) < 1e-5
+    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < 1e-5
     cfg = H.oracle_cfg(g)
     fs = float(g["fs"]); tau = float(g["tau"])
     cfg.nir = O.neuron_kernel(np.arange(T) / fs, tau, tau)
@@ -183,8 +182,7 @@ def test_full_size_config4_multi_source_360_grid():
     eng = engine_for(g, T)
     out = eng.run(to_dev(x), want_spikes=True, fused=True)
     st = eng.run(to_dev(x), want_spikes=True, fused=False)
-    assert H.spike_agreement(out["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= SPIKE_AGREE
-    assert torch.equal(out["doa"], st["doa"])
+    assert torch.equal(out["spikes"], st["spikes"]) and torch.equal(out["doa"], st["doa"])
     cfg = H.oracle_cfg(g)
     cfg.nir = O.neuron_kernel(t, float(g["tau"]), float(g["tau"]))
     ref = O.snn_run_batch(cfg, x, nthreads=3, want_spikes=True)
@@ -235,7 +233,7 @@ def test_ragged_and_tiny_clips():
         fu = eng.run(to_dev(x), want_spikes=True, fused=True)
         st = eng.run(to_dev(x), want_spikes=True, fused=False)
         torch.cuda.synchronize()
-        assert H.spike_agreement(fu["spikes"].cpu().numpy(), st["spikes"].cpu().numpy()) >= 0.99, T
+        assert torch.equal(fu["spikes"], st["spikes"]), T
         ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
         assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= 0.99, T
 
