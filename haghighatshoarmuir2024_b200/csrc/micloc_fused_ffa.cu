@@ -9,23 +9,23 @@
 // lanes, so that the serial depth of each role per tile is short) and run as a software pipeline, one
 // named barrier per tile (iteration k):
 //
-//   loader       tile k+1   audio (HBM) -> the three sub-sequence rings of every microphone in shared
-//                           memory (see "fast FIR" below)
-//   FIR warps x3 tile k     STHT quadrature FIR as three half-length sub-filters; every lane owns 8
-//                           consecutive output pairs of one (microphone, sub-filter) and walks its 120
-//                           taps in blocks of 8 with a sliding register window (packed FFMA2, see fir_block);
-//                           the three partial results are recombined inside the warp and the finished
-//                           quadrature tile goes to shared memory
-//   band-pass    tile k-1   one lane per (clip, channel): SOS band-pass recurrence, running sum,
-//                           sign / zero bit masks of every 32-sample segment -> shared memory; the
-//                           in-phase input x[(t - K/2) mod T] (np.roll) is re-read from global memory (L2)
-//   RZCC         tile k-2   one lane per (clip, channel): the masks are turned into RZCC
+//   FIR warps x4 tile k-1   recombine the sub-filter results of the previous step into the quadrature tile
+//                tile k     STHT quadrature FIR as three half-length sub-filters, each split into three tap
+//                           thirds ("pieces" of 5 tap blocks); every lane runs two pieces of 8 consecutive output
+//                           pairs with a sliding register window (packed FFMA2) and trades partial sums with
+//                           two partner lanes by shuffles; the finished vectors go to shared memory
+//   band-pass    tile k-2   one lane per (clip, channel): SOS band-pass recurrence, running sum, sign masks of
+//                           every 32-sample segment -> shared memory; the in-phase input x[(t - K/2) mod T]
+//                           (np.roll) comes from the R0 / R1 rings (clip tail: global memory)
+//   RZCC         tile k-3   one lane per (clip, channel): the masks are turned into RZCC
 //                           candidates and resolved (find_peaks distance rule) into a bit-packed
 //                           spike ring
 //   neuron       tile k-d   (d = the latency of the exact find_peaks decision) one lane per (clip,
 //                           channel): alpha-kernel neuron recurrences driven by the final spike
 //                           bits -> membrane tile + int8 spike tile in shared memory
-//   Gram         tile k-d-1 C += v v^T of the membrane tile (FFMA2 on 4x4 blocks), int8 spike
+//   Gram+loader  tile k+1   audio (HBM) -> the three sub-sequence rings of every microphone (loads issued at
+//                           the start of the step, stored at its end)
+//                tile k-d-1 C += V V^T of the membrane tile on the tensor cores (TF32 x3 split), int8 spike
 //                           raster of the tile -> HBM
 //   clip end                power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 //
@@ -39,12 +39,19 @@
 // of the multiply-adds of the direct form is never executed (a 2-parallel fast FIR algorithm; the float32
 // error against the float64 reference stays at the direct form's ~1e-6 relative).  The loader keeps R0, R1
 // and S = R0 + R1 of every microphone in three rings, so that each sub-filter is the same register-blocked
-// sliding-window loop on its own ring with its own tap array.
+// sliding-window loop on its own ring with its own tap array.  The 12 M tasks (sub-filter x row x half tile) of
+// a group-tile do not fill a whole number of warps; cut into tap thirds they fill four warps to 98 %, and a
+// warp issues 10 tap blocks per tile where the direct form issues 15 (see fir_role).
 //
 // Issue slots, not the FMA pipe alone, bound this kernel: an FFMA2 occupies two issue slots of its SM
 // sub-partition (tools/sched_probe.py), so every instruction of the serial roles displaces half an FFMA2.
-// One CTA holds two groups (GROUPS = 2, sixteen warps, one CTA per SM); the roles are laid out over the four
-// sub-partitions so that their instruction counts per tile balance (see k_fused).
+// One CTA holds two groups (GROUPS = 2, sixteen warps, one CTA per SM), one FIR warp of each group per
+// sub-partition (see k_fused).
+//
+// Status (round 1, B200): parity-green; the FIR warps alone sustain 315k clips/s (270k for the direct form), the
+// whole kernel 153-158k against the default kernel's 172k: its serial roles run slower here (band-pass 9500
+// cycles per tile against 5400) -- larger code (5400 against 4700 instructions: "no instruction" stalls 0.75
+// against 0.13 per issue), more band-pass instructions (ring address arithmetic), conflicted shared-memory loads.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -61,21 +68,21 @@ constexpr int kQPitch = kTile + 4;
 constexpr int kVmRows = 16 * kSlots;    // membrane tile rows: [slot][16 channels] (channels 14, 15 stay zero)
 constexpr int kVmPitch = kTile + 4;     // floats per row of the membrane tile (channel-major: ldmatrix rows of 4 samples)
 constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
-constexpr int kWarps = 8;      // 3 x FIR (sub-filter rows), loader, band-pass, RZCC, neuron, Gram
-constexpr int kFirWarps = 3;
-constexpr int kRoleLoader = 3, kRoleBandpass = 4, kRoleRzcc = 5, kRoleNeuron = 6, kRoleGram = 7;
+constexpr int kWarps = 8;      // 4 x FIR (tap thirds of the sub-filters), band-pass, RZCC, neuron, Gram + loader
+constexpr int kFirWarps = 4;
+constexpr int kRoleBandpass = 4, kRoleRzcc = 5, kRoleNeuron = 6, kRoleGram = 7;
+constexpr int kPieceBlocks = 5;    // tap blocks of 8 per piece: a sub-filter of 15 blocks is three pieces
 constexpr int kThreads = kWarps * 32;
 constexpr int kGramFlush = 2;  // tiles of float32 Gram accumulation (inside the tensor cores: truncating adds) between two folds into float64
 constexpr int kTileM = kTile / 4;      // groups of four samples (= one pair of each sub-sequence) per tile
 constexpr int kShiftP = 7;     // ring coordinate of pair m is (m + kShiftP) mod ring_p: window chunks start 8-aligned
-constexpr int kUvPitch = 2 * kTileM + 4;   // floats per row of the U / V hand-over scratch (+ one pair of the previous tile)
+constexpr int kUvPitch = 2 * kTileM + 4;   // floats per row of the U / V / W hand-over scratch (+ one pair of the previous tile)
 
 struct FusedGeom {
     int ring_p;      // pairs per sub-sequence ring (multiple of 8)
     int pitch_x;     // floats per ring; pitch_x / 4 is odd (LDS.128 of consecutive rings hit distinct bank groups)
     int nblk;        // tap blocks of 8 per sub-filter (multiple of 3: walked in groups of three)
     int tap_pitch;   // floats per tap array (A, B, A+B)
-    int rows_per_warp;   // (clip, microphone) rows per FIR warp
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int stagger;     // debug (MICLOC_FUSED_STAGGER): cycles by which group 1 of a CTA starts behind group 0
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
@@ -178,9 +185,9 @@ struct RoleTimer {
 
 struct FusedSmem {
     float *taps;            // [3: A, B, A+B][tap_pitch]
-    float *xs;              // [kSlots*M rows][3: R0, R1, R0+R1][pitch_x] sub-sequence rings
+    float *xs;              // [3: R0, R1, R0+R1][kSlots*M rows][pitch_x] sub-sequence rings
     float *qs;              // [2 tiles][kSlots*M][kQPitch]: finished quadrature tiles
-    float *uv;              // [2: U, V][kSlots*M][kUvPitch]: partial results handed over inside a FIR warp
+    float *uv;              // [3: U, V, W][kSlots*M][kUvPitch]: sub-filter results of one tile, recombined one step later
     float *vms;             // [2 tiles][kVmRows][kVmPitch] membrane tiles, channel-major
     float *cs;
     unsigned int *seg;      // [2 tiles][kTile/kSeg][3: neg mask, zero mask, carry][32 lanes]: band-pass -> RZCC hand-over
@@ -194,145 +201,197 @@ struct FusedSmem {
 };
 constexpr int kSegsPerTile = kTile / kSeg;
 
-// ======= loader warp: audio tile k+1 (HBM) -> sub-sequence rings R0, R1, S = R0 + R1 of every microphone =======
-// lane = slot * 16 + group of four consecutive samples u = 4m - k0 + e, e < 4 (one pair of R0, one of R1)
+// ======= loader (part of the Gram warp): audio tile k+1 (HBM) -> sub-sequence rings R0, R1, S = R0 + R1 =======
+// lane = slot * 16 + group of four consecutive samples u = 4m - k0 + e, e < 4 (one pair of R0, one of R1);
+// fetch() issues the global loads at the start of a pipeline step, store() puts them into the rings at its end
 template <typename IN_T, int MM>
-__device__ __forceinline__ void loader_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                            const IN_T *__restrict__ audio, long long clip0, long long B, long long T64,
-                                            int lane, int NT, int k_last) {
-    const int M = MM ? MM : p.M;
-    const int T = (int)T64;
-    const int slot = lane >> 4, gi = lane & 15;
-    const bool clip_ok = clip0 + slot < B;
-    const IN_T *src = audio + (clip_ok ? clip0 + slot : clip0) * T64 * M;
-    float *rows = sm.xs + slot * M * 3 * g.pitch_x;
-    int m = gi;                                      // pair index of the tile being filled (tile 0 at k = -1)
-    int coord = (gi + kShiftP) % g.ring_p;           // its ring coordinate, kept incrementally
-    ROLE_TIMER_DECL;
-
-    for (int k = -1; k <= k_last; ++k) {
-        if (k + 1 < NT && clip_ok) {
-            const int u0 = 4 * m - p.tap_first;
-            float v[4][kRows];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int u = u0 + e;
-                const bool ok = u >= 0 && u < T;
-                const IN_T *fr = src + (ok ? (long long)u * M : 0);
-#pragma unroll
-                for (int mm = 0; mm < kRows; ++mm) v[e][mm] = (ok && mm < M) ? to_f32<IN_T>(fr[mm]) : 0.f;
-            }
-#pragma unroll
-            for (int mm = 0; mm < kRows; ++mm)
-                if (mm < M) {
-                    float *r = rows + mm * 3 * g.pitch_x + 2 * coord;
-                    *reinterpret_cast<float2 *>(r) = make_float2(v[0][mm], v[1][mm]);
-                    *reinterpret_cast<float2 *>(r + g.pitch_x) = make_float2(v[2][mm], v[3][mm]);
-                    *reinterpret_cast<float2 *>(r + 2 * g.pitch_x) = make_float2(v[0][mm] + v[2][mm], v[1][mm] + v[3][mm]);
-                }
-            m += kTileM;
-            coord += kTileM; if (coord >= g.ring_p) coord -= g.ring_p;
-        }
-        ROLE_BARRIER();
+struct Loader {
+    const IN_T *src;
+    float *rows;
+    int m, coord, M, T, k0, ring_p, pitch_x, f_stride;
+    bool clip_ok;
+    __device__ __forceinline__ void init(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                         const IN_T *__restrict__ audio, long long clip0, long long B, long long T64, int lane) {
+        M = MM ? MM : p.M; T = (int)T64; k0 = p.tap_first; ring_p = g.ring_p; pitch_x = g.pitch_x;
+        const int slot = lane >> 4, gi = lane & 15;
+        clip_ok = clip0 + slot < B;
+        src = audio + (clip_ok ? clip0 + slot : clip0) * T64 * M;
+        rows = sm.xs + slot * M * g.pitch_x;
+        f_stride = kSlots * M * g.pitch_x;              // rings are [3: R0, R1, S][clip row][pitch_x]
+        m = gi;                                      // pair index of the tile being filled (tile 0 at k = -1)
+        coord = (gi + kShiftP) % g.ring_p;           // its ring coordinate, kept incrementally
     }
-    ROLE_TIMER_FLUSH(kRoleLoader);
+    __device__ __forceinline__ void fetch(float (&v)[4][kRows]) const {
+        const int u0 = 4 * m - k0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int u = u0 + e;
+            const bool ok = u >= 0 && u < T;
+            const IN_T *fr = src + (ok ? (long long)u * M : 0);
+#pragma unroll
+            for (int mm = 0; mm < kRows; ++mm) v[e][mm] = (ok && mm < M) ? to_f32<IN_T>(fr[mm]) : 0.f;
+        }
+    }
+    __device__ __forceinline__ void store(const float (&v)[4][kRows]) {
+#pragma unroll
+        for (int mm = 0; mm < kRows; ++mm)
+            if (mm < M) {
+                float *r = rows + mm * pitch_x + 2 * coord;
+                *reinterpret_cast<float2 *>(r) = make_float2(v[0][mm], v[1][mm]);
+                *reinterpret_cast<float2 *>(r + f_stride) = make_float2(v[2][mm], v[3][mm]);
+                *reinterpret_cast<float2 *>(r + 2 * f_stride) = make_float2(v[0][mm] + v[2][mm], v[1][mm] + v[3][mm]);
+            }
+        m += kTileM;
+        coord += kTileM; if (coord >= ring_p) coord -= ring_p;
+    }
+};
+
+// ======= FIR warps: STHT quadrature FIR of tile k as the three half-length sub-filters U, V, W, in tap thirds =======
+// A task = 8 output pairs of one (chunk, sub-filter, row); its 15 tap blocks are three PIECES of 5 (a, b, c).  The 12 M
+// tasks of a tile are split evenly over the four FIR warps (n = 3 M each, 21 for M = 7) and every lane runs two
+// pieces per tile, so that a warp issues 10 tap blocks instead of 15.  With h = n / 2 the lanes form triples
+//     lane j      (j < h): pieces a, b of task j        (one running sum)  + piece c from lane h + j
+//     lane h + j         : piece a of task h + j, then piece c of task j   (handed on by shuffles)
+//     lane 2h + j        : pieces b, c of task h + j    (one running sum)  + piece a from lane h + j
+// (odd n: lanes 3h, 3h + 1 share the last task).  Consecutive lanes work on consecutive rows of the same sub-filter
+// and mostly the same tap third: their window loads spread over the shared-memory banks (6.4 wavefronts per
+// LDS.128 against 10.9 for consecutive pieces per lane).  The finished U, V, W vectors go to shared memory; the FIR
+// warps recombine them into the quadrature tile at the start of the next pipeline step
+// (Y[2m] = U[m] + V[m-1], Y[2m+1] = W[m] - U[m] - V[m]).
+struct Piece { const float *row; const float *tp; int c0; bool on; };
+
+__device__ __forceinline__ void run_piece(unsigned long long (&acc)[8], const Piece &q, int ringf) {
+    Chunk A, Bq, Cq;
+    Taps8 t0, t1;
+    int cn = q.c0 + 16; if (cn >= ringf) cn -= ringf;
+    load_chunk(Bq, q.row, cn);
+    load_chunk(A, q.row, q.c0);
+    cn = q.c0 - 16; if (cn < 0) cn += ringf;
+    load_taps(t0, q.tp);
+    load_chunk(Cq, q.row, cn); cn -= 16; if (cn < 0) cn += ringf;
+    load_taps(t1, q.tp + 8);
+    fir_block(acc, A, Bq, t0);
+    load_chunk(Bq, q.row, cn); cn -= 16; if (cn < 0) cn += ringf;
+    load_taps(t0, q.tp + 16);
+    fir_block(acc, Cq, A, t1);
+    load_chunk(A, q.row, cn); cn -= 16; if (cn < 0) cn += ringf;
+    load_taps(t1, q.tp + 24);
+    fir_block(acc, Bq, Cq, t0);
+    load_chunk(Cq, q.row, cn);
+    load_taps(t0, q.tp + 32);
+    fir_block(acc, A, Bq, t1);
+    fir_block(acc, Cq, A, t0);
 }
 
-// ======= FIR warps: STHT quadrature FIR of tile k as the three half-length sub-filters U, V, W =======
-// lane = chunk * 15 + local row * 3 + sub-filter (lanes 30, 31 idle); a lane owns the 8 output pairs
-// m = 16k + 8 chunk + i of its (row, sub-filter)
 template <int MM>
 __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
-                                         long long clip0, long long B, int warp_f, int lane, int NT, int k_last) {
+                                         long long clip0, long long B, int warp_f, int lane, int NT, int k_last, int fir_bar) {
     const int M = MM ? MM : p.M;
-    const int f_chunk = lane >= 15 ? 1 : 0;
-    const int q = lane - 15 * f_chunk, rl = q / 3, f = q - 3 * rl;
-    const int rowi = warp_f * g.rows_per_warp + rl;             // (slot, microphone) row
-    const bool work = lane < 30 && rl < g.rows_per_warp && rowi < kSlots * M && clip0 + rowi / M < B;
+    const int rows = kSlots * M;
     const int ringf = 2 * g.ring_p;
-    const float *row = sm.xs + ((work ? rowi : 0) * 3 + f) * g.pitch_x;
-    const float *tp0 = sm.taps + f * g.tap_pitch;
-    float *uv_u = sm.uv + (work ? rowi : 0) * kUvPitch + 4;                         // U pairs of this row, pair j at 2j
-    float *uv_v = uv_u + kSlots * M * kUvPitch;                                     // V pairs (pair -1 = last of the previous tile)
-    // ring coordinate (floats) of this lane's window of tap block 0 at tile 0, kept incrementally
-    int c0 = 2 * ((8 * f_chunk) % g.ring_p);
+    const int n_t = 3 * M, h = n_t / 2;
+    // pieces of this lane (task within the warp, tap third) and the lanes it trades partial sums with
+    int p_task[2] = {-1, -1}, p_third[2] = {0, 0};
+    int role3 = 1;                      // 0: owns pieces a, b (+ c after round 1); 2: owns b, c (+ a after round 0); 1: hands on
+    int src0 = lane, src1 = lane;       // source lanes of the shuffles after round 0 / round 1
+    if (lane < h) { p_task[0] = p_task[1] = lane; p_third[0] = 0; p_third[1] = 1; role3 = 0; src1 = lane + h; }
+    else if (lane < 2 * h) { p_task[0] = lane; p_third[0] = 0; p_task[1] = lane - h; p_third[1] = 2; }
+    else if (lane < 3 * h) { p_task[0] = p_task[1] = lane - h; p_third[0] = 1; p_third[1] = 2; role3 = 2; src0 = lane - h; }
+    else if ((n_t & 1) && lane == 3 * h) { p_task[0] = p_task[1] = 2 * h; p_third[0] = 0; p_third[1] = 1; role3 = 3; src0 = lane + 1; }
+    else if ((n_t & 1) && lane == 3 * h + 1) { p_task[0] = 2 * h; p_third[0] = 2; }
+    Piece pc[2];
+    int t_f = 0, t_row = 0, t_chunk = 0;
+    bool t_on = false;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const bool in = p_task[r] >= 0;
+        const int tg = warp_f * n_t + (in ? p_task[r] : 0);    // task of the group-tile: (chunk, sub-filter) major, row minor
+        const int cf = tg / rows, rowi = tg - cf * rows, chunk = cf / 3, f = cf - 3 * chunk;
+        pc[r].on = in && clip0 + rowi / M < B;
+        pc[r].row = sm.xs + (f * rows + rowi) * g.pitch_x;
+        pc[r].tp = sm.taps + f * g.tap_pitch + 8 * kPieceBlocks * p_third[r];
+        int c = (8 * chunk - 8 * kPieceBlocks * p_third[r]) % g.ring_p;
+        if (c < 0) c += g.ring_p;
+        pc[r].c0 = 2 * c;                                      // ring coordinate (floats) of block 0's window at tile 0
+        // the task whose finished vector this lane holds after the exchanges
+        if (((role3 == 0 || role3 == 3) && r == 0) || (role3 == 2 && r == 1)) { t_f = f; t_row = rowi; t_chunk = chunk; t_on = pc[r].on; }
+    }
+    float *t_dst = sm.uv + (t_f * rows + t_row) * kUvPitch + 4 + 16 * t_chunk;
+    // recombination of this warp: 2M of the 8M (row, chunk, Y[2m] | Y[2m+1]) vectors, two lanes (four pairs each) per vector
+    const int ct = warp_f * 2 * M + (lane >> 1), c_half = lane & 1;
+    const int c_cg = ct >> 1, c_odd = ct & 1, c_row = (c_cg >> 1) < rows ? (c_cg >> 1) : 0, c_chunk = c_cg & 1;
+    const bool c_on = lane < 4 * M && clip0 + c_row / M < B;
+    const float *c_u = sm.uv + c_row * kUvPitch + 4 + 16 * c_chunk + 8 * c_half;
+    const float *c_v = c_u + rows * kUvPitch, *c_w = c_v + rows * kUvPitch;
+    const unsigned long long one2 = pack2(1.f, 1.f);
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
+        // (a) quadrature tile k-1 from the U, V, W vectors the FIR warps left in shared memory one step ago
+        if (k >= 1 && k - 1 < NT && c_on) {
+            float *qrow = sm.qs + (((k - 1) & 1) * rows + c_row) * kQPitch + 32 * c_chunk + 16 * c_half;
+            if (!c_odd) {
+                float2 uu[4], vv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uu[i] = *reinterpret_cast<const float2 *>(c_u + 2 * i);
+                    vv[i] = *reinterpret_cast<const float2 *>(c_v + 2 * i - 2);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float2 *>(qrow + 4 * i) = make_float2(uu[i].x + vv[i].x, uu[i].y + vv[i].y);
+            } else {
+                float4 uu[2], vv[2], ww[2];
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4) {
+                    uu[v4] = reinterpret_cast<const float4 *>(c_u)[v4];
+                    vv[v4] = reinterpret_cast<const float4 *>(c_v)[v4];
+                    ww[v4] = reinterpret_cast<const float4 *>(c_w)[v4];
+                }
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4) {
+                    *reinterpret_cast<float2 *>(qrow + 8 * v4 + 2) =
+                        make_float2((ww[v4].x - uu[v4].x) - vv[v4].x, (ww[v4].y - uu[v4].y) - vv[v4].y);
+                    *reinterpret_cast<float2 *>(qrow + 8 * v4 + 6) =
+                        make_float2((ww[v4].z - uu[v4].z) - vv[v4].z, (ww[v4].w - uu[v4].w) - vv[v4].w);
+                }
+            }
+        }
+        // every FIR warp has read the old vectors before any of them writes new ones
+        asm volatile("bar.sync %0, %1;" ::"r"(fir_bar), "n"(32 * kFirWarps) : "memory");
+        // (b) the pieces of tile k
         if (k >= 0 && k < NT) {
             unsigned long long acc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0ull;
-            if (work) {
-                Chunk A, Bq, Cq;
-                { int ch = c0 + 16; if (ch >= ringf) ch -= ringf; load_chunk(Bq, row, ch); }
-                load_chunk(A, row, c0);
-                int cn = c0 - 16; if (cn < 0) cn += ringf;
-                // window chunks and taps are fetched one block ahead of their use
-                const float *tp = tp0;
-                Taps8 t0, t1;
-                load_taps(t0, tp);
 #pragma unroll 1
-                for (int jb = 0; jb < (g.fir_blocks ? g.fir_blocks : g.nblk); jb += 3) {
-                    load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += ringf;
-                    load_taps(t1, tp + 8);
-                    fir_block(acc, A, Bq, t0);
-                    load_chunk(Bq, row, cn); cn -= 16; if (cn < 0) cn += ringf;
-                    load_taps(t0, tp + 16);
-                    fir_block(acc, Cq, A, t1);
-                    load_chunk(A, row, cn); cn -= 16; if (cn < 0) cn += ringf;
-                    load_taps(t1, tp + 24);             // first block of the next round (zero padding behind the last)
-                    fir_block(acc, Bq, Cq, t0);
-                    t0 = t1;
-                    tp += 24;
-                }
-                // U and V go through shared memory to the lanes that recombine them
-                if (f < 2) {
-                    float *dst = (f == 0 ? uv_u : uv_v) + 16 * f_chunk;
+            for (int r = 0; r < 2; ++r) {
+                // (one copy of the tap loop: the kernel's code footprint matters, its eight roles share the instruction cache)
+                Piece q;
+                q.row = r ? pc[1].row : pc[0].row; q.tp = r ? pc[1].tp : pc[0].tp;
+                q.c0 = r ? pc[1].c0 : pc[0].c0; q.on = r ? pc[1].on : pc[0].on;
+                if (q.on) run_piece(acc, q, ringf);
+                const int src = r ? src1 : src0;
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        float4 o;
-                        unpack2(acc[2 * v4], o.x, o.y);
-                        unpack2(acc[2 * v4 + 1], o.z, o.w);
-                        reinterpret_cast<float4 *>(dst)[v4] = o;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned long long got = __shfl_sync(0xffffffffu, acc[i], src);
+                    if (r == 0 ? role3 >= 2 : role3 == 0) ffma2(acc[i], got, one2);
+                    if (r == 0 && role3 == 1) acc[i] = 0ull;
                 }
             }
-            __syncwarp();
-            if (work) {
-                float *qrow = sm.qs + ((k & 1) * kSlots * M + rowi) * kQPitch + 32 * f_chunk;
-                if (f == 0) {
-                    // Y[2m] = U[m] + V[m-1]
-                    const float *vp = uv_v + 16 * f_chunk - 2;
+            if (t_on && role3 != 1) {
+                if (t_f == 1 && t_chunk == 1)           // V[16(k-1) + 15] becomes the V[m-1] of the next tile's first pair
+                    *reinterpret_cast<float2 *>(t_dst - 16 - 2) = *reinterpret_cast<const float2 *>(t_dst + 14);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 vv = *reinterpret_cast<const float2 *>(vp + 2 * i);
-                        float ux, uy;
-                        unpack2(acc[i], ux, uy);
-                        *reinterpret_cast<float2 *>(qrow + 4 * i) = make_float2(ux + vv.x, uy + vv.y);
-                    }
-                } else if (f == 2) {
-                    // Y[2m+1] = W[m] - U[m] - V[m]
-                    const float *up = uv_u + 16 * f_chunk, *vp = uv_v + 16 * f_chunk;
-#pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        const float4 uu = reinterpret_cast<const float4 *>(up)[v4];
-                        const float4 vv = reinterpret_cast<const float4 *>(vp)[v4];
-                        float wx, wy;
-                        unpack2(acc[2 * v4], wx, wy);
-                        *reinterpret_cast<float2 *>(qrow + 8 * v4 + 2) = make_float2((wx - uu.x) - vv.x, (wy - uu.y) - vv.y);
-                        unpack2(acc[2 * v4 + 1], wx, wy);
-                        *reinterpret_cast<float2 *>(qrow + 8 * v4 + 6) = make_float2((wx - uu.z) - vv.z, (wy - uu.w) - vv.w);
-                    }
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    float4 o;
+                    unpack2(acc[2 * v4], o.x, o.y);
+                    unpack2(acc[2 * v4 + 1], o.z, o.w);
+                    reinterpret_cast<float4 *>(t_dst)[v4] = o;
                 }
             }
-            __syncwarp();
-            if (work && f == 1 && f_chunk == 1) {      // V[16k + 15] is the next tile's V[m-1]
-                float lx, ly;
-                unpack2(acc[7], lx, ly);
-                *reinterpret_cast<float2 *>(uv_v - 2) = make_float2(lx, ly);
-            }
-            c0 += 2 * kTileM; if (c0 >= ringf) c0 -= ringf;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { pc[r].c0 += 2 * kTileM; if (pc[r].c0 >= ringf) pc[r].c0 -= ringf; }
         }
         ROLE_BARRIER();
     }
@@ -372,15 +431,10 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
     }
     BiquadState bq; biquad_reset(bq);
     float csum = 0.f;
-    float xpre[8];                      // in-phase samples fetched ahead for the next segment
-    bool pre_ok = false;
-    int pre_src = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) xpre[i] = 0.f;
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kc = k - 1;
+        const int kc = k - 2;
         const int t0 = kc * kTile;
         if (kc >= 0 && t0 < T) {
 #pragma unroll 1
@@ -389,17 +443,22 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                 float *cs = sm.cs + ((kc & 1) * kSegsPerTile + sg) * kSeg * 32 + lane;
                 unsigned int *sgm = sm.seg + ((kc & 1) * kSegsPerTile + sg) * 3 * 32 + lane;
                 if (ts >= T || !c_valid) continue;
-                // in-phase input: x[(t - K/2) mod T] (np.roll, snn_beamformer.py:325), re-read from global memory
-                // (the loader fetched these frames a few tiles ago: L2 hits); quadrature input: the FIR warps' tile
+                // in-phase input x[(t - K/2) mod T] (np.roll, snn_beamformer.py:325): from the R0 / R1 rings where the
+                // segment lies inside their history, from global memory for the clip tail in front of the clip
+                // (t < K/2) and for ragged segments; quadrature input: the FIR warps' tile
                 int src0 = (ts - p.half) % T;             // (warp-uniform) source sample of the segment's first sample
                 if (src0 < 0) src0 += T;
-                const IN_T *gp = clip_audio + (long long)src0 * M + (c_inphase ? c_ch : 0);
                 const float *qp = sm.qs + (((kc & 1) * kSlots + c_slot) * M + (c_inphase ? 0 : c_ch - M)) * kQPitch + sg * kSeg;
-                // (warp-uniform) a whole segment inside the clip whose in-phase source does not wrap
-                const bool fast = ts + kSeg <= T && src0 + kSeg <= T;
+                // sample u sits in pair m = (u + k0) >> 2 of ring (u + k0) >> 1 & 1, half (u + k0) & 1; a group of 8
+                // samples that starts with (u + k0) & 3 == 1 is R0[m].y, R1[m], R0[m+1], R1[m+1], R0[m+2].x
+                const int ua = ts - p.half + p.tap_first;
+                const bool fast = ts + kSeg <= T && ts >= p.half && (ua & 3) == 1;      // (warp-uniform)
+                int cseg = ((ua >> 2) + kShiftP) % g.ring_p;                              // ring coordinate of the segment's first pair
+                const float *r0 = sm.xs + (c_slot * M + (c_inphase ? c_ch : 0)) * g.pitch_x;
+                const float *r1 = r0 + kSlots * M * g.pitch_x;
                 const float carry = csum;
                 unsigned int neg = 0u, zero = 0u;
-                // sample by sample with explicit sign / zero masks (ragged segments, wrapping in-phase source, exact zeros)
+                // sample by sample with explicit sign / zero masks (ragged segments, clip-tail in-phase source, exact zeros)
                 auto slow_segment = [&](int nvalid) {
                     int src = src0;
 #pragma unroll 1
@@ -413,31 +472,32 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                         zero |= (z == 0.f ? 1u : 0u) << (31 - i);
                     }
                 };
+                auto load_group = [&](int o, float (&x)[8]) {
+                    if (c_inphase) {
+                        int c = cseg + 2 * o; if (c >= g.ring_p) c -= g.ring_p;
+                        const int c1 = c + 1 == g.ring_p ? 0 : c + 1, c2 = c1 + 1 == g.ring_p ? 0 : c1 + 1;
+                        x[0] = r0[2 * c + 1];
+                        const float2 a = *reinterpret_cast<const float2 *>(r1 + 2 * c);
+                        const float2 b = *reinterpret_cast<const float2 *>(r0 + 2 * c1);
+                        const float2 d = *reinterpret_cast<const float2 *>(r1 + 2 * c1);
+                        x[1] = a.x; x[2] = a.y; x[3] = b.x; x[4] = b.y; x[5] = d.x; x[6] = d.y;
+                        x[7] = r0[2 * c2];
+                    } else {
+                        const float4 a = reinterpret_cast<const float4 *>(qp)[2 * o], b = reinterpret_cast<const float4 *>(qp)[2 * o + 1];
+                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    }
+                };
                 if (fast) {
                     const BiquadState bq0 = bq;
                     float zmin = 1.f;                   // smallest |z| of the segment: exact zeros are rare (silence)
                     float xn[8];
-                    const bool pre = pre_ok && pre_src == src0;     // (warp-uniform) this segment's first in-phase group is here already
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) xn[i] = c_inphase ? (pre ? xpre[i] : to_f32<IN_T>(gp[i * M])) : qp[i];
+                    load_group(0, xn);
 #pragma unroll 1
                     for (int o = 0; o < kSeg / 8; ++o) {
                         float xc[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) xc[i] = xn[i];
-                        if (o + 1 < kSeg / 8) {         // inputs of the next group: their latency hides behind this one
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                xn[i] = c_inphase ? to_f32<IN_T>(gp[(8 * (o + 1) + i) * M]) : qp[8 * (o + 1) + i];
-                        } else {
-                            // the next segment's first in-phase group (global memory: it does not wait for the tile barrier)
-                            pre_src = src0 + kSeg;
-                            pre_ok = pre_src + 8 <= T;
-                            if (pre_ok && c_inphase) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) xpre[i] = to_f32<IN_T>(gp[(kSeg + i) * M]);
-                            }
-                        }
+                        if (o + 1 < kSeg / 8) load_group(o + 1, xn);     // inputs of the next group: their latency hides behind this one
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float z = biquad2_step(sos, bq, xc[i]);
@@ -452,7 +512,6 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                         slow_segment(kSeg);
                     }
                 } else {
-                    pre_ok = false;
                     slow_segment(T - ts < kSeg ? T - ts : kSeg);
                 }
                 sgm[0] = neg; sgm[32] = zero; sgm[64] = __float_as_uint(carry);
@@ -482,7 +541,7 @@ __device__ __forceinline__ void rzcc_role(const FusedSmem &sm, const ChainParams
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
-        const int kr = k - 2;
+        const int kr = k - 3;
         const int t0 = kr * kTile;
         if (kr >= 0 && t0 < T && c_valid) {
 #pragma unroll 1
@@ -597,10 +656,14 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &g, int8_t *__restrict__ spikes,
-                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
-    const int C2 = 2 * MMv;
+template <typename IN_T, int MM>
+__device__ __forceinline__ void gram_role(const FusedSmem &sm, const ChainParams &p, const FusedGeom &g,
+                                          const IN_T *__restrict__ audio, int8_t *__restrict__ spikes,
+                                          long long clip0, long long B, long long T64, int lane, int NT, int k_last) {
+    const int C2 = 2 * (MM ? MM : p.M);
     const int T = (int)T64;
+    Loader<IN_T, MM> ld;
+    ld.init(sm, p, g, audio, clip0, B, T64, lane);
     // ldmatrix row of this lane: matrix lane / 8 = (channels 0-7 | 8-15) x (samples 0-3 | 4-7) of a k-step
     const int lm_row = (lane & 7) + 8 * ((lane >> 3) & 1), lm_t = 4 * (lane >> 4);
     float accf[kSlots][2][4];           // float32 partial sums: [slot][column block][m16n8 accumulator fragment]
@@ -614,6 +677,10 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
+        // audio tile k+1: the loads are issued here and stored after the Gram work, their latency hides behind it
+        const bool filling = k + 1 < NT && ld.clip_ok;
+        float av[4][kRows];
+        if (filling) ld.fetch(av);
         const int j = k - g.dtile - 1;
         const int u0 = j * kTile;
         const bool live = j >= 0 && u0 < T;
@@ -669,6 +736,7 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
                 }
             }
         }
+        if (filling) ld.store(av);
         ROLE_BARRIER();
     }
     ROLE_TIMER_FLUSH(kRoleGram);
@@ -685,39 +753,18 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &
             }
 }
 
-// GROUPS = 2: ONE CTA of sixteen warps per SM holding two independent clip-pair groups (own named barrier,
+// GROUPS = 2: ONE CTA of sixteen warps per SM holding two independent clip-pair groups (own named barriers,
 //             own shared-memory region, own clip pairs).  Hardware warp slot w belongs to sub-partition
-//             w % 4, whose single issue port all its warps share.  Streams and chains are kept apart:
-//                sub-partition 0 / 1: the three FIR warps and the loader of group 0 / 1
-//                sub-partition 2 / 3: band-pass, RZCC, neuron and Gram of group 0 / 1
-//             Three FIR warps saturate their sub-partition's issue port with independent FFMA2s (~2000 slots
-//             each per tile); the serial roles are chains of dependent instructions per sample, and a chain
-//             that shares a sub-partition with an FFMA2 stream runs three times slower per instruction
-//             (tools/sched_probe.py), while four chains side by side fill one another's latency gaps
-//             (~5500 slots per tile).
-// GROUPS = 1: a CTA is one group of eight warps (two CTAs per SM), role = warp; the fallback when two
-//             groups do not fit the shared memory of one CTA (long STHT kernels).
-static const unsigned char kRoleMaps[4][16] = {
-    // layout 0 (mixed): (group << 3 | role) of warp 4 i + sub-partition
-    {0 << 3 | 0, 0 << 3 | 1, 0 << 3 | 2, 1 << 3 | 2,
-     1 << 3 | 0, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
-     0 << 3 | kRoleGram, 1 << 3 | kRoleGram, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
-     1 << 3 | kRoleLoader, 0 << 3 | kRoleLoader, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleRzcc},
-    // layout 1 (streams and chains apart)
-    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
-     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleRzcc,
-     0 << 3 | 2, 1 << 3 | 2, 0 << 3 | kRoleNeuron, 1 << 3 | kRoleNeuron,
-     0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader, 0 << 3 | kRoleGram, 1 << 3 | kRoleGram},
-    // layout 2 (balanced for the tensor-core Gram: FIR 0, 1 + RZCC + Gram | FIR 2 + band-pass + neuron + loader)
-    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
-     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
-     1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
-     1 << 3 | kRoleGram, 0 << 3 | kRoleGram, 0 << 3 | kRoleLoader, 1 << 3 | kRoleLoader},
-    // layout 3: FIR 0, 1 + RZCC + loader | FIR 2 + band-pass + neuron + Gram
-    {0 << 3 | 0, 1 << 3 | 0, 0 << 3 | 2, 1 << 3 | 2,
-     0 << 3 | 1, 1 << 3 | 1, 0 << 3 | kRoleBandpass, 1 << 3 | kRoleBandpass,
-     1 << 3 | kRoleRzcc, 0 << 3 | kRoleRzcc, 1 << 3 | kRoleNeuron, 0 << 3 | kRoleNeuron,
-     1 << 3 | kRoleLoader, 0 << 3 | kRoleLoader, 0 << 3 | kRoleGram, 1 << 3 | kRoleGram}};
+//             w % 4, whose single issue port all its warps share: one FIR warp of each group per
+//             sub-partition, the serial roles of the two groups in opposite order.
+// GROUPS = 1: a CTA is one group of eight warps (two CTAs per SM), role = warp.
+static const unsigned char kRoleMaps[1][16] = {
+    // (group << 3 | role) of warp 4 i + sub-partition: one FIR warp of each group per sub-partition, the serial
+    // roles of group 1 in reverse order so that band-pass + Gram/loader and RZCC + neuron share a sub-partition
+    {0 << 3 | 0, 0 << 3 | 1, 0 << 3 | 2, 0 << 3 | 3,
+     1 << 3 | 0, 1 << 3 | 1, 1 << 3 | 2, 1 << 3 | 3,
+     0 << 3 | kRoleBandpass, 0 << 3 | kRoleRzcc, 0 << 3 | kRoleNeuron, 0 << 3 | kRoleGram,
+     1 << 3 | kRoleGram, 1 << 3 | kRoleNeuron, 1 << 3 | kRoleRzcc, 1 << 3 | kRoleBandpass}};
 
 template <typename IN_T, int MM, int GROUPS>
 __global__ void __launch_bounds__(kThreads * GROUPS, GROUPS == 1 ? 2 : 1)
@@ -807,7 +854,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             float4 *x4 = reinterpret_cast<float4 *>(sm.xs);
             const int n4 = kSlots * M * 3 * g.pitch_x / 4;
             for (int i = tid; i < n4; i += kThreads) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = tid; i < 2 * kSlots * M * kUvPitch; i += kThreads) sm.uv[i] = 0.f;    // V[-1] = 0
+            for (int i = tid; i < 3 * kSlots * M * kUvPitch; i += kThreads) sm.uv[i] = 0.f;    // V[-1] = 0
             // no spikes before the clip start; membrane columns of unused lanes stay zero
             for (int i = tid; i < 2 * kRingWords * 32; i += kThreads) sm.bits[i] = 0u;
             for (int i = tid; i < 2 * kVmRows * kVmPitch; i += kThreads) sm.vms[i] = 0.f;
@@ -815,14 +862,16 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         group_sync();
 
         if ((g.skip >> role) & 1) {
-            for (int k = -1; k <= k_last; ++k) tile_barrier(bar_id);
+            for (int k = -1; k <= k_last; ++k) {
+                if (role < kFirWarps) asm volatile("bar.sync %0, %1;" ::"r"(3 + group), "n"(32 * kFirWarps) : "memory");
+                tile_barrier(bar_id);
+            }
         } else if (role < kFirWarps)
-            fir_role<MM>(sm, p, g, clip0, B, role, lane, NT, k_last);
-        else if (role == kRoleLoader) loader_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, NT, k_last);
+            fir_role<MM>(sm, p, g, clip0, B, role, lane, NT, k_last, 3 + group);
         else if (role == kRoleBandpass) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
         else if (role == kRoleRzcc) rzcc_role(sm, p, flags, clip0, B, T, M, lane, k_last);
         else if (role == kRoleNeuron) neuron_role(sm, p, g, clip0, B, T, M, lane, k_last);
-        else gram_role(sm, g, spikes, clip0, B, T, M, lane, k_last);
+        else gram_role<IN_T, MM>(sm, p, g, audio, spikes, clip0, B, T, lane, NT, k_last);
         group_sync();
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
         // one DoA column per thread and pass: its 2M weights are fetched first (independent loads, one
@@ -892,7 +941,10 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
 }
 
 bool fused_supported(const ChainParams &p) {
-    return p.tap_stride == 2 && p.M <= kRows && p.nsec == 2 && (p.n_taps % 8) == 0;
+    // sub-filters of exactly three pieces of kPieceBlocks tap blocks (STHT kernels of 385...480 samples: 10 ms at 48 kHz)
+    const int sub_blocks = ((p.n_taps + 1) / 2 + 7) / 8;
+    return p.tap_stride == 2 && p.M <= kRows && p.nsec == 2 && (p.n_taps % 8) == 0 &&
+           (sub_blocks + 2) / 3 * 3 == 3 * kPieceBlocks;
 }
 
 template <typename IN_T, int MM, int GROUPS>
@@ -931,27 +983,24 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
     if (const char *e = getenv("MICLOC_FUSED_STAGGER")) g.stagger = (int)strtol(e, nullptr, 0);
     {
-        int layout = 2;
-        if (const char *e = getenv("MICLOC_FUSED_LAYOUT")) layout = atoi(e);     // role placement experiments
-        for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[layout >= 0 && layout < 4 ? layout : 2][w];
+        for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[0][w];
     }
     // sub-filters of n_taps / 2 taps in blocks of 8, walked in groups of three (zero taps appended)
     const int sub_taps = (p.n_taps + 1) / 2;
     g.nblk = ((sub_taps + 7) / 8 + 2) / 3 * 3;
-    g.tap_pitch = 8 * g.nblk + 8;                        // + the block the tap prefetch runs ahead
+    g.tap_pitch = 8 * g.nblk + 12;                       // + padding: the three tap arrays start in different bank groups
     // a ring holds the oldest pair a tile's windows load (8 nblk - 1 back), the tile in the FIR and the tile being filled
     g.ring_p = (8 * g.nblk + 2 * kTileM + 7) / 8 * 8;
     g.pitch_x = 2 * g.ring_p + 4;
     if ((g.pitch_x / 4) % 2 == 0) g.pitch_x += 4;
-    g.rows_per_warp = (kSlots * p.M + kFirWarps - 1) / kFirWarps;
     // a spike at p is final once the RZCC warp passed p + rzcc_lag(w) - 1; the neuron warp works on
-    // tile k - dtile while the RZCC warp has completed tile k - 3
-    g.dtile = 3 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
+    // tile k - dtile while the RZCC warp has completed tile k - 4
+    g.dtile = 4 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
     const int rows = kSlots * p.M;
     int off = (3 * g.tap_pitch * (int)sizeof(float) + 15) & ~15;
     g.off_x = off; off += rows * 3 * g.pitch_x * (int)sizeof(float);
     g.off_q = off; off += 2 * rows * kQPitch * (int)sizeof(float);
-    g.off_uv = off; off += 2 * rows * kUvPitch * (int)sizeof(float);
+    g.off_uv = off; off += 3 * rows * kUvPitch * (int)sizeof(float);
     g.off_vm = off; off += 2 * kVmRows * kVmPitch * (int)sizeof(float);
     g.off_cs = off; off += 2 * kSegsPerTile * kSeg * 32 * (int)sizeof(float);
     g.off_seg = off; off += 2 * kSegsPerTile * 3 * 32 * (int)sizeof(int);
@@ -959,11 +1008,11 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.smem_bytes = (off + 15) & ~15;
-    if (3 * g.rows_per_warp * 2 > 32)
-        return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel: %d microphones do not fit the FIR lane map", p.M);
+    if (g.nblk != 3 * kPieceBlocks)
+        return set_error(MICLOC_ERR_UNSUPPORTED, "fast-FIR variant: sub-filters of %d tap blocks (it covers %d)", g.nblk, 3 * kPieceBlocks);
     // the spike-bit ring must hold the neuron warp's oldest read and the RZCC warp's newest write
-    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 2)
-    if (kTile * (g.dtile - 1) + p.nL + kSeg > kRingWords * 32)
+    // (the neuron warp reads back to (k - dtile) * kTile - nL while the RZCC warp clears the words of tile k - 3)
+    if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
     if (kSlots * 256 * (int)sizeof(double) > rows * 3 * g.pitch_x * (int)sizeof(float) ||
