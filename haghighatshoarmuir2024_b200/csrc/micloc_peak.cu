@@ -111,10 +111,15 @@ k_peak_mixed(float *out, int iters, float a, float b, double da, double db) {
 //   7 dependent DFMA chain                                    8 independent DFMA stream (8 accumulators)
 //   9 / 11 FFMA2 with the FIR operand pattern (all operands in non-uniform registers; tap scalar / tap pair)
 //   10 scalar FFMA with the FIR operand pattern
+//   12 / 13 FIR pattern with the taps in kernel parameters (uniform registers), tap-major / window-major order
+//   14 FIR pattern, window-major order, taps in registers
 // out[warp] = cycles of CTA 0's warp, out[16 + warp] = instructions of the measured kind it issued.
 // ---------------------------------------------------------------------------
+struct ProbeTaps { float t[64]; };
+
 __global__ void __launch_bounds__(512, 1)
-k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsigned long long *out, float *sink) {
+k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsigned long long *out, float *sink,
+              const __grid_constant__ ProbeTaps ptaps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int role = roles[warp];
     __syncthreads();
@@ -308,6 +313,93 @@ k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsign
 #pragma unroll
         for (int i = 0; i < 16; ++i) res += acc[i];
     }
+    else if (role == 12 || role == 13) {
+        // the FIR's operand pattern with the taps in the kernel parameters (constant bank -> uniform registers):
+        // role 12 in tap-major order (the tap is reused by 8 consecutive FFMA2), role 13 window-major (the window
+        // pair is reused by up to 8 consecutive FFMA2)
+        unsigned long long acc[8], win[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(lo), "f"(hi));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float lo = b + 1e-6f * (float)(lane + i), hi = lo + 1e-7f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(win[i]) : "f"(lo), "f"(hi));
+        }
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+            const int tb = 8 * (sub & 7);
+            if (role == 12) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    unsigned long long t2;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(t2) : "f"(ptaps.t[tb + j]));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(win[i + 7 - j]), "l"(t2));
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < 15; ++w)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = w - 7 + j;
+                        if (i >= 0 && i < 8) {
+                            unsigned long long t2;
+                            asm("mov.b64 %0, {%1, %1};" : "=l"(t2) : "f"(ptaps.t[tb + j]));
+                            asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(win[w]), "l"(t2));
+                        }
+                    }
+            }
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+            res += lo + hi;
+        }
+    } else if (role == 14) {
+        // window-major order with the tap in a (non-uniform) register
+        unsigned long long acc[8], win[16];
+        float tap[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(lo), "f"(hi));
+            tap[i] = a + 1e-6f * (float)(lane + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float lo = b + 1e-6f * (float)(lane + i), hi = lo + 1e-7f;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(win[i]) : "f"(lo), "f"(hi));
+        }
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int w = 0; w < 15; ++w)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = w - 7 + j;
+                    if (i >= 0 && i < 8) {
+                        unsigned long long t2;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(t2) : "f"(tap[j]));
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i]) : "l"(win[w]), "l"(t2));
+                    }
+                }
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+            res += lo + hi;
+        }
+    }
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
     if (res == 123.456f) sink[0] = res;
     if (blockIdx.x == 0 && lane == 0) { out[warp] = (unsigned long long)(t1 - t0); out[16 + warp] = n_inst; }
@@ -367,7 +459,9 @@ extern "C" int micloc_sched_probe(int device, const int32_t roles[16], int iters
     MICLOC_CUDA(cudaMemcpy(d_roles, roles, 16 * sizeof(int), cudaMemcpyHostToDevice));
     MICLOC_CUDA(cudaMemset(d_out, 0, 32 * sizeof(unsigned long long)));
     for (int rep = 0; rep < 2; ++rep) {     // the second run is the one reported (warm instruction cache)
-        k_sched_probe<<<sms, 32 * nw>>>(d_roles, iters, 0.999f, 0.001f, d_out, d_sink);
+        ProbeTaps pt;
+        for (int i = 0; i < 64; ++i) pt.t[i] = 0.999f + 1e-6f * (float)i;
+        k_sched_probe<<<sms, 32 * nw>>>(d_roles, iters, 0.999f, 0.001f, d_out, d_sink, pt);
         count_launch(1);
         MICLOC_CUDA(cudaDeviceSynchronize());
     }

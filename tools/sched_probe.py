@@ -5,7 +5,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from haghighatshoarmuir2024_b200 import _native as N
 lib = N.lib()
-NAMES = {0: "-", 1: "ffma2", 2: "chain", 3: "alu", 4: "ffma", 5: "chainmix", 6: "ffma2+alu", 7: "dchain", 8: "dfma", 9: "fir2", 10: "fir1", 11: "fir2p"}
+NAMES = {0: "-", 1: "ffma2", 2: "chain", 3: "alu", 4: "ffma", 5: "chainmix", 6: "ffma2+alu", 7: "dchain", 8: "dfma", 9: "fir2", 10: "fir1", 11: "fir2p", 12: "fir2u", 13: "fir2uw", 14: "fir2w"}
 
 def run(title, placement, iters=4000):
     roles = (ctypes.c_int32 * 16)(*([0] * 16))
@@ -64,3 +64,9 @@ run("FIR-pattern ffma x1", {0: 10})
 run("FIR-pattern ffma x2", {0: 10, 4: 10})
 run("FIR-pattern ffma x3", {0: 10, 4: 10, 8: 10})
 run("FIR-pattern ffma2 x3, all 4 SMSPs", {w: 9 for w in range(12)})
+run("FIR ffma2, uniform taps, tap-major x1", {0: 12})
+run("FIR ffma2, uniform taps, tap-major x2", {0: 12, 4: 12})
+run("FIR ffma2, uniform taps, window-major x1", {0: 13})
+run("FIR ffma2, uniform taps, window-major x2", {0: 13, 4: 13})
+run("FIR ffma2, register taps, window-major x1", {0: 14})
+run("FIR ffma2, register taps, window-major x2", {0: 14, 4: 14})
