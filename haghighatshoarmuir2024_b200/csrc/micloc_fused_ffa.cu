@@ -818,8 +818,8 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.dbg = sm_slots;
     sm.bar_id = bar_id;
     sm.rec = GROUPS * (int)blockIdx.x + group;
-    double *red_v = reinterpret_cast<double *>(smem_raw + g.off_q);      // [kThreads], clip epilogue only
-    int *red_i = reinterpret_cast<int *>(smem_raw + g.off_q + kThreads * sizeof(double));
+    double *red_v = reinterpret_cast<double *>(smem_raw + g.off_cs);     // [kThreads], clip epilogue only (reuses the running sums)
+    int *red_i = reinterpret_cast<int *>(smem_raw + g.off_cs + kThreads * sizeof(double));
 
     // tap arrays of the three sub-filters: A_n = c_2n, B_n = c_2n+1, A + B (zero padded)
     for (int i = tid; i < g.tap_pitch; i += kThreads) {
@@ -1015,8 +1015,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the fused kernel's spike ring; "
                          "use the staged path", p.w, p.nL);
-    if (kSlots * 256 * (int)sizeof(double) > rows * 3 * g.pitch_x * (int)sizeof(float) ||
-        kThreads * 12 > 2 * rows * kQPitch * (int)sizeof(float))
+    if (kSlots * 256 * (int)sizeof(double) > rows * 3 * g.pitch_x * (int)sizeof(float))
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory tiles too small for the epilogue");
     if (g.smem_bytes > 227 * 1024)
         return set_error(MICLOC_ERR_UNSUPPORTED, "fused kernel needs %d B of shared memory; use the staged path", g.smem_bytes);

@@ -103,6 +103,41 @@ def test_fast_fir_variant_batch_vs_oracle(monkeypatch):
     assert int(fu["flags"].sum()) == 0
 
 
+def _sub_array(g, mics):
+    """The golden case restricted to a subset of its microphones (rows of bf_mat follow: in-phase | quadrature)."""
+    M = g["x"].shape[1]
+    mics = np.asarray(mics)
+    g2 = dict(g)
+    g2["x"] = np.ascontiguousarray(g["x"][:, mics])
+    g2["r_vec"], g2["theta_vec"] = g["r_vec"][mics], g["theta_vec"][mics]
+    g2["bf_mat"] = np.ascontiguousarray(g["bf_mat"][np.concatenate([mics, M + mics])])
+    return g2
+
+
+@pytest.mark.parametrize("mics,variant", [((0, 2, 3, 5), ""), ((1, 2, 3, 4, 6), ""), ((0, 1, 2, 3, 4, 5), ""), ((3,), ""),
+                                          ((0, 2, 3, 5), "ffa"), ((0, 1, 2, 3, 4, 5), "ffa")])
+def test_smaller_arrays_generic_microphone_count(mics, variant, monkeypatch):
+    """Arrays of 1...6 microphones take the fused kernels' generic-M instantiation: fused vs staged vs oracle."""
+    g = _sub_array(H.load("snn_c1_bipolar"), mics)
+    T, B = 4000, 12
+    x, _ = H.synth_clips(g, B, T, seed=77 + len(mics))
+    eng = engine_for(g, T)
+    st = eng.run(to_dev(x), want_spikes=True, fused=False)
+    if variant:
+        monkeypatch.setenv("MICLOC_FUSED_FIR", variant)
+    fu = eng.run(to_dev(x), want_spikes=True, fused=True)
+    torch.cuda.synchronize()
+    cfg = H.oracle_cfg(g)
+    cfg.nir = O.neuron_kernel(np.arange(T) / float(g["fs"]), float(g["tau"]), float(g["tau"]))
+    ref = O.snn_run_batch(cfg, x, nthreads=4, want_spikes=True)
+    if not variant:
+        assert torch.equal(st["spikes"], fu["spikes"])
+    assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
+    assert (fu["doa"].cpu().numpy() == ref["doa"]).mean() >= 0.9      # 12 clips: one near-tie may flip
+    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < (1e-5 if not variant else 1e-3)
+    assert int(fu["flags"].sum()) == 0
+
+
 # ---------------------------------------------------------------------------
 # batches against the oracle: fused and staged agree within the reference tolerance with each other
 # (their float32 Gram sums run on different units) and with the oracle
