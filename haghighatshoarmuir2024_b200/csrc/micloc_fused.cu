@@ -99,8 +99,8 @@ __device__ __forceinline__ void load_taps(Taps8 &t, const float *__restrict__ ta
 }
 // Written window-major (the window pair is shared by consecutive multiply-adds).  ptxas schedules the 64 FFMA2 of a
 // block in its own order whatever the source says (`volatile` does not pin it); the sequence it emits for this
-// source measured 7 % faster for the FIR warps alone (290 k against 270 k clips/s) than the one it emits for the
-// tap-major source.  tools/sched_probe.py (roles 9, 12-14): between 2.4 and 5.2 cycles per FFMA2 and sub-partition
+// source measured fastest of five source forms (FIR warps alone 290 k clips/s; tap-major 278 k, accumulator-major
+// 283 k, older chunk first 285-291 k; whole kernel 171.8-174.1 k).  tools/sched_probe.py (roles 9, 12-14): between 2.4 and 5.2 cycles per FFMA2 and sub-partition
 // depending on the sequence.
 __device__ __forceinline__ void ffma2_ordered(unsigned long long &acc, unsigned long long w, unsigned long long g2) {
     asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(g2));
