@@ -61,7 +61,6 @@ struct FusedGeom {
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
-    int stagger;     // cycles by which clip-pair group 1 of a CTA starts behind group 0 (see k_fused)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
     int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_qa;   // byte offsets in dynamic smem
     int smem_bytes;
@@ -687,11 +686,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
                 for (int w = 0; w < kWarps; ++w) {
                     if (taken[w]) continue;
                     const unsigned int c = *(volatile unsigned int *)(fir_cnt + s_smsp[w]);
-#ifdef MICLOC_FIR_HIGH_WARPS
-                    if (c <= bestc) { bestc = c; best = w; }     // experiment: ties go to the highest warp slot
-#else
                     if (c < bestc) { bestc = c; best = w; }
-#endif
                 }
                 taken[best] = true;
                 s_role[best] = r;
@@ -751,17 +746,6 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     const int NT = (int)((T + kTile - 1) / kTile);
     const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 tiles behind
     const long long npairs = (B + kSlots - 1) / kSlots;
-
-    // The two FIR warps of a sub-partition (one per group) share its FMA pipe.  Started together they stay
-    // in phase for the whole launch (equal work per tile): both are inside their tap loop at the same time,
-    // and both are outside it (tile hand-over, audio fill, barrier) at the same time, when the pipe idles.
-    // Group 1 therefore starts a fraction of a tile period late; the offset is neutrally stable, and one
-    // group's hand-over then hides behind the other's tap loop.
-    if (GROUPS == 2 && group == 1 && g.stagger > 0) {
-        long long t0, t1;
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
-        do { asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1)); } while (t1 - t0 < (long long)g.stagger);
-    }
 
     // Clip pairs are handed out dynamically: co-resident groups do not run at the same speed, so a static
     // split would wait for the slowest one.
@@ -902,8 +886,6 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
-    g.stagger = 0;
-    if (const char *e = getenv("MICLOC_FUSED_STAGGER")) g.stagger = (int)strtol(e, nullptr, 0);
     // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
     g.nblk = (p.n_taps / 8 + 5) / 6 * 6;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load

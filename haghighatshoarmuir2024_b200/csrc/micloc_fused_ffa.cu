@@ -84,7 +84,6 @@ struct FusedGeom {
     int nblk;        // tap blocks of 8 per sub-filter (multiple of 3: walked in groups of three)
     int tap_pitch;   // floats per tap array (A, B, A+B)
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
-    int stagger;     // debug (MICLOC_FUSED_STAGGER): cycles by which group 1 of a CTA starts behind group 0
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
     unsigned char role_map[16];   // GROUPS = 2: (group << 3 | role) of warp w (sub-partition w % 4), see k_fused
@@ -834,13 +833,6 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 tiles behind
     const long long npairs = (B + kSlots - 1) / kSlots;
 
-    // experiment knob (MICLOC_FUSED_STAGGER): group 1 starts a number of cycles behind group 0 (no measured effect)
-    if (GROUPS == 2 && group == 1 && g.stagger > 0) {
-        long long t0, t1;
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0));
-        do { asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1)); } while (t1 - t0 < (long long)g.stagger);
-    }
-
     // Clip pairs are handed out dynamically: co-resident groups do not run at the same speed, so a static
     // split would wait for the slowest one.
     for (;;) {
@@ -981,7 +973,6 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
-    if (const char *e = getenv("MICLOC_FUSED_STAGGER")) g.stagger = (int)strtol(e, nullptr, 0);
     {
         for (int w = 0; w < 16; ++w) g.role_map[w] = kRoleMaps[0][w];
     }
