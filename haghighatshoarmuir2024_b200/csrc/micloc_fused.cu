@@ -61,6 +61,7 @@ struct FusedGeom {
     int dtile;       // the neuron warp runs dtile tiles behind the pipeline step (RZCC decision latency)
     int tiles_is;    // tiles whose in-phase input comes from the clip tail (t < K/2)
     int fir_blocks;  // debug (MICLOC_FUSED_FIRBLOCKS): tap blocks each FIR warp really computes (0 = all; results are garbage)
+    int perm;        // serial roles of group 1 on sub-partitions 0..3, two bits each (see k_fused)
     int skip;        // debug (MICLOC_FUSED_SKIP): bit r set = role r only attends the tile barriers (results are garbage)
     int off_x, off_q, off_vm, off_is, off_cs, off_seg, off_clus, off_bits, off_stage, off_qa;   // byte offsets in dynamic smem
     int smem_bytes;
@@ -707,7 +708,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             role = warp & 3;
         } else {
             group = (warp - 2 * kFirWarps) >> 2;
-            role = kFirWarps + (group == 0 ? (warp & 3) : 3 - (warp & 3));
+            role = kFirWarps + (group == 0 ? (warp & 3) : (g.perm >> (2 * (warp & 3))) & 3);
         }
         if (lane == 0) {
             unsigned int wid;
@@ -886,6 +887,14 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     FusedGeom g{};
     if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
+    {
+        // group 0 runs band-pass, RZCC, neuron, Gram on sub-partitions 0..3; group 1's order decides which roles share one
+        static const int perms[3][4] = {{3, 2, 1, 0}, {2, 3, 0, 1}, {1, 0, 3, 2}};
+        int layout = 0;
+        if (const char *e = getenv("MICLOC_FUSED_LAYOUT")) layout = atoi(e);
+        if (layout < 0 || layout > 2) layout = 0;
+        g.perm = perms[layout][0] | perms[layout][1] << 2 | perms[layout][2] << 4 | perms[layout][3] << 6;
+    }
     // FIR tap blocks of 8, two halves walked in groups of three (zero taps appended up to a multiple of 48)
     g.nblk = (p.n_taps / 8 + 5) / 6 * 6;
     const int lookback = p.tap_first + 14 + 16 * (g.nblk - 1);      // oldest sample a tile's FIR windows load
