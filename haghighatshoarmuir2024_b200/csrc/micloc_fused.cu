@@ -4,10 +4,10 @@
 // Reference sites: micloc/snn_beamformer.py:283-370 and the callers' power/argmax
 // paper_plots/target_snn_localization.py:462-464.
 //
-// One persistent CTA of eight warps owns kSlots = 2 clips at a time and walks them in time tiles
+// A clip-pair GROUP of eight warps owns kSlots = 2 clips at a time and walks them in time tiles
 // of kTile = 64 samples.  The warps are specialised BY FUNCTION (every role serves both clips with
 // all its lanes, so that the serial depth of each role per tile is short) and run as a software
-// pipeline, one barrier per tile (iteration k):
+// pipeline, one named barrier per tile (iteration k):
 //
 //   FIR warps x4 tile k+1   audio (HBM) -> mic-major ring in shared memory (two warps per clip, 32
 //                           samples each)
@@ -19,20 +19,22 @@
 //                           in shared memory) through the other 120 taps: the summation order is
 //                           that of one warp walking all taps
 //   band-pass    tile k-2   one lane per (clip, channel): SOS band-pass recurrence, running sum,
-//                           sign / zero bit masks of every 32-sample segment -> shared memory
+//                           sign bit masks of every 32-sample segment -> shared memory (exact zeros:
+//                           the segment is redone sample by sample)
 //   RZCC         tile k-3   one lane per (clip, channel): the masks are turned into RZCC
 //                           candidates and resolved (find_peaks distance rule) into a bit-packed
 //                           spike ring
 //   neuron       tile k-d   (d = the latency of the exact find_peaks decision) one lane per (clip,
 //                           channel): alpha-kernel neuron recurrences driven by the final spike
-//                           bits -> membrane tile + int8 spike tile in shared memory
-//   Gram         tile k-d-1 C += v v^T of the membrane tile (FFMA2 on 4x4 blocks), int8 spike
-//                           raster of the tile -> HBM
+//                           bits -> membrane tiles (fp16 hi / lo pairs) + int8 spike tile in shared memory
+//   Gram         tile k-d-1 C += V V^T of the membrane tile on the tensor cores (ldmatrix + fp16
+//                           m16n8k16 MMAs on the hi / lo split), int8 spike raster of the tile -> HBM
 //   clip end                power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 //
-// Two CTAs are resident per SM; the FIR roles go to the warps whose SM sub-partition holds the
-// fewest FIR warps so far, so that every sub-partition's FMA pipe always has two FIR warps to
-// keep it busy (one alone leaves it idle whenever it loses an issue slot to another warp).
+// One CTA of sixteen warps per SM holds two such groups (own barrier, own shared memory, own clip pairs): one
+// FIR warp of each group per SM sub-partition.  What bounds the kernel is the issue port of the sub-partitions:
+// an FFMA2 with three register operands issues every ~2.6 cycles, and every instruction of a serial role displaces
+// FIR work (tools/sched_probe.py).  micloc_fused_ffa.cu is the fast-FIR variant of this kernel.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -43,7 +45,7 @@
 namespace micloc {
 
 constexpr int kTile = 64;      // samples per pipeline step
-constexpr int kSlots = 2;      // clips per CTA
+constexpr int kSlots = 2;      // clips per group
 constexpr int kRows = 8;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmRows = 16 * kSlots;    // membrane tile rows: [slot][16 channels] (channels 14, 15 stay zero)
@@ -714,8 +716,8 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         role = s_role[warp];
     } else {
         // warps 0..3: FIR of group 0, 4..7: FIR of group 1 (one per sub-partition each); warps 8..11 / 12..15:
-        // band-pass, RZCC, neuron, Gram of group 0 / 1, rotated by two between the groups so that the two
-        // roles with FMA work (band-pass, Gram) of a sub-partition are of different kinds
+        // band-pass, RZCC, neuron, Gram of group 0 / 1; group 1's order (g.perm) decides which roles share a
+        // sub-partition (default: band-pass + Gram, RZCC + neuron)
         if (warp < 2 * kFirWarps) {
             group = warp >> 2;
             role = warp & 3;
