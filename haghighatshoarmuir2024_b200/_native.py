@@ -86,7 +86,7 @@ class MiclocError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ for sm_100a with nvcc (csrc/Makefile)."""
-    args = ["make", "-C", CSRC] + (["-B"] if force else [])
+    args = ["make", "-j", "6", "-C", CSRC] + (["-B"] if force else [])
     subprocess.run(args, check=True, stdout=None if verbose else subprocess.DEVNULL)
     return LIB_PATH
 
