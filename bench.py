@@ -440,8 +440,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips-per-band", type=int, default=7104,
-                    help="clips per band per step; 7104 = 8 x (148 SMs x 3 CTAs x 2 clips): the fused kernel hands clip pairs "
-                         "to its persistent CTAs dynamically, a step should hold many pairs per CTA")
+                    help="clips per band per step; 7104 = 12 x (148 SMs x 2 groups x 2 clips): the fused kernel hands clip pairs "
+                         "to its persistent warp groups dynamically, a step should hold many pairs per group")
     ap.add_argument("--e2e-clips-per-band", type=int, default=1776, help="clips per band per step of the host-buffer (e2e) leg")
     ap.add_argument("--no-band-streams", dest="band_streams", action="store_false",
                     help="run the three band launches of a step back to back on one stream")
