@@ -113,6 +113,7 @@ k_peak_mixed(float *out, int iters, float a, float b, double da, double db) {
 //   10 scalar FFMA with the FIR operand pattern
 //   12 / 13 FIR pattern with the taps in kernel parameters (uniform registers), tap-major / window-major order
 //   14 FIR pattern, window-major order, taps in registers
+//   15 independent mma.sync m16n8k16 f16 stream (legacy tensor-core path)
 // out[warp] = cycles of CTA 0's warp, out[16 + warp] = instructions of the measured kind it issued.
 // ---------------------------------------------------------------------------
 struct ProbeTaps { float t[64]; };
@@ -399,6 +400,33 @@ k_sched_probe(const int *__restrict__ roles, int iters, float a, float b, unsign
             asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
             res += lo + hi;
         }
+    }
+    else if (role == 15) {
+        // independent legacy tensor-core MMAs (mma.sync m16n8k16 f16, four accumulator sets): what do they cost the
+        // sub-partition's issue port / FMA pipe beside FFMA2 streams?
+        float d[4][4];
+        unsigned ar[4], br[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ar[i] = 0x3c003c00u + (unsigned)lane;        // fp16 pairs near 1.0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+        }
+        br[0] = 0x3c003c00u; br[1] = 0x38003800u;
+        for (int it = 0; probe_running(t0, iters, it); ++it)
+#pragma unroll 1
+        for (int sub = 0; sub < 16; ++sub) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                                 : "r"(ar[0]), "r"(ar[1]), "r"(ar[2]), "r"(ar[3]), "r"(br[0]), "r"(br[1]));
+        }
+        n_inst = 1024ull * (unsigned long long)rounds_done;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res += d[i][0] + d[i][1] + d[i][2] + d[i][3];
     }
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1));
     if (res == 123.456f) sink[0] = res;
