@@ -196,6 +196,33 @@ def test_full_size_clip_config1():
             assert pos.size < 2 or np.diff(pos).min() >= int(g["robust_width"])
 
 
+def test_full_size_config2_three_bands_449_grid():
+    """Config 2 size (bench.py's workload): 1 s clips, three bands, G = 449, 11 SNRs from -10 to 20 dB -- the fused
+    kernel against the oracle on 192 clips per band: spike agreement, DoA match rate, and the DoA histogram kernel."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    import bench as Bn
+    from haghighatshoarmuir2024_b200.montecarlo import BandSetup, SnrSweep
+    d, bands = Bn.load_workload()
+    setups = [BandSetup(band=bands[i], tau=float(d[f"tau_{i}"]), bf_mat=d[f"bf_{i}"]) for i in range(len(bands))]
+    sweep = SnrSweep(setups, d["r_vec"], d["theta_vec"], Bn.FS, float(d["kernel_duration"]), Bn.T_CLIP, device=0)
+    cfgs = Bn.oracle_cfgs(d, bands)
+    n = 192
+    match = total = 0
+    for i in range(len(bands)):
+        x = Bn.host_clips(d, i, bands, n, seed=500 + i)
+        hist = torch.zeros(sweep.G, dtype=torch.int64, device="cuda")
+        out = sweep.run_band(i, to_dev(x), want_spikes=True, want_power=True, hist=hist)
+        torch.cuda.synchronize()
+        ref = O.snn_run_batch(cfgs[i], x, nthreads=8, want_spikes=True)
+        assert H.spike_agreement(out["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE, i
+        doa = out["doa"].cpu().numpy()
+        match += int((doa == ref["doa"]).sum()); total += n
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(doa, minlength=sweep.G)), i
+        assert int(out["flags"].sum()) == 0
+    assert match / total >= DOA_AGREE, f"DoA match rate {match}/{total}"
+
+
 def test_full_size_config4_multi_source_360_grid():
     """Config 4 size: 1 s clips with two simultaneous sources, G = 360, fused kernel vs oracle."""
     g = H.load("snn_c4_multi")
