@@ -25,7 +25,7 @@
 //                           bits -> membrane tile + int8 spike tile in shared memory
 //   Gram+loader  tile k+1   audio (HBM) -> the three sub-sequence rings of every microphone (loads issued at
 //                           the start of the step, stored at its end)
-//                tile k-d-1 C += V V^T of the membrane tile on the tensor cores (TF32 x3 split), int8 spike
+//                tile k-d-1 C += V V^T of the membrane tile on the tensor cores (fp16 hi / lo split), int8 spike
 //                           raster of the tile -> HBM
 //   clip end                power[g] = w_g^T C w_g / T (float64), DoA = first argmax.
 //
@@ -52,6 +52,7 @@
 // whole kernel 153-158k against the default kernel's 172k: its serial roles run slower here (band-pass 9500
 // cycles per tile against 5400) -- larger code (5400 against 4700 instructions: "no instruction" stalls 0.75
 // against 0.13 per issue), more band-pass instructions (ring address arithmetic), conflicted shared-memory loads.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -66,7 +67,8 @@ constexpr int kSlots = 2;      // clips per group
 constexpr int kRows = 7;       // most microphones per clip the lane maps cover
 constexpr int kQPitch = kTile + 4;
 constexpr int kVmRows = 16 * kSlots;    // membrane tile rows: [slot][16 channels] (channels 14, 15 stay zero)
-constexpr int kVmPitch = kTile + 4;     // floats per row of the membrane tile (channel-major: ldmatrix rows of 4 samples)
+constexpr int kVmPitch = kTile + 8;     // halves per row of a membrane tile (channel-major: ldmatrix rows of 8 samples)
+constexpr float kVmScale = 16384.f;     // membrane values are stored x 2^14 (|v| <= 1: the alpha kernel sums to 1) as fp16 hi + lo
 constexpr int kRingWords = 16; // spike-bit ring: 16 words of 32 samples per channel and polarity
 constexpr int kWarps = 8;      // 4 x FIR (tap thirds of the sub-filters), band-pass, RZCC, neuron, Gram + loader
 constexpr int kFirWarps = 4;
@@ -187,7 +189,7 @@ struct FusedSmem {
     float *xs;              // [3: R0, R1, R0+R1][kSlots*M rows][pitch_x] sub-sequence rings
     float *qs;              // [2 tiles][kSlots*M][kQPitch]: finished quadrature tiles
     float *uv;              // [3: U, V, W][kSlots*M][kUvPitch]: sub-filter results of one tile, recombined one step later
-    float *vms;             // [2 tiles][kVmRows][kVmPitch] membrane tiles, channel-major
+    __half *vms;            // [2: hi, lo][2 tiles][kVmRows][kVmPitch] membrane tiles (x 2^14, fp16 split), channel-major
     float *cs;
     unsigned int *seg;      // [2 tiles][kTile/kSeg][3: neg mask, zero mask, carry][32 lanes]: band-pass -> RZCC hand-over
     int *clus;
@@ -574,7 +576,7 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
     const int c_slot = lane >> 4, c_ch = lane & 15;
     const bool c_valid = c_ch < C2 && clip0 + c_slot < B;
     const unsigned int *bits = sm.bits + lane;
-    const float na = p.na, nc = p.nc, ncT = p.ncT, nLf = p.nLf;
+    const float na = p.na, nc = p.nc * kVmScale, ncT = p.ncT * kVmScale, nLf = p.nLf;     // membrane values x 2^14
     const int nL = p.nL;
     NeuronState nr; neuron_reset(nr);
     ROLE_TIMER_DECL;
@@ -584,7 +586,7 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
         const int u0 = j * kTile;
         if (j >= 0 && u0 < T && c_valid) {
             int8_t *stg = sm.stage + ((j & 1) * kSlots + c_slot) * kTile * C2 + c_ch;
-            float *vmo = sm.vms + ((j & 1) * kVmRows + lane) * kVmPitch;
+            __half *vmo = sm.vms + ((j & 1) * kVmRows + lane) * kVmPitch;      // hi tile; the lo tile follows all hi tiles
 #pragma unroll 1
             for (int sg = 0; sg < kSegsPerTile; ++sg) {
                 const int us = u0 + sg * kSeg;
@@ -605,11 +607,11 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                     const unsigned int keep = nvalid <= 0 ? 0u : (0xffffffffu >> (32 - nvalid));
                     P &= keep; Nn &= keep; PD &= keep; ND &= keep;
                 }
-                float *vseg = vmo + sg * kSeg;
+                __half *vseg = vmo + sg * kSeg;
                 int8_t *sseg = stg + sg * kSeg * C2;
 #pragma unroll 1
                 for (int o = 0; o < kSeg / 8; ++o) {
-                    float vq[4];
+                    float vq[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         // neuron_step with s, sd in {-1, 0, +1} given as bits; a (p2 + p1) as a p2 + (a p1): the
@@ -626,15 +628,29 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
                         nr.q1 = b1;
                         const float tail = fmaf(nLf, nr.q1, nr.q2);
                         const float v = fmaf(-ncT, tail, nc * nr.p2);
-                        vq[i & 3] = v;
-                        if ((i & 3) == 3)
-                            *reinterpret_cast<float4 *>(vseg + 8 * o + i - 3) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+                        vq[i] = v;
                         sseg[(8 * o + i) * C2] = (int8_t)(((P >> i) & 1u) - ((Nn >> i) & 1u));
                     }
+                    // v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 22 significant bits for the tensor-core Gram
+                    uint4 h4, l4;
+                    unsigned int *hp = &h4.x, *lp = &l4.x;
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        const __half2 hh = __floats2half2_rn(vq[2 * i2], vq[2 * i2 + 1]);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(vq[2 * i2] - hf.x, vq[2 * i2 + 1] - hf.y);
+                        hp[i2] = *reinterpret_cast<const unsigned int *>(&hh);
+                        lp[i2] = *reinterpret_cast<const unsigned int *>(&ll);
+                    }
+                    *reinterpret_cast<uint4 *>(vseg + 8 * o) = h4;
+                    *reinterpret_cast<uint4 *>(vseg + 2 * kVmRows * kVmPitch + 8 * o) = l4;
                     P >>= 8; Nn >>= 8; PD >>= 8; ND >>= 8;
                 }
                 // the membrane potential behind the clip end does not count (ragged last segment)
-                for (int i = nvalid; i < kSeg; ++i) vseg[i] = 0.f;
+                for (int i = nvalid; i < kSeg; ++i) {
+                    vseg[i] = __float2half(0.f);
+                    vseg[2 * kVmRows * kVmPitch + i] = __float2half(0.f);
+                }
             }
         }
         ROLE_BARRIER();
@@ -643,14 +659,14 @@ __device__ __forceinline__ void neuron_role(const FusedSmem &sm, const ChainPara
 }
 
 // ==== Gram warp: C += V V^T of the membrane tile k - dtile - 1 on the tensor cores, then that tile's int8 spike
-// raster -> HBM.  Per clip slot and 8 time samples: one ldmatrix.x4 fetches the m16n8k8 fragments of
-// V^T (16 channels x 8 samples; the same registers serve as the "col" operand, the matrix is V V^T), every
-// value is split v = hi + lo with hi = v rounded to TF32 (11 significand bits), and
-// C += hi hi^T + hi lo^T + lo hi^T runs as three TF32 MMAs per 8-channel column block: float32-grade products
-// (the dropped lo lo^T is below 2^-22 relative) accumulated in float32 over kGramFlush tiles -- the tensor cores add
-// with truncation, a long chain would bias the sum -- and then folded into float64 registers.  The FMA pipe and ~1000 issue slots per tile stay with the FIR warps.
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+// raster -> HBM.  The neuron warp leaves every membrane value (x 2^14) as an fp16 pair v = hi + lo (22 significant
+// bits).  Per clip slot and 16 time samples one ldmatrix.x4 each fetches the m16n8k16 fragments of hi and lo of
+// V^T (16 channels x 16 samples; the same registers serve as the "col" operand, the matrix is V V^T), and
+// C += hi hi^T + hi lo^T + lo hi^T runs as three fp16 MMAs per 8-channel column block: exact products (the dropped
+// lo lo^T is below 2^-22 relative) accumulated in float32 over kGramFlush tiles -- the tensor cores add with
+// truncation, a long chain would bias the sum -- and then folded into float64 registers.
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -664,7 +680,7 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const ChainParams
     Loader<IN_T, MM> ld;
     ld.init(sm, p, g, audio, clip0, B, T64, lane);
     // ldmatrix row of this lane: matrix lane / 8 = (channels 0-7 | 8-15) x (samples 0-3 | 4-7) of a k-step
-    const int lm_row = (lane & 7) + 8 * ((lane >> 3) & 1), lm_t = 4 * (lane >> 4);
+    const int lm_row = (lane & 7) + 8 * ((lane >> 3) & 1), lm_t = 8 * (lane >> 4);
     float accf[kSlots][2][4];           // float32 partial sums: [slot][column block][m16n8 accumulator fragment]
     double accd[kSlots][2][4];
 #pragma unroll
@@ -684,29 +700,25 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const ChainParams
         const int u0 = j * kTile;
         const bool live = j >= 0 && u0 < T;
         if (live) {
-            const float *vm = sm.vms + ((j & 1) * kVmRows + lm_row) * kVmPitch + lm_t;
+            const __half *vm = sm.vms + ((j & 1) * kVmRows + lm_row) * kVmPitch + lm_t;
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
                 const unsigned addr = (unsigned)__cvta_generic_to_shared(vm + s * 16 * kVmPitch);
-#pragma unroll 2
-                for (int ks = 0; ks < kTile / 8; ++ks) {
-                    unsigned v[4], hi[4], lo[4];
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr + 32u * ks));
+                const unsigned lo_off = 2 * kVmRows * kVmPitch * (unsigned)sizeof(__half);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        // hi = v rounded to nearest TF32 (integer add on the bit pattern: a truncating split would
-                        // bias every product the same way); lo = v - hi is exact, its own truncation is unbiased
-                        hi[i] = (v[i] + 0x1000u) & 0xffffe000u;
-                        lo[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(hi[i]));
-                    }
+                for (int ks = 0; ks < kTile / 16; ++ks) {
+                    unsigned hi[4], lo[4];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]) : "r"(addr + 32u * ks));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]) : "r"(addr + lo_off + 32u * ks));
                     // column block 0 = channels 0-7: its k x n fragment is (a0, a2); block 1 = channels 8-15: (a1, a3)
-                    mma_tf32_16x8x8(accf[s][0], hi, hi[0], hi[2]);
-                    mma_tf32_16x8x8(accf[s][1], hi, hi[1], hi[3]);
-                    mma_tf32_16x8x8(accf[s][0], hi, lo[0], lo[2]);
-                    mma_tf32_16x8x8(accf[s][1], hi, lo[1], lo[3]);
-                    mma_tf32_16x8x8(accf[s][0], lo, hi[0], hi[2]);
-                    mma_tf32_16x8x8(accf[s][1], lo, hi[1], hi[3]);
+                    mma_f16_16x8x16(accf[s][0], hi, hi[0], hi[2]);
+                    mma_f16_16x8x16(accf[s][1], hi, hi[1], hi[3]);
+                    mma_f16_16x8x16(accf[s][0], hi, lo[0], lo[2]);
+                    mma_f16_16x8x16(accf[s][1], hi, lo[1], lo[3]);
+                    mma_f16_16x8x16(accf[s][0], lo, hi[0], hi[2]);
+                    mma_f16_16x8x16(accf[s][1], lo, hi[1], hi[3]);
                 }
             }
             if ((j % kGramFlush) == kGramFlush - 1 || (j + 1) * kTile >= T) {
@@ -748,7 +760,7 @@ __device__ __forceinline__ void gram_role(const FusedSmem &sm, const ChainParams
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = (lane >> 2) + 8 * (i >> 1), col = 8 * nb + 2 * (lane & 3) + (i & 1);
-                sm.gram[s * 256 + row * 16 + col] = accd[s][nb][i];
+                sm.gram[s * 256 + row * 16 + col] = accd[s][nb][i] * (1.0 / ((double)kVmScale * (double)kVmScale));
             }
 }
 
@@ -807,7 +819,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.xs = reinterpret_cast<float *>(smem_raw + g.off_x);
     sm.qs = reinterpret_cast<float *>(smem_raw + g.off_q);
     sm.uv = reinterpret_cast<float *>(smem_raw + g.off_uv);
-    sm.vms = reinterpret_cast<float *>(smem_raw + g.off_vm);
+    sm.vms = reinterpret_cast<__half *>(smem_raw + g.off_vm);
     sm.cs = reinterpret_cast<float *>(smem_raw + g.off_cs);      // [2][kSegsPerTile][kSeg][32] running sums
     sm.seg = reinterpret_cast<unsigned int *>(smem_raw + g.off_seg);     // [2][kSegsPerTile][3][32]
     sm.clus = reinterpret_cast<int *>(smem_raw + g.off_clus);    // RZCC cluster buffers, interleaved over 32 lanes
@@ -849,7 +861,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
             for (int i = tid; i < 3 * kSlots * M * kUvPitch; i += kThreads) sm.uv[i] = 0.f;    // V[-1] = 0
             // no spikes before the clip start; membrane columns of unused lanes stay zero
             for (int i = tid; i < 2 * kRingWords * 32; i += kThreads) sm.bits[i] = 0u;
-            for (int i = tid; i < 2 * kVmRows * kVmPitch; i += kThreads) sm.vms[i] = 0.f;
+            for (int i = tid; i < 2 * 2 * kVmRows * kVmPitch / 2; i += kThreads) reinterpret_cast<unsigned int *>(sm.vms)[i] = 0u;
         }
         group_sync();
 
@@ -992,7 +1004,7 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     g.off_x = off; off += rows * 3 * g.pitch_x * (int)sizeof(float);
     g.off_q = off; off += 2 * rows * kQPitch * (int)sizeof(float);
     g.off_uv = off; off += 3 * rows * kUvPitch * (int)sizeof(float);
-    g.off_vm = off; off += 2 * kVmRows * kVmPitch * (int)sizeof(float);
+    g.off_vm = off; off += 2 * 2 * kVmRows * kVmPitch * (int)sizeof(__half);
     g.off_cs = off; off += 2 * kSegsPerTile * kSeg * 32 * (int)sizeof(float);
     g.off_seg = off; off += 2 * kSegsPerTile * 3 * 32 * (int)sizeof(int);
     g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
