@@ -50,8 +50,11 @@ struct micloc_snn {
     float *d_sos = nullptr;        // [1][kMaxSections][5]
     float *d_W = nullptr;          // [C2][G] f32
     double *d_Wd = nullptr;        // [C2][G] f64
-    unsigned int *d_sm_slots = nullptr;  // [2][kSlotWords]: per-SM CTA arrival counters + clip-pair counter of the fused
-                                         // kernel (+ debug counters); one set per concurrently running launch
+    unsigned int *d_sm_slots = nullptr;  // [3][kSlotWords]: per-SM CTA arrival counters + clip-pair counter of the fused
+                                         // kernel (+ debug counters); one set per concurrently running launch: set 0 for
+                                         // micloc_snn_run on the caller's stream, sets 1 and 2 for run_host's two streams
+    cudaEvent_t ev_last = nullptr;       // recorded behind the last launch of micloc_snn_run / run_taps / gram: run_host's
+                                         // private streams wait for it before they touch the shared scratch
     DevBuf q, spikes, vmem, gram, flags, part;
     // host staging for run_host
     DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
@@ -156,8 +159,9 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
     }
     rc = upload_bf(c, cfg->bf_mat, cfg->num_doa);
     if (rc) { micloc_snn_destroy(c); return rc; }
-    if (cudaMalloc(&c->d_sm_slots, 2 * kSlotWords * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(c->d_sm_slots, 0, 2 * kSlotWords * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&c->d_sm_slots, 3 * kSlotWords * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->d_sm_slots, 0, 3 * kSlotWords * sizeof(unsigned int)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming) != cudaSuccess) {
         micloc_snn_destroy(c);
         return set_error(MICLOC_ERR_CUDA, "cudaMalloc(sm_slots) failed");
     }
@@ -176,6 +180,7 @@ extern "C" int micloc_snn_destroy(micloc_snn *c) {
         if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
     }
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     delete c;
     return MICLOC_OK;
 }
@@ -350,6 +355,7 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
     }
     MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
+    MICLOC_CUDA(cudaEventRecord(c->ev_last, st));
     return MICLOC_OK;
 }
 
@@ -375,6 +381,7 @@ extern "C" int micloc_snn_gram(micloc_snn *c, const void *audio, int dtype, int6
     k_gram<<<gg, 256, 0, st>>>((const float *)c->vmem.ptr, gram_dev, p.C2, T, t_start);
     count_launch(2);
     MICLOC_CUDA(cudaGetLastError());
+    MICLOC_CUDA(cudaEventRecord(c->ev_last, st));
     return MICLOC_OK;
 }
 
@@ -398,6 +405,7 @@ static int snn_run_impl(micloc_snn *c, const void *audio, int dtype, int64_t B, 
                             c->d_sm_slots + (size_t)slot_set * kSlotWords, c->sm_count, st));
     MICLOC_TRY(timing_mark(c, st));
     c->last_kernels = (int)(g_launches.load() - l0);
+    if (slot_set == 0) MICLOC_CUDA(cudaEventRecord(c->ev_last, st));
     return MICLOC_OK;
 }
 
@@ -434,6 +442,9 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
         MICLOC_TRY(c->h_doa[i].reserve((size_t)chunk * sizeof(int32_t)));
         MICLOC_TRY(c->h_flg[i].reserve((size_t)chunk * sizeof(int32_t)));
     }
+    // whatever micloc_snn_run / run_taps / gram left running on the caller's stream owns the context scratch until it
+    // is done: both private streams wait for it
+    for (int i = 0; i < 2; ++i) MICLOC_CUDA(cudaStreamWaitEvent(c->hs[i], c->ev_last, 0));
     // the staged path shares one scratch set, so its chunks are serialised on stream 0
     int slot = 0;
     for (long long b0 = 0; b0 < B; b0 += chunk, slot ^= fused ? 1 : 0) {
@@ -444,7 +455,7 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
         int8_t *d_spk = spikes_host ? (int8_t *)c->h_spk[slot].ptr : nullptr;
         float *d_pow = power_host ? (float *)c->h_pow[slot].ptr : nullptr;
         int rc = snn_run_impl(c, c->h_audio[slot].ptr, dtype, nb, T, d_spk, d_pow, (int32_t *)c->h_doa[slot].ptr,
-                              (int32_t *)c->h_flg[slot].ptr, fused, st, slot);
+                              (int32_t *)c->h_flg[slot].ptr, fused, st, 1 + slot);
         if (rc) return rc;
         if (spikes_host)
             MICLOC_CUDA(cudaMemcpyAsync(spikes_host + (size_t)b0 * clip_spk, d_spk, (size_t)nb * clip_spk,

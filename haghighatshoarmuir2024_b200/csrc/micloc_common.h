@@ -65,12 +65,12 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
                  unsigned int *sm_slots, int sm_count, cudaStream_t st);
 bool fused_supported(const ChainParams &p);
-// fast-FIR variant of the fused kernel (micloc_fused_ffa.cu), selected with MICLOC_FUSED_FIR=ffa
-namespace ffa {
+// tensor-core variant (micloc_fused_tc.cu): STHT as a tcgen05 Toeplitz GEMM; the default where it applies
+namespace tc {
 int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
                  unsigned int *sm_slots, int sm_count, cudaStream_t st);
 bool fused_supported(const ChainParams &p);
-}  // namespace ffa
+}  // namespace tc
 
 }  // namespace micloc

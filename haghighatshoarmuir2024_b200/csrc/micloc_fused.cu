@@ -34,7 +34,7 @@
 // One CTA of sixteen warps per SM holds two such groups (own barrier, own shared memory, own clip pairs): one
 // FIR warp of each group per SM sub-partition.  What bounds the kernel is the issue port of the sub-partitions:
 // an FFMA2 with three register operands issues every ~2.6 cycles, and every instruction of a serial role displaces
-// FIR work (tools/sched_probe.py).  micloc_fused_ffa.cu is the fast-FIR variant of this kernel.
+// FIR work (tools/sched_probe.py).  micloc_fused_tc.cu (the default) runs the FIR on the tensor cores instead.
 #include <cstdlib>
 
 #include "micloc_fused_common.cuh"
@@ -111,6 +111,7 @@ struct FusedSmem {
     double *gram;           // [kSlots][16][16], clip epilogue only (reuses the audio rings)
     unsigned int *dbg;      // sm_slots (debug counters behind the first 256 entries)
     int bar_id;             // named barrier of this clip-pair group
+    int bar_threads;        // threads meeting at it
     int rec;                // index of this group's debug record (MICLOC_ROLE_TIMING builds)
 };
 
@@ -173,8 +174,13 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
                 const float *tp = sm.taps + 8 * half * nb2;
                 Taps8 t0, t1;
                 load_taps(t0, tp);
+#ifdef MICLOC_DEBUG_SWITCHES
+                const int nb_run = g.fir_blocks ? g.fir_blocks : nb2;
+#else
+                const int nb_run = nb2;
+#endif
 #pragma unroll 1
-                for (int jb = 0; jb < (g.fir_blocks ? g.fir_blocks : nb2); jb += 3) {
+                for (int jb = 0; jb < nb_run; jb += 3) {
                     load_chunk(Cq, row, cn); cn -= 16; if (cn < 0) cn += g.ring_x;
                     load_taps(t1, tp + 8);
                     fir_block(acc, A, Bq, t0);
@@ -333,97 +339,6 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
     ROLE_TIMER_FLUSH(kRoleBandpass);
 }
 
-// ==== Gram warp: C += V V^T of the membrane tile k - dtile - 1 on the tensor cores, then that tile's int8 spike
-// raster -> HBM.  The neuron warp leaves every membrane value (x 2^14) as an fp16 pair v = hi + lo (22 significant
-// bits).  Per clip slot and 16 time samples one ldmatrix.x4 each fetches the m16n8k16 fragments of hi and lo of
-// V^T (16 channels x 16 samples; the same registers serve as the "col" operand, the matrix is V V^T), and
-// C += hi hi^T + hi lo^T + lo hi^T runs as three fp16 MMAs per 8-channel column block: exact products (the dropped
-// lo lo^T is below 2^-22 relative) accumulated in float32 over kGramFlush tiles -- the tensor cores add with
-// truncation, a long chain would bias the sum -- and then folded into float64 registers.
-__device__ __forceinline__ void gram_role(const FusedSmem &sm, const FusedGeom &g, int8_t *__restrict__ spikes,
-                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
-    const int C2 = 2 * MMv;
-    const int T = (int)T64;
-    // ldmatrix row of this lane: matrix lane / 8 = (channels 0-7 | 8-15) x (samples 0-7 | 8-15) of a k-step
-    const int lm_row = (lane & 7) + 8 * ((lane >> 3) & 1), lm_t = 8 * (lane >> 4);
-    float accf[kSlots][2][4];           // float32 partial sums: [slot][column block][m16n8 accumulator fragment]
-    double accd[kSlots][2][4];
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s)
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { accf[s][nb][i] = 0.f; accd[s][nb][i] = 0.0; }
-    ROLE_TIMER_DECL;
-
-    for (int k = -1; k <= k_last; ++k) {
-        const int j = k - g.dtile - 1;
-        const int u0 = j * kTile;
-        const bool live = j >= 0 && u0 < T;
-        if (live) {
-            const __half *vm = sm.vms + ((j & 1) * kVmRows + lm_row) * kVmPitch + lm_t;
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                const unsigned addr = (unsigned)__cvta_generic_to_shared(vm + s * 16 * kVmPitch);
-                const unsigned lo_off = 2 * kVmRows * kVmPitch * (unsigned)sizeof(__half);
-#pragma unroll
-                for (int ks = 0; ks < kTile / 16; ++ks) {
-                    unsigned hi[4], lo[4];
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]) : "r"(addr + 32u * ks));
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]) : "r"(addr + lo_off + 32u * ks));
-                    // column block 0 = channels 0-7: its k x n fragment is (a0, a2); block 1 = channels 8-15: (a1, a3)
-                    mma_f16_16x8x16(accf[s][0], hi, hi[0], hi[2]);
-                    mma_f16_16x8x16(accf[s][1], hi, hi[1], hi[3]);
-                    mma_f16_16x8x16(accf[s][0], hi, lo[0], lo[2]);
-                    mma_f16_16x8x16(accf[s][1], hi, lo[1], lo[3]);
-                    mma_f16_16x8x16(accf[s][0], lo, hi[0], hi[2]);
-                    mma_f16_16x8x16(accf[s][1], lo, hi[1], hi[3]);
-                }
-            }
-            if ((j % kGramFlush) == kGramFlush - 1 || (j + 1) * kTile >= T) {
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s)
-#pragma unroll
-                    for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { accd[s][nb][i] += (double)accf[s][nb][i]; accf[s][nb][i] = 0.f; }
-            }
-        }
-        // int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
-        if (live && spikes) {
-            const int nrow = T - u0 < kTile ? T - u0 : kTile;
-            for (int s = 0; s < kSlots; ++s) {
-                if (clip0 + s >= B) continue;
-                const int8_t *src = sm.stage + ((j & 1) * kSlots + s) * kTile * C2;
-                int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
-                const int nbytes = nrow * C2;
-                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0 &&
-                    ((kTile * C2) & 15) == 0) {
-                    for (int v = lane; v < nbytes / 16; v += 32)
-                        reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
-                } else {
-                    for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
-                }
-            }
-        }
-        ROLE_BARRIER();
-    }
-    ROLE_TIMER_FLUSH(kRoleGram);
-    // the Gram matrices of the two clips -> shared memory for the clip epilogue (the audio rings are dead now):
-    // accumulator fragment (m16n8): c0, c1 = row lane/4, columns 2 (lane%4) + {0, 1}; c2, c3 = row lane/4 + 8
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s)
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = (lane >> 2) + 8 * (i >> 1), col = 8 * nb + 2 * (lane & 3) + (i & 1);
-                sm.gram[s * 256 + row * 16 + col] = accd[s][nb][i] * (1.0 / ((double)kVmScale * (double)kVmScale));
-            }
-}
-
 // GROUPS = 1: a CTA is one clip-pair group of eight warps, two CTAs per SM, FIR roles placed per SM
 //             sub-partition at run time (hardware warp slots of a second CTA are not known in advance).
 // GROUPS = 2: ONE CTA of sixteen warps per SM holding two independent clip-pair groups (own named barrier,
@@ -530,6 +445,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.gram = reinterpret_cast<double *>(smem_raw + g.off_x);    // [kSlots][16][16], clip epilogue only
     sm.dbg = sm_slots;
     sm.bar_id = bar_id;
+    sm.bar_threads = kThreads;
     sm.rec = GROUPS * (int)blockIdx.x + group;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_cs);     // [kThreads], clip epilogue only (reuses the running sums)
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_cs + kThreads * sizeof(double));
@@ -559,15 +475,18 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
         }
         group_sync();
 
+#ifdef MICLOC_DEBUG_SWITCHES
         if ((g.skip >> role) & 1) {
             for (int k = -1; k <= k_last; ++k) tile_barrier(bar_id);
-        } else if (role < kFirWarps)
+        } else
+#endif
+        if (role < kFirWarps)
             fir_role<IN_T, MM>(sm, p, g, audio, clip0 + (role >> 1), clip0 + (role >> 1) < B, T, role >> 1, role & 1, lane,
                                NT, k_last);
         else if (role == kRoleBandpass) bandpass_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, k_last);
         else if (role == kRoleRzcc) rzcc_role<FusedSmem, kRingWords>(sm, p, flags, clip0, B, T, M, lane, k_last);
         else if (role == kRoleNeuron) neuron_role<FusedSmem, FusedGeom, kRingWords>(sm, p, g, clip0, B, T, M, lane, k_last);
-        else gram_role(sm, g, spikes, clip0, B, T, M, lane, k_last);
+        else gram_role<FusedSmem, FusedGeom>(sm, g, spikes, clip0, B, T, M, lane, k_last);
         group_sync();
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
         // one DoA column per thread and pass: its 2M weights are fetched first (independent loads, one
@@ -667,18 +586,25 @@ static int launch_fused_t(const ChainParams &p, const FusedGeom &g, const float 
 int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, const void *audio, int dtype,
                  long long B, long long T, int8_t *spikes, float *power, int32_t *doa, int32_t *flags,
                  unsigned int *sm_slots, int sm_count, cudaStream_t st) {
-    // A/B switch: the fast-FIR variant (three half-length sub-filters, micloc_fused_ffa.cu) executes a quarter
-    // fewer multiply-adds but balances worse over the four sub-partitions; measured 4 % slower
-    if (const char *e = getenv("MICLOC_FUSED_FIR"))
-        if (e[0] == 'f' && ffa::fused_supported(p))
-            return ffa::launch_fused(p, d_taps, d_Wd, audio, dtype, B, T, spikes, power, doa, flags, sm_slots, sm_count, st);
+    // default: the tensor-core kernel (micloc_fused_tc.cu) wherever its geometry applies; this FFMA kernel covers
+    // the rest (long STHT kernels that do not fit its rings) and stays selectable with MICLOC_FUSED_FIR=ffma
+    {
+        const char *e = getenv("MICLOC_FUSED_FIR");
+        const bool want_ffma = e && e[0] == 'f';        // "ffma": force this kernel (A/B measurements)
+        if (!want_ffma && tc::fused_supported(p)) {
+            const int rc = tc::launch_fused(p, d_taps, d_Wd, audio, dtype, B, T, spikes, power, doa, flags, sm_slots, sm_count, st);
+            if (rc != MICLOC_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (!fused_supported(p))
         return set_error(MICLOC_ERR_UNSUPPORTED,
                          "fused kernel covers Hilbert-type STHT kernels (every other tap zero), a 2-section band-pass "
                          "and up to %d microphones; use the staged path", kRows);
     FusedGeom g{};
-    if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);   // role ablation, debugging only
+#ifdef MICLOC_DEBUG_SWITCHES   // role ablation (tools/build_rt.sh builds only): these make the results garbage
+    if (const char *e = getenv("MICLOC_FUSED_SKIP")) g.skip = (int)strtol(e, nullptr, 0);
     if (const char *e = getenv("MICLOC_FUSED_FIRBLOCKS")) g.fir_blocks = (int)strtol(e, nullptr, 0);
+#endif
     {
         // group 0 runs band-pass, RZCC, neuron, Gram on sub-partitions 0..3; group 1's order decides which roles share one
         static const int perms[3][4] = {{3, 2, 1, 0}, {2, 3, 0, 1}, {1, 0, 3, 2}};

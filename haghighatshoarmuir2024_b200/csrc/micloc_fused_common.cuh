@@ -1,5 +1,5 @@
-// micloc_fused_common.cuh -- what the two fused kernels (micloc_fused.cu: direct-form STHT, micloc_fused_ffa.cu:
-// fast-FIR STHT) share: tile geometry, packed-FMA helpers, the per-tile barrier and the optional role timers, the
+// micloc_fused_common.cuh -- what the two fused kernels (micloc_fused_tc.cu: STHT on the tensor cores, the default;
+// micloc_fused.cu: STHT on the FP32 FMA pipe) share: tile geometry, packed-FMA helpers, the per-tile barrier and the optional role timers, the
 // band-pass biquad pair, the RZCC and neuron warp roles and the tensor-core MMA of the Gram warp.
 //
 // Reference sites: micloc/snn_beamformer.py:283-370 (see the kernels' own headers).
@@ -38,7 +38,11 @@ __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long lon
 
 // The eight warps of one clip-pair group meet here once per pipeline step (the roles run different code);
 // every group of a CTA owns one named barrier.
-__device__ __forceinline__ void tile_barrier(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+__device__ __forceinline__ void tile_barrier(int id, int nthreads = kThreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Called by every serial role at the top of pipeline step k, before its own work: the tensor-core kernel
+// (micloc_fused_tc.cu) moves the finished STHT tile out of tensor memory there; the FFMA kernel passes this no-op.
+struct NoStepHook { __device__ __forceinline__ void operator()(int) const {} };
 
 // Optional role timing (MICLOC_ROLE_TIMING): busy cycles of each warp role between barriers, summed into
 // the 64-bit counters at sm_slots[kSlotDbg] (busy of roles 0..7, then the number of warps that reported
@@ -70,12 +74,22 @@ struct RoleTimer {
         }
     }
 };
+// phase timers inside a role: cycles summed into debug counters 18 + i (i < 14), read back by micloc_snn_debug_counters
+#define PH_DECL long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pht_ = 0
+#define PH_START() pht_ = rt_clock()
+#define PH_END(i) do { const long long n_ = rt_clock(); ph_[i] += n_ - pht_; pht_ = n_; } while (0)
+#define PH_FLUSH(dbg, base, n) do { if (lane == 0) for (int i_ = 0; i_ < (n); ++i_) \
+        atomicAdd(reinterpret_cast<unsigned long long *>((dbg) + kSlotDbg) + 18 + (base) + i_, (unsigned long long)ph_[i_]); } while (0)
 #define ROLE_TIMER_DECL RoleTimer rt_; rt_.start()
-#define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(sm.bar_id); rt_.after_barrier(); } while (0)
+#define ROLE_BARRIER() do { rt_.before_barrier(); tile_barrier(sm.bar_id, sm.bar_threads); rt_.after_barrier(); } while (0)
 #define ROLE_TIMER_FLUSH(role) rt_.flush(sm.dbg, role, lane, sm.rec)
 #else
+#define PH_DECL
+#define PH_START()
+#define PH_END(i)
+#define PH_FLUSH(dbg, base, n)
 #define ROLE_TIMER_DECL
-#define ROLE_BARRIER() tile_barrier(sm.bar_id)
+#define ROLE_BARRIER() tile_barrier(sm.bar_id, sm.bar_threads)
 #define ROLE_TIMER_FLUSH(role)
 #endif
 
@@ -93,9 +107,10 @@ __device__ __forceinline__ float biquad2_step(const Sos2 &c, BiquadState &st, fl
 }
 
 // ============ RZCC warp: masks of tile k-2 -> candidates -> clusters -> spike bits, lane = slot*16 + channel ============
-template <typename SMEM, int kRingWords>
+template <typename SMEM, int kRingWords, typename HOOK = NoStepHook>
 __device__ __forceinline__ void rzcc_role(const SMEM &sm, const ChainParams &p, int32_t *__restrict__ flags,
-                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
+                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last,
+                                          HOOK hook = HOOK()) {
     const int C2 = 2 * MMv;
     const int T = (int)T64;
     const int c_slot = lane >> 4, c_ch = lane & 15;
@@ -112,6 +127,7 @@ __device__ __forceinline__ void rzcc_role(const SMEM &sm, const ChainParams &p, 
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
+        hook(k);
         const int kr = k - 3;
         const int t0 = kr * kTile;
         if (kr >= 0 && t0 < T && c_valid) {
@@ -139,9 +155,10 @@ __device__ __forceinline__ void rzcc_role(const SMEM &sm, const ChainParams &p, 
 }
 
 // ==== neuron warp: alpha-kernel recurrences of tile k - dtile -> membrane tile + int8 spike tile, lane = slot*16 + channel ====
-template <typename SMEM, typename GEOM, int kRingWords>
+template <typename SMEM, typename GEOM, int kRingWords, typename HOOK = NoStepHook>
 __device__ __forceinline__ void neuron_role(const SMEM &sm, const ChainParams &p, const GEOM &g,
-                                            long long clip0, long long B, long long T64, int MMv, int lane, int k_last) {
+                                            long long clip0, long long B, long long T64, int MMv, int lane, int k_last,
+                                            HOOK hook = HOOK()) {
     const int C2 = 2 * MMv;
     const int T = (int)T64;
     const int c_slot = lane >> 4, c_ch = lane & 15;
@@ -153,6 +170,7 @@ __device__ __forceinline__ void neuron_role(const SMEM &sm, const ChainParams &p
     ROLE_TIMER_DECL;
 
     for (int k = -1; k <= k_last; ++k) {
+        hook(k);
         const int j = k - g.dtile;
         const int u0 = j * kTile;
         if (j >= 0 && u0 < T && c_valid) {
@@ -234,5 +252,100 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const unsigned (&
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+
+// ==== Gram warp: C += V V^T of the membrane tile k - dtile - 1 on the tensor cores, then that tile's int8 spike
+// raster -> HBM.  The neuron warp leaves every membrane value (x 2^14) as an fp16 pair v = hi + lo (22 significant
+// bits).  Per clip slot and 16 time samples one ldmatrix.x4 each fetches the m16n8k16 fragments of hi and lo of
+// V^T (16 channels x 16 samples; the same registers serve as the "col" operand, the matrix is V V^T), and
+// C += hi hi^T + hi lo^T + lo hi^T runs as three fp16 MMAs per 8-channel column block: exact products (the dropped
+// lo lo^T is below 2^-22 relative) accumulated in float32 over kGramFlush tiles -- the tensor cores add with
+// truncation, a long chain would bias the sum -- and then folded into float64 registers.
+template <typename SMEM, typename GEOM, typename HOOK = NoStepHook>
+__device__ __forceinline__ void gram_role(const SMEM &sm, const GEOM &g, int8_t *__restrict__ spikes,
+                                          long long clip0, long long B, long long T64, int MMv, int lane, int k_last,
+                                          HOOK hook = HOOK()) {
+    const int C2 = 2 * MMv;
+    const int T = (int)T64;
+    // ldmatrix row of this lane: matrix lane / 8 = (channels 0-7 | 8-15) x (samples 0-7 | 8-15) of a k-step
+    const int lm_row = (lane & 7) + 8 * ((lane >> 3) & 1), lm_t = 8 * (lane >> 4);
+    float accf[kSlots][2][4];           // float32 partial sums: [slot][column block][m16n8 accumulator fragment]
+    double accd[kSlots][2][4];
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { accf[s][nb][i] = 0.f; accd[s][nb][i] = 0.0; }
+    ROLE_TIMER_DECL;
+
+    for (int k = -1; k <= k_last; ++k) {
+        hook(k);
+        const int j = k - g.dtile - 1;
+        const int u0 = j * kTile;
+        const bool live = j >= 0 && u0 < T;
+        if (live) {
+            const __half *vm = sm.vms + ((j & 1) * kVmRows + lm_row) * kVmPitch + lm_t;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const unsigned addr = (unsigned)__cvta_generic_to_shared(vm + s * 16 * kVmPitch);
+                const unsigned lo_off = 2 * kVmRows * kVmPitch * (unsigned)sizeof(__half);
+#pragma unroll
+                for (int ks = 0; ks < kTile / 16; ++ks) {
+                    unsigned hi[4], lo[4];
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]) : "r"(addr + 32u * ks));
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]) : "r"(addr + lo_off + 32u * ks));
+                    // column block 0 = channels 0-7: its k x n fragment is (a0, a2); block 1 = channels 8-15: (a1, a3)
+                    mma_f16_16x8x16(accf[s][0], hi, hi[0], hi[2]);
+                    mma_f16_16x8x16(accf[s][1], hi, hi[1], hi[3]);
+                    mma_f16_16x8x16(accf[s][0], hi, lo[0], lo[2]);
+                    mma_f16_16x8x16(accf[s][1], hi, lo[1], lo[3]);
+                    mma_f16_16x8x16(accf[s][0], lo, hi[0], hi[2]);
+                    mma_f16_16x8x16(accf[s][1], lo, hi[1], hi[3]);
+                }
+            }
+            if ((j % kGramFlush) == kGramFlush - 1 || (j + 1) * kTile >= T) {
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s)
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { accd[s][nb][i] += (double)accf[s][nb][i]; accf[s][nb][i] = 0.f; }
+            }
+        }
+        // int8 spike raster of the tile -> HBM (contiguous [kTile][C2] in both places)
+        if (live && spikes) {
+            const int nrow = T - u0 < kTile ? T - u0 : kTile;
+            for (int s = 0; s < kSlots; ++s) {
+                if (clip0 + s >= B) continue;
+                const int8_t *src = sm.stage + ((j & 1) * kSlots + s) * kTile * C2;
+                int8_t *dst = spikes + ((clip0 + s) * T64 + u0) * C2;
+                const int nbytes = nrow * C2;
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0 &&
+                    ((kTile * C2) & 15) == 0) {
+                    for (int v = lane; v < nbytes / 16; v += 32)
+                        reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
+                } else {
+                    for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
+                }
+            }
+        }
+        ROLE_BARRIER();
+    }
+    ROLE_TIMER_FLUSH(kRoleGram);
+    // the Gram matrices of the two clips -> shared memory for the clip epilogue (the audio rings are dead now):
+    // accumulator fragment (m16n8): c0, c1 = row lane/4, columns 2 (lane%4) + {0, 1}; c2, c3 = row lane/4 + 8
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = (lane >> 2) + 8 * (i >> 1), col = 8 * nb + 2 * (lane & 3) + (i & 1);
+                sm.gram[s * 256 + row * 16 + col] = accd[s][nb][i] * (1.0 / ((double)kVmScale * (double)kVmScale));
+            }
+}
+
 
 }  // namespace micloc

@@ -43,11 +43,13 @@ def neuron_alpha_params(time_vec: np.ndarray, tau_vec: Sequence[float]):
     0.999.  Returned closed form: h[n] = c * n * a^n for n < L."""
     tau_syn, tau_mem = float(tau_vec[0]), float(tau_vec[1])
     tn = np.asarray(time_vec, dtype=np.float64) - time_vec[0]
-    if tau_mem == tau_syn:
-        h = (tn / tau_syn) * np.exp(-tn / tau_syn)
-    else:
-        h = (np.exp(-tn / tau_syn) - np.exp(tn / tau_mem)) / (1 / tau_mem - 1 / tau_syn)
-        assert np.all(h >= 0)
+    if tau_mem != tau_syn:
+        # The reference's kernel for unequal time constants, (exp(-t/tau_syn) - exp(+t/tau_mem)) / (1/tau_mem - 1/tau_syn)
+        # (snn_beamformer.py:349-353), grows without bound and trips its own `assert np.all(h >= 0)`; the device
+        # recurrence implements the alpha kernel c n a^n of the tau_syn == tau_mem branch only.
+        raise ValueError("tau_syn != tau_mem is not supported: the device neuron filter is the alpha kernel of "
+                         "tau_syn == tau_mem (the reference's unequal-tau kernel fails its own assertion)")
+    h = (tn / tau_syn) * np.exp(-tn / tau_syn)
     total = np.sum(h)
     h = h / total
     L = int(np.sum(np.cumsum(h) < 0.999))
@@ -86,6 +88,7 @@ class SnnEngine:
         N.check(self._lib.micloc_snn_create(C.byref(cfg), device, C.byref(h)))
         self._h = h
         self.M, self.C2, self.G = spec.num_mic, 2 * spec.num_mic, bf.shape[1]
+        self._fused_unsupported = False
 
     def close(self):
         if getattr(self, "_h", None):
@@ -102,7 +105,7 @@ class SnnEngine:
         self.G = bf.shape[1]
 
     # ------------------------------------------------------------------
-    def _check_audio(self, audio: torch.Tensor):
+    def _check_audio(self, audio: torch.Tensor, check_device: bool = True):
         if audio.dim() == 2:
             audio = audio.unsqueeze(0)
         if audio.dim() != 3 or audio.shape[2] != self.M:
@@ -114,22 +117,30 @@ class SnnEngine:
             dt = N.I16
         else:
             raise ValueError(f"audio must be float32 or int16, got {audio.dtype}")
+        if check_device and audio.device != self.device:
+            raise ValueError(f"audio lives on {audio.device}, engine on {self.device}")
         return audio.contiguous(), dt
 
     def run(self, audio: torch.Tensor, want_spikes: bool = False, want_power: bool = True,
             fused: bool = True) -> Dict[str, torch.Tensor]:
         """audio [B,T,M] on this engine's GPU -> {'doa','power','spikes','flags'} (device tensors)."""
         audio, dt = self._check_audio(audio)
-        if audio.device != self.device:
-            raise ValueError(f"audio lives on {audio.device}, engine on {self.device}")
         B, T, _ = audio.shape
         dev = self.device
         doa = torch.empty(B, dtype=torch.int32, device=dev)
         flags = torch.empty(B, dtype=torch.int32, device=dev)
         power = torch.empty((B, self.G), dtype=torch.float32, device=dev) if want_power else None
         spikes = torch.empty((B, T, self.C2), dtype=torch.int8, device=dev) if want_spikes else None
-        N.check(self._lib.micloc_snn_run(self._h, _ptr(audio), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
-                                         _ptr(flags), int(fused), _stream_ptr(dev)))
+        fused = bool(fused) and not self._fused_unsupported
+        rc = self._lib.micloc_snn_run(self._h, _ptr(audio), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
+                                      _ptr(flags), int(fused), _stream_ptr(dev))
+        if rc == N.ERR_UNSUPPORTED and fused:
+            # geometries the fused kernels do not cover (more than 8 microphones, dense STHT kernels, ...) take the
+            # tiled / staged kernels; remembered per engine
+            self._fused_unsupported = True
+            rc = self._lib.micloc_snn_run(self._h, _ptr(audio), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
+                                          _ptr(flags), 0, _stream_ptr(dev))
+        N.check(rc)
         return {"doa": doa, "power": power, "spikes": spikes, "flags": flags}
 
     def run_taps(self, audio: torch.Tensor, want: Sequence[str] = ("q", "z", "spikes", "vmem", "y", "power", "doa")):
@@ -167,7 +178,7 @@ class SnnEngine:
         t = torch.as_tensor(audio)
         if t.is_cuda:
             raise ValueError("run_host takes host memory; use run() for device tensors")
-        t, dt = self._check_audio(t)
+        t, dt = self._check_audio(t, check_device=False)
         B, T, _ = t.shape
         pin = t.is_pinned()
         mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=pin)

@@ -7,6 +7,7 @@ Monte-Carlo driver should use (audio in, DoA indices out, nothing dense).
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from numbers import Number
 from typing import Dict, Tuple, Union
 
@@ -49,7 +50,8 @@ class SNNBeamformer:
                                                     device=device)
         self.device = device
         self.verbose = True
-        self._engines: Dict[tuple, SnnEngine] = {}
+        self._engines: "OrderedDict[tuple, SnnEngine]" = OrderedDict()
+        self.max_engines = 4          # contexts kept alive (one per clip length / encoder setting), least recently used first out
 
     # ------------------------------------------------------------------
     def chain_spec(self, time_vec: np.ndarray) -> ChainSpec:
@@ -63,17 +65,30 @@ class SNNBeamformer:
         spec = self.chain_spec(time_vec)
         if self.spk_encoder.robust_width < 1:
             raise ValueError("`distance` must be greater or equal to 1")
-        key = (spec.neuron_len, round(spec.neuron_decay, 15), round(spec.neuron_scale, 18), spec.num_mic)
+        # the encoder's settings are read at evolve time in the reference (callers may change them after construction)
+        key = (spec.neuron_len, round(spec.neuron_decay, 15), round(spec.neuron_scale, 18), spec.num_mic,
+               spec.robust_width, bool(spec.bipolar))
+        eng = self._engines.get(key)
+        # the beamforming matrix is a per-call argument: the same array object (unchanged since) skips the hashing
+        same_obj = eng is not None and getattr(eng, "_bf_obj", None) is bf_mat and not getattr(bf_mat, "flags", None) is None \
+            and not bf_mat.flags.writeable
+        if same_obj:
+            self._engines.move_to_end(key)
+            return eng
         bf = np.ascontiguousarray(bf_mat, dtype=np.float64)
         sig = (bf.shape, hash(bf.tobytes()))
-        eng = self._engines.get(key)
         if eng is None:
             eng = SnnEngine(spec, bf, device=self.device)
             eng._bf_sig = sig
             self._engines[key] = eng
+            while len(self._engines) > self.max_engines:          # variable-length frames must not grow GPU memory without bound
+                _, old = self._engines.popitem(last=False)
+                old.close()
         elif eng._bf_sig != sig:
             eng.set_bf(bf)
             eng._bf_sig = sig
+        eng._bf_obj = bf_mat
+        self._engines.move_to_end(key)
         return eng
 
     # ------------------------------------------------------------------

@@ -17,6 +17,9 @@
  *   - every function returns 0 on success or a negative micloc_status;
  *     micloc_last_error() gives the message of the calling thread's last failure.
  *   - launches are stream-ordered; no internal threads; one context per GPU.
+ *   - ONE STREAM PER CONTEXT AT A TIME: a context owns scratch buffers and the fused kernel's work counter, so
+ *     calls on the same context must be issued on one stream (or be ordered by the caller); use one context per
+ *     concurrent stream.  micloc_snn_run_host orders itself behind the context's previous device-side call.
  *   - audio layout is the reference's: [B][T][M] row-major, mics interleaved
  *     (micloc/snn_beamformer.py:298 `T x num_mic`; micloc/record.py:54-75 wav frames).
  */

@@ -51,12 +51,14 @@ def test_staged_taps_match_reference_golden(name):
     assert int(out["doa"][0]) == int(g["doa"])
 
 
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
 @pytest.mark.parametrize("name", H.SNN_CASES)
-def test_fused_matches_reference_golden(name):
+def test_fused_matches_reference_golden(name, variant, monkeypatch):
     g = H.load(name)
     eng = engine_for(g)
-    if eng.M > 7:
-        pytest.skip("fused kernel covers up to 7 microphones; larger arrays take the staged path")
+    if eng.M > 8:
+        pytest.skip("the fused kernels cover up to 8 microphones; larger arrays take the tiled path")
+    use_variant(monkeypatch, variant)
     out = eng.run(to_dev(g["x"]), want_spikes=True, fused=True)
     torch.cuda.synchronize()
     spikes = out["spikes"][0].cpu().numpy()
@@ -67,40 +69,23 @@ def test_fused_matches_reference_golden(name):
     assert int(out["doa"][0]) == int(g["doa"])
 
 
-# ---------------------------------------------------------------------------
-# fast-FIR variant of the fused kernel (MICLOC_FUSED_FIR=ffa: STHT as three half-length sub-filters)
-# ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name", H.SNN_CASES)
-def test_fast_fir_variant_matches_reference_golden(name, monkeypatch):
-    g = H.load(name)
-    eng = engine_for(g)
-    if eng.M > 7:
-        pytest.skip("fused kernel covers up to 7 microphones; larger arrays take the staged path")
-    monkeypatch.setenv("MICLOC_FUSED_FIR", "ffa")
-    out = eng.run(to_dev(g["x"]), want_spikes=True, fused=True)
-    torch.cuda.synchronize()
-    spikes = out["spikes"][0].cpu().numpy()
-    assert H.spike_agreement(spikes, g["spikes"]) >= SPIKE_AGREE
-    assert int(out["flags"][0]) == 0
-    if np.array_equal(spikes, g["spikes"]):
-        assert H.rel_err(out["power"][0].cpu().numpy(), g["power"]) < 1e-4
-    assert int(out["doa"][0]) == int(g["doa"])
+VARIANTS = ["tc", "ffma"]     # fused kernels: STHT on the tensor cores (default) / on the FP32 FMA pipe
 
 
-def test_fast_fir_variant_batch_vs_oracle(monkeypatch):
-    g = H.load("snn_c1_bipolar")
-    T, B = 4800, 48
-    x, _ = H.synth_clips(g, B, T, seed=4900)
-    eng = engine_for(g, T)
-    monkeypatch.setenv("MICLOC_FUSED_FIR", "ffa")
-    fu = eng.run(to_dev(x), want_spikes=True, fused=True)
-    torch.cuda.synchronize()
-    cfg = H.oracle_cfg(g)
-    cfg.nir = O.neuron_kernel(np.arange(T) / float(g["fs"]), float(g["tau"]), float(g["tau"]))
-    ref = O.snn_run_batch(cfg, x, nthreads=8, want_spikes=True)
-    assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
-    assert (fu["doa"].cpu().numpy() == ref["doa"]).mean() >= DOA_AGREE
-    assert int(fu["flags"].sum()) == 0
+def use_variant(monkeypatch, variant):
+    if variant == "ffma":
+        monkeypatch.setenv("MICLOC_FUSED_FIR", "ffma")
+    else:
+        monkeypatch.delenv("MICLOC_FUSED_FIR", raising=False)
+
+
+def same_spikes(fused, staged, variant, floor=SPIKE_AGREE):
+    """The FFMA kernel repeats the staged kernels' float32 arithmetic in the same order (identical spikes); the
+    tensor-core kernel sums the STHT in another order (hi/lo fp16 products, float32 accumulation) and is held to
+    the north-star tolerance."""
+    if variant == "ffma":
+        return torch.equal(fused, staged)
+    return H.spike_agreement(fused.cpu().numpy(), staged.cpu().numpy()) >= floor
 
 
 def _sub_array(g, mics):
@@ -114,8 +99,8 @@ def _sub_array(g, mics):
     return g2
 
 
-@pytest.mark.parametrize("mics,variant", [((0, 2, 3, 5), ""), ((1, 2, 3, 4, 6), ""), ((0, 1, 2, 3, 4, 5), ""), ((3,), ""),
-                                          ((0, 2, 3, 5), "ffa"), ((0, 1, 2, 3, 4, 5), "ffa")])
+@pytest.mark.parametrize("mics,variant", [((0, 2, 3, 5), "tc"), ((1, 2, 3, 4, 6), "tc"), ((0, 1, 2, 3, 4, 5), "tc"), ((3,), "tc"),
+                                          ((0, 2, 3, 5), "ffma"), ((0, 1, 2, 3, 4, 5), "ffma"), ((3,), "ffma")])
 def test_smaller_arrays_generic_microphone_count(mics, variant, monkeypatch):
     """Arrays of 1...6 microphones take the fused kernels' generic-M instantiation: fused vs staged vs oracle."""
     g = _sub_array(H.load("snn_c1_bipolar"), mics)
@@ -123,18 +108,16 @@ def test_smaller_arrays_generic_microphone_count(mics, variant, monkeypatch):
     x, _ = H.synth_clips(g, B, T, seed=77 + len(mics))
     eng = engine_for(g, T)
     st = eng.run(to_dev(x), want_spikes=True, fused=False)
-    if variant:
-        monkeypatch.setenv("MICLOC_FUSED_FIR", variant)
+    use_variant(monkeypatch, variant)
     fu = eng.run(to_dev(x), want_spikes=True, fused=True)
     torch.cuda.synchronize()
     cfg = H.oracle_cfg(g)
     cfg.nir = O.neuron_kernel(np.arange(T) / float(g["fs"]), float(g["tau"]), float(g["tau"]))
     ref = O.snn_run_batch(cfg, x, nthreads=4, want_spikes=True)
-    if not variant:
-        assert torch.equal(st["spikes"], fu["spikes"])
+    assert same_spikes(fu["spikes"], st["spikes"], variant)
     assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
     assert (fu["doa"].cpu().numpy() == ref["doa"]).mean() >= 0.9      # 12 clips: one near-tie may flip
-    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < (1e-5 if not variant else 1e-3)
+    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < (1e-5 if variant == "ffma" else 2e-3)
     assert int(fu["flags"].sum()) == 0
 
 
@@ -142,23 +125,25 @@ def test_smaller_arrays_generic_microphone_count(mics, variant, monkeypatch):
 # batches against the oracle: fused and staged agree within the reference tolerance with each other
 # (their float32 Gram sums run on different units) and with the oracle
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name,T,int16", [("snn_c1_bipolar", 4800, False), ("snn_c1_unipolar", 3000, False),
                                           ("snn_band2_sine", 4801, True), ("snn_band3_i16", 1000, True),
                                           ("snn_k20ms", 2500, False)])
-def test_batch_fused_vs_staged_vs_oracle(name, T, int16):
+def test_batch_fused_vs_staged_vs_oracle(name, T, int16, variant, monkeypatch):
     g = H.load(name)
     B = 48
     x, _ = H.synth_clips(g, B, T, seed=100 + T, int16=int16)
     eng = engine_for(g, T)
     xd = to_dev(x)
     st = eng.run(xd, want_spikes=True, fused=False)
+    use_variant(monkeypatch, variant)
     fu = eng.run(xd, want_spikes=True, fused=True)
     torch.cuda.synchronize()
-    # the two device paths run the same STHT / band-pass / RZCC arithmetic in the same order: identical spikes;
-    # the Gram sums differ (tensor cores with a TF32 x3 split vs FP64)
-    assert torch.equal(st["spikes"], fu["spikes"])
+    # FFMA kernel: same STHT / band-pass / RZCC arithmetic in the same order as the staged kernels (identical
+    # spikes; the Gram sums differ: fp16 hi/lo tensor-core products vs FP64)
+    assert same_spikes(fu["spikes"], st["spikes"], variant)
     assert (st["doa"] == fu["doa"]).float().mean().item() >= DOA_AGREE
-    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < 1e-5
+    assert H.rel_err(fu["power"].cpu().numpy(), st["power"].cpu().numpy()) < (1e-5 if variant == "ffma" else 2e-3)
     cfg = H.oracle_cfg(g)
     fs = float(g["fs"]); tau = float(g["tau"])
     cfg.nir = O.neuron_kernel(np.arange(T) / fs, tau, tau)
@@ -244,7 +229,7 @@ def test_full_size_config4_multi_source_360_grid():
     eng = engine_for(g, T)
     out = eng.run(to_dev(x), want_spikes=True, fused=True)
     st = eng.run(to_dev(x), want_spikes=True, fused=False)
-    assert torch.equal(out["spikes"], st["spikes"]) and torch.equal(out["doa"], st["doa"])
+    assert same_spikes(out["spikes"], st["spikes"], "tc") and torch.equal(out["doa"], st["doa"])
     cfg = H.oracle_cfg(g)
     cfg.nir = O.neuron_kernel(t, float(g["tau"]), float(g["tau"]))
     ref = O.snn_run_batch(cfg, x, nthreads=3, want_spikes=True)
@@ -269,8 +254,6 @@ def test_full_size_config5_64_mics_10s_512_grid():
     assert H.spike_agreement(out["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
     assert int(out["doa"][0]) == int(ref["doa"][0])
     assert H.rel_err(out["power"].cpu().numpy(), ref["power"]) < 2e-3
-    with pytest.raises(Exception):
-        eng.run(to_dev(x[:, :4096]), fused=True)               # 64 microphones: the fused kernel says so loudly
 
 
 def test_stht_linearity_and_zero_input():
@@ -286,16 +269,19 @@ def test_stht_linearity_and_zero_input():
     assert int(zero["spikes"].abs().sum()) == 0 and int(zero["doa"][0]) == 0      # all-equal power -> first index
 
 
-def test_ragged_and_tiny_clips():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ragged_and_tiny_clips(variant, monkeypatch):
     g = H.load("snn_c1_bipolar")
     cfg = H.oracle_cfg(g)
-    for T in (3, 17, 255, 256, 257, 481, 1023):
+    for T in (1, 2, 3, 17, 127, 128, 129, 255, 256, 257, 481, 1023):
         x, _ = H.synth_clips(g, 3, T, seed=T)
         eng = engine_for(g, max(T, 64))
-        fu = eng.run(to_dev(x), want_spikes=True, fused=True)
+        monkeypatch.delenv("MICLOC_FUSED_FIR", raising=False)
         st = eng.run(to_dev(x), want_spikes=True, fused=False)
+        use_variant(monkeypatch, variant)
+        fu = eng.run(to_dev(x), want_spikes=True, fused=True)
         torch.cuda.synchronize()
-        assert torch.equal(fu["spikes"], st["spikes"]), T
+        assert same_spikes(fu["spikes"], st["spikes"], variant, floor=0.99), T
         ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
         assert H.spike_agreement(fu["spikes"].cpu().numpy(), ref["spikes"]) >= 0.99, T
 
@@ -314,6 +300,7 @@ def test_run_host_end_to_end_equals_device_path():
     x, _ = H.synth_clips(g, 40, 2400, seed=5, int16=True)
     eng = engine_for(g, 2400)
     dev = eng.run(to_dev(x), want_spikes=True, fused=True)
+    torch.cuda.synchronize()
     host = eng.run_host(torch.from_numpy(x).pin_memory(), want_spikes=True, fused=True)
     assert np.array_equal(host["doa"].numpy(), dev["doa"].cpu().numpy())
     assert np.array_equal(host["spikes"].numpy(), dev["spikes"].cpu().numpy())
@@ -327,6 +314,7 @@ def test_run_host_overlapping_chunks_equal_device_path(monkeypatch):
     x, _ = H.synth_clips(g, 700, 1200, seed=9)
     eng = engine_for(g, 1200)
     dev = eng.run(to_dev(x), want_spikes=True, fused=True)
+    torch.cuda.synchronize()
     monkeypatch.setenv("MICLOC_HOST_CHUNK_CLIPS", "90")
     for _ in range(3):
         host = eng.run_host(torch.from_numpy(x).pin_memory(), want_spikes=True, fused=True)

@@ -37,6 +37,8 @@ for rep in range(3):
     print(f"rep {rep}: {ms:.3f} ms, {B / ms:.1f} clips/ms; " + ", ".join(
         f"{n}: {v[i] / max(v[8 + i], 1) / iters:.0f}" for i, n in enumerate(names)) + " busy cyc/tile")
     print(f"   CTA 0: {v[16]} clock64 cycles in {v[17]} ns -> {v[16] / max(v[17], 1) * 1e3:.0f} MHz")
+    if any(v[18:]):
+        print("   phase cycles per step and reporting warp:", ", ".join(f"{x / max(v[8], 1) / iters:.0f}" for x in v[18:]))
 
 n = min(296, (B + 1) // 2)  # CTAs of the launch (148 SMs x 2)
 buf = (ctypes.c_uint64 * (16 * n))()
