@@ -215,6 +215,10 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pin this rank (and the pinned staging it allocates from now on) to its GPU's NUMA node: the host-buffer leg
+    # streams tens of GB/s per GPU over PCIe
+    from haghighatshoarmuir2024_b200.distributed import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = N.lib()
@@ -296,34 +300,53 @@ def run_gpu(args):
     del outs
     torch.cuda.empty_cache()
 
-    # ---- end to end through the C-ABI with HOST buffers (`e2e`) ----
+    # ---- end to end through the C-ABI with HOST buffers (`e2e`): both wire formats ----
+    # int16 PCM is the reference's wire format (micloc/record.py:54-75 reads integer wav frames) and the documented
+    # default of the host path: half the PCIe bytes of float32.  `e2e` is the int16 leg, `e2e.f32` the float32 one.
     Be = min(Bb, args.e2e_clips_per_band)                          # bounded: the host copy of the full step would be tens of GB
-    host = [a[:Be].cpu().pin_memory() for a in audio]
-    esz = host[0].element_size()
-    h2d = sum(h.numel() for h in host) * esz
     d2h = nb * Be * (4 + 4)                                       # doa + flags per clip
-    def e2e_step():
-        res = []
-        for i in range(nb):
-            res.append(sweep.engines[i].run_host(host[i], want_spikes=False, want_power=False, fused=True))
-        return res
-    for _ in range(max(1, min(args.warmup, 2))):
-        res = e2e_step()
-    barrier()
-    l1 = lib.micloc_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    launches += lib.micloc_launch_count() - l1
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = nb * Be * world * args.steps / float(te.item())
+
+    def e2e_leg(host):
+        h2d = sum(h.numel() for h in host) * host[0].element_size()
+        def e2e_step():
+            return [sweep.engines[i].run_host(host[i], want_spikes=False, want_power=False, fused=True) for i in range(nb)]
+        for _ in range(max(1, min(args.warmup, 2))):
+            res = e2e_step()
+        barrier()
+        l1 = lib.micloc_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        n_launch = lib.micloc_launch_count() - l1
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        secs = float(te.item())
+        return res, nb * Be * world * args.steps / secs, h2d, h2d * args.steps / secs / 1e9, n_launch
+
+    host_f32 = [a[:Be].cpu().pin_memory() for a in audio] if tdtype == torch.float32 else None
+    if tdtype == torch.int16:
+        audio16 = audio
+    else:
+        audio16 = [sweep.synthesize(i, Be, seed=10_000 * (rank + 1) + i, snr_db_grid=SNR_GRID, dtype=torch.int16)[0]
+                   for i in range(nb)]
+    host_i16 = [a[:Be].cpu().pin_memory() for a in audio16]
+    res16, e2e_value, h2d, e2e_gbs, nl = e2e_leg(host_i16)
+    launches += nl
     # the host path and the device path must agree bit for bit
+    dev_doa16 = [sweep.run_band(i, audio16[i][:Be], want_power=False)["doa"].cpu().numpy() for i in range(nb)]
+    e2e_same = all(np.array_equal(res16[i]["doa"].numpy(), dev_doa16[i]) for i in range(nb))
+    e2e_f32 = None
     dev_doa = [sweep.run_band(i, audio[i][:Be], want_power=False)["doa"].cpu().numpy() for i in range(nb)]
-    e2e_same = all(np.array_equal(res[i]["doa"].numpy(), dev_doa[i]) for i in range(nb))
+    host = host_f32 if host_f32 is not None else host_i16
+    if host_f32 is not None:
+        res32, v32, h2d32, gbs32, nl = e2e_leg(host_f32)
+        launches += nl
+        same32 = all(np.array_equal(res32[i]["doa"].numpy(), dev_doa[i]) for i in range(nb))
+        e2e_f32 = {"value": v32, "unit": UNIT, "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": d2h,
+                   "pcie_h2d_gbs": gbs32, "matches_device_path": bool(same32)}
 
     if rank != 0:
         if world > 1:
@@ -368,11 +391,15 @@ def run_gpu(args):
         except Exception:
             pass
     roofline = {
-        "bound": "fp32", "kernel": "k_fused", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "k_fused" if os.environ.get("MICLOC_FUSED_FIR", "")[:1] == "f" else "k_fused_tc",
+        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak, "traffic": traffic,
         "peak_source": f"measured in this run by micloc_fp32_peak (FFMA {peak['ffma']:.1f}, FFMA2 {peak['ffma2']:.1f} TFLOP/s)",
         "flop_per_mic_sample": F_gram, "flop_per_mic_sample_survey_formula": F_survey,
         "achieved_survey_formula": achieved * F_survey / F_gram,
+        "note": "algorithmic FLOPs of the chain (574 per mic-sample, STHT = 480 of them) over the measured FP32 FMA peak, the "
+                "north star's roofline; k_fused_tc executes the STHT share as fp16 hi/lo tcgen05.mma (3 products, 128x368 "
+                "Toeplitz tiles), so the FP32 pipe itself carries only the 94 non-STHT FLOPs per mic-sample",
         "avg_launch_ms": avg_launch_ms, "launches_timed": kern_n, "mic_samples_per_launch": mic_samples_per_launch,
         "kernel_share_of_step": kern_ms / ms,
         "launch_timing": ("3 band launches per step overlap on 3 streams: avg_launch_ms = step device time / 3; "
@@ -406,8 +433,10 @@ def run_gpu(args):
         "outputs_in_timed_region": "int8 spikes [B,T,14] + int32 DoA [B] + DoA histogram written to HBM",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "micloc_snn_run_host (pinned host audio in, DoA indices + flags out)",
-                "clips_per_band_per_step": Be, "pcie_h2d_gbs": h2d * args.steps / float(te.item()) / 1e9,
-                "matches_device_path": bool(e2e_same)},
+                "wire_format": "int16 PCM [B][T][M] (the reference's recorder format, micloc/record.py:54-75); "
+                               "the float32 leg is under `f32`",
+                "clips_per_band_per_step": Be, "pcie_h2d_gbs": e2e_gbs,
+                "matches_device_path": bool(e2e_same), "f32": e2e_f32, "numa": numa},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "spike_density": spike_density, "rzcc_overflow_clips": flags,
     }

@@ -112,6 +112,7 @@ struct FusedSmem {
     unsigned int *dbg;      // sm_slots (debug counters behind the first 256 entries)
     int bar_id;             // named barrier of this clip-pair group
     int bar_threads;        // threads meeting at it
+    int k_first;            // first pipeline step of the serial roles (-1 here)
     int rec;                // index of this group's debug record (MICLOC_ROLE_TIMING builds)
 };
 
@@ -446,6 +447,7 @@ k_fused(const IN_T *__restrict__ audio, const float *__restrict__ taps, const do
     sm.dbg = sm_slots;
     sm.bar_id = bar_id;
     sm.bar_threads = kThreads;
+    sm.k_first = -1;
     sm.rec = GROUPS * (int)blockIdx.x + group;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_cs);     // [kThreads], clip epilogue only (reuses the running sums)
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_cs + kThreads * sizeof(double));

@@ -126,7 +126,7 @@ __device__ __forceinline__ void rzcc_role(const SMEM &sm, const ChainParams &p, 
     RzccState rz; rzcc_reset(rz);
     ROLE_TIMER_DECL;
 
-    for (int k = -1; k <= k_last; ++k) {
+    for (int k = sm.k_first; k <= k_last; ++k) {
         hook(k);
         const int kr = k - 3;
         const int t0 = kr * kTile;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void neuron_role(const SMEM &sm, const ChainParams &p
     NeuronState nr; neuron_reset(nr);
     ROLE_TIMER_DECL;
 
-    for (int k = -1; k <= k_last; ++k) {
+    for (int k = sm.k_first; k <= k_last; ++k) {
         hook(k);
         const int j = k - g.dtile;
         const int u0 = j * kTile;
@@ -278,7 +278,7 @@ __device__ __forceinline__ void gram_role(const SMEM &sm, const GEOM &g, int8_t 
             for (int i = 0; i < 4; ++i) { accf[s][nb][i] = 0.f; accd[s][nb][i] = 0.0; }
     ROLE_TIMER_DECL;
 
-    for (int k = -1; k <= k_last; ++k) {
+    for (int k = sm.k_first; k <= k_last; ++k) {
         hook(k);
         const int j = k - g.dtile - 1;
         const int u0 = j * kTile;

@@ -11,20 +11,25 @@
 //   polyphase   The Hilbert kernel has a tap at every other lag, so Q at odd times is a DENSE FIR of the even
 //               samples E[n] = x[2n] and Q at even times the same FIR of the odd samples O[n] = x[2n-1]:
 //               Q[2n+1] = sum_j g[j] E[n-j],  Q[2n] = sum_j g[j] O[n-j]   (g[j] = h[k0 + 2j], k0 odd).
-//   operands    Every stream (microphone x parity) lives time-contiguous in a shared-memory ring as two fp16
-//               pieces u = hi + lo (22 significant bits; the clip is scaled by a power of two so that it fits the
-//               fp16 range -- band-pass and RZCC are scale invariant).  The A operand of an M=128 x N=16 x K=16
-//               instruction is the HANKEL matrix A[m][e] = u[8m - lag + e] read straight from that ring: a K-major
-//               no-swizzle descriptor whose 8-row core matrices overlap (row r starts 16 bytes = 8 samples after
-//               row r-1, leading byte offset 16), 16 row groups = the 2M streams of one clip at the ring pitch.
-//               B is the constant Toeplitz block of the taps for the 8 output phases, split hi | lo (x 2^14):
-//               B[a][e] = g[a + lag - e].  2 x 16 instructions per clip and 128 frames give
-//               D[m][a] + D[m][8+a] = y[8m + a] with all four hi/lo cross terms, accumulated in float32.
-//   in          The producer warp streams 128-frame audio tiles with 1-D TMA bulk copies (cp.async.bulk +
-//               mbarrier) into a staging buffer, converts them into the hi/lo rings and issues the MMAs.
-//   out         The four serial warps each own one 32-lane quarter of tensor memory: at the top of a step they move
-//               their share of the finished quadrature tile into the step's q rows (tcgen05.ld) and rebuild the
-//               in-phase samples x[t - K/2] (np.roll: the first K/2 come from the clip tail) from the rings.
+//   GEMM        D[a][n] = sum_e A[a][e] B[n][e] per tile of 128 stream samples (256 frames) of the group's two clips:
+//               A[a][e] = g[a + lag - e] is the constant Toeplitz matrix of the taps (128 output phases x window of
+//               lag + 128 samples), resident in TENSOR MEMORY as two fp16 pieces (taps x 2^14 = hi + lo, written once
+//               per CTA with tcgen05.st); B[n][e] = u_n[128 tile - lag + e] holds the window of stream n (2 clips x
+//               microphones x parity = 28 columns, N = 32).  The streams live in shared memory in rings of 8-sample
+//               chunks, the chunks of all streams interleaved -- exactly the canonical K-major core-matrix layout
+//               of the B operand, so a descriptor with the right start address IS the sliding window (nothing is
+//               copied) -- as two fp16 pieces u = hi + lo (22 significant bits; the clip is scaled by a power of two
+//               so that it fits the fp16 range: band-pass and RZCC are scale invariant).  Three products per K step
+//               (hi hi, hi lo, lo hi; the dropped lo lo is below 2^-22), float32 accumulation.  Shared-memory traffic
+//               of an instruction: 1 KB.  (A first version had the samples as the A operand, a Hankel matrix read
+//               through overlapping core matrices: correct, but 4.5 KB of shared-memory reads per instruction starved
+//               the serial warps -- profiles/README.md.)
+//   in          The producer warp streams 128-frame audio tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
+//               into a staging buffer; the four serial warps convert it into the hi/lo rings at the top of a step;
+//               the producer issues the MMAs of a tile once its four audio tiles are in.
+//   out         A step's 32 stream samples are one 32-lane quarter of the accumulator: the warp owning that quarter
+//               moves them into the step's q rows (tcgen05.ld); all four warps rebuild the in-phase samples
+//               x[t - K/2] (np.roll: the first K/2 come from the clip tail) from the rings.
 //
 // One CTA holds two independent clip-pair groups of five warps (four serial roles + producer).
 #include <cstdlib>
@@ -34,29 +39,31 @@
 namespace micloc {
 namespace tc {
 
-constexpr int kGWarps = 5;                // warps of a clip-pair group
+constexpr int kGWarps = 8;                // warps of a clip-pair group: four serial roles + four front-end warps
 constexpr int kGThreads = kGWarps * 32;
-constexpr int kRoleProducer = 4;          // roles 0..3: band-pass, RZCC, neuron, Gram = tensor-memory lane quarter
+constexpr int kRoleFront = 4;             // roles 0..3: band-pass, RZCC, neuron, Gram; 4 + q: front-end warp of lane quarter q
 constexpr int kRingWords = 16;            // spike-bit ring: 16 words of 32 samples per channel and polarity
-constexpr int kMac = 2 * kTile;           // frames per MMA tile (8 rows x 8 samples per stream and parity)
-constexpr int kMirror = 56;               // ring positions repeated behind the ring end (a row group reads 72 in a row)
+constexpr int kMac = 2 * kTile;           // frames per audio tile (TMA, conversion): 64 samples of every stream
+constexpr int kBlk = 128;                 // stream samples per MMA tile = output phases = rows of A
 constexpr int kQRow = kTile + 4;          // floats per channel row of a q sub-tile: [even times: 32][odd times: 32] + pad
-constexpr int kRows = 8;                  // most microphones (16 row groups = 8 microphones x 2 parities)
+constexpr int kRows = 8;                  // most microphones
 constexpr float kTapScale = 16384.f;      // taps are stored x 2^14 as fp16 hi + lo
-constexpr int kColsPerTile = 32;          // tensor-memory columns of one tile: hi-piece and lo-piece accumulators of N = 16
+constexpr int kMmaN = 32;                 // columns of an MMA: the group's streams (2 clips x microphones x parity <= 32)
+constexpr int kLead = 3;                  // steps the front end runs ahead of the serial roles
 
 struct TcGeom {
-    int R;          // ring length in stream samples (multiple of 64)
-    int pitch_b;    // bytes per stream row: 2 (R + kMirror)
-    int lag;        // a row's window starts `lag` samples before its first output (multiple of 16)
-    int ksteps;     // MMA K steps of 16 per piece
+    int RC;         // ring length in 8-sample chunks (even)
+    int NSP;        // streams per chunk row: kSlots * 2M
+    int piece_b;    // bytes of one ring piece: RC * NSP * 16
+    int lag;        // the window of a tile starts `lag` samples before its first output (multiple of 16)
+    int ksteps;     // MMA K steps of 16: (lag + 128) / 16
     int H;          // K/2 / 2: in-phase delay in stream samples
     int d0;         // leading zero taps of the polyphase filter
     int dtile;      // the neuron warp runs dtile steps behind (RZCC decision latency)
     int tiles_is;   // sub-tiles whose in-phase input comes from the clip tail
     int off_ring, off_stin, off_q, off_vm, off_cs, off_seg, off_clus, off_bits, off_stage, off_misc;
     int smem_group; // bytes of one group
-    int smem_bytes; // bytes of the CTA (groups + tap matrix)
+    int smem_bytes; // bytes of the CTA
 };
 
 struct TcSmem {
@@ -69,16 +76,16 @@ struct TcSmem {
     int8_t *stage;
     double *gram;
     unsigned int *dbg;
-    int bar_id, bar_threads, rec;
+    int bar_id, bar_threads, rec, k_first;
     // tensor-core side
-    unsigned char *ring;      // [kSlots][2 pieces][2M streams][pitch_b] (+ 2 rows of padding)
+    unsigned char *ring;      // [2 pieces][RC chunks][NSP streams][8 halves]
     unsigned char *stin;      // TMA staging of one audio tile [kMac][M]
     float *q;                 // [2 sub-tiles][kSlots][2M][kQRow]
     float *scale;             // [kSlots] power-of-two clip scale
     unsigned int *amax;       // [kSlots]
     unsigned int *amax_next;  // [kSlots] of the clip pair this group takes next (scanned by the producer warp meanwhile)
     float *carry;             // [kSlots][2][8] last frame of the previous audio tile (first odd-stream sample of the next)
-    unsigned long long *mbar; // [0..3] MMA done (slot, buffer), [4] audio tile staged, [5] tile converted into the rings
+    unsigned long long *mbar; // [0..1] MMA done (accumulator buffer), [4] audio tile staged
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -106,6 +113,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d, uint64_t ad, uint64_t bd,
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(accum) : "memory");
 }
+// A from tensor memory (lane = row, column c of a K step holds elements k = 2c (low half) and 2c + 1), B from shared memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -126,7 +142,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // kind::f16, A and B fp16 K-major, D float32, M = 128, N = 16 (cute::UMMA::InstrDescriptor)
-constexpr int kMmaN = 16;
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kMmaN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 template <typename IN_T> __device__ __forceinline__ float clip_scale(unsigned int amax_bits);
@@ -140,35 +155,48 @@ template <> __device__ __forceinline__ float clip_scale<float>(unsigned int amax
     return __uint_as_float((unsigned int)(s + 127) << 23);
 }
 
-// ======================= producer warp: TMA -> staging, MMAs; amax scan of the next clip pair =======================
-// Step k belongs to audio tile J = (k + 1) / 2 of clip slot (k odd ? 0 : 1): the four serial warps convert the staged
-// tile into the hi / lo rings at the top of the step (StepHook), the producer waits for them, sends the next tile
-// on its way and issues the tile's MMAs.
-__device__ __forceinline__ bool tile_of_step(int k, int NJ, bool ok1, int &slot, int &J) {
-    slot = (k & 1) ? 0 : 1;
-    J = (k + 1) >> 1;
+// ======================= front-end warps (4 per group): audio in, STHT on the tensor cores, q rows out =======================
+// The front end runs kLead steps ahead of the serial roles.  Step k handles audio tile `it` = k + kLead + 1:
+// tile it is the 128-frame tile J = it / 2 of clip slot it & 1; the four tiles 4 Jb .. 4 Jb + 3 make up MMA tile Jb
+// (256 frames of both clips).  Per step, all four warps:
+//   (a) turn the staged audio tile into hi / lo ring chunks (a thread builds one 8-sample chunk of one stream),
+//   (b) meet; warp 0 sends the next audio tile on its way (TMA) and, behind the fourth tile of an MMA tile, issues its
+//       MMAs (one lane) and commits them to the accumulator buffer's mbarrier,
+//   (c) move sub-tile k - 1 into the q rows the band-pass warp reads at the next step: the warp whose tensor-memory
+//       lane quarter holds the sub-tile's 32 stream samples stores Q, every warp rebuilds the in-phase samples of one
+//       (clip slot, parity) from the rings,
+//   (d) warp 1 scans a slice of the NEXT clip pair for its largest magnitude (float32 input: fp16 clip scale).
+__device__ __forceinline__ bool tile_of_step(int k, int NJ, bool ok1, int &it, int &slot, int &J) {
+    it = k + kLead + 1;
+    slot = it & 1;
+    J = it >> 1;
     return J < NJ && (slot == 0 || ok1);
 }
 
 template <typename IN_T, int MM>
-__device__ __forceinline__ void producer_role(const TcSmem &sm, const ChainParams &p, const TcGeom &g,
-                                              const IN_T *__restrict__ audio, long long clip0, long long B,
-                                              long long T64, int lane, int NJ, int k_last, uint32_t tmem_cols,
-                                              uint32_t tapsB, uint32_t &ring_phase, long long next_clip0) {
-    const int M = MM ? MM : p.M;
+__device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &p, const TcGeom &g,
+                                           const IN_T *__restrict__ audio, long long clip0, long long B,
+                                           long long T64, int quarter, int lane, int NT, int NJ, int k_last,
+                                           uint32_t tmem_a, uint32_t tmem_d, uint32_t &tma_phase, int front_bar,
+                                           long long next_clip0) {
+    const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
     const bool ok1 = clip0 + 1 < B;
     const IN_T *src[kSlots] = {audio + clip0 * T64 * M, audio + (ok1 ? clip0 + 1 : clip0) * T64 * M};
     const bool al[kSlots] = {(reinterpret_cast<uintptr_t>(src[0]) & 15) == 0, (reinterpret_cast<uintptr_t>(src[1]) & 15) == 0};
     const uint32_t tile_bytes = (uint32_t)(kMac * M * sizeof(IN_T));
-    const uint32_t bar_tma = smem_u32(sm.mbar + 4), bar_ring = smem_u32(sm.mbar + 5);
+    const uint32_t bar_tma = smem_u32(sm.mbar + 4);
     const uint32_t stin_a = smem_u32(sm.stin);
     IN_T *stin = reinterpret_cast<IN_T *>(sm.stin);
+    const int NJb = (NJ + 1) >> 1;            // MMA tiles of 256 frames
+    const int t128 = quarter * 32 + lane;
+    const float sx[kSlots] = {sm.scale[0], sm.scale[1]};
+    auto front_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(front_bar) : "memory"); };
     ROLE_TIMER_DECL;
     PH_DECL;
 
-    // audio tile J of clip slot `slot` -> staging: one 1-D TMA bulk copy when the tile is whole and 16-byte aligned,
-    // else plain loads with zero fill behind the clip end; either way the tile's arrival completes a phase of bar_tma
+    // audio tile J of clip slot `slot` -> staging (warp 0): one 1-D TMA bulk copy when the tile is whole and 16-byte
+    // aligned, else plain loads with zero fill behind the clip end; either way its arrival completes a phase of bar_tma
     auto issue_load = [&](int slot, int J) {
         const int f0 = kMac * J;
         const IN_T *s = src[slot] + (long long)f0 * M;
@@ -187,217 +215,243 @@ __device__ __forceinline__ void producer_role(const TcSmem &sm, const ChainParam
         __syncwarp();
     };
 
-    // largest magnitude of the NEXT clip pair (float32 input), a slice per step: its clip scale is ready when that pair starts
-    const bool scan = sizeof(IN_T) == 4 && next_clip0 >= 0 && ((T64 * M) & 3) == 0 &&
-                      (reinterpret_cast<uintptr_t>(audio + next_clip0 * T64 * M) & 15) == 0;
+    // (d) state of the scan of the next pair (warp 1)
+    const bool scan = quarter == 1 && sizeof(IN_T) == 4 && next_clip0 >= 0 && ((T64 * M) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(audio + next_clip0 * T64 * M) & 15) == 0 &&
+                      ((T64 * M) >> 2) <= 128ll * (k_last + kLead + 1);
     const long long n4 = (T64 * M) >> 2;
-    const int per_step = (int)((n4 + k_last + 1) / (k_last + 2));
+    constexpr int kScanLd = 4;                 // float4 loads per lane, clip and step
+    float4 sv[kSlots][kScanLd];
+#pragma unroll
+    for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+        for (int u = 0; u < kScanLd; ++u) sv[c][u] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *scan_src[kSlots] = {reinterpret_cast<const float4 *>(audio + (next_clip0 < 0 ? 0 : next_clip0) * T64 * M),
                                       reinterpret_cast<const float4 *>(audio + (next_clip0 < 0 ? 0 : next_clip0 + 1) * T64 * M)};
     const bool scan_ok1 = next_clip0 + 1 < B;
     float mx[kSlots] = {0.f, 0.f};
     long long scan_i = 0;
 
-    issue_load(0, 0);
-    for (int k = -1; k <= k_last; ++k) {
-        int slot, J;
-        if (tile_of_step(k, NJ, ok1, slot, J)) {
-            PH_START();
-            mbar_wait(bar_ring, ring_phase);          // the serial warps have turned the staged tile into ring samples
-            ring_phase ^= 1u;
+    if (quarter == 0) issue_load(0, 0);
+    for (int k = sm.k_first; k <= k_last; ++k) {
+        int it, slot, J;
+        const bool valid = tile_of_step(k, NJ, ok1, it, slot, J);
+        PH_START();
+        // ---- (a) staging -> rings.  The chunks overwritten lie in the window of MMA tile Jb - 1 (second half of tile
+        //      Jb) or Jb - 2 (first half): issued 3 or more steps ago, observed here ----
+        if (valid) {
+            const int Jw = (it >> 2) - ((it & 2) ? 1 : 2);
+            if (Jw >= 0) mbar_wait(smem_u32(sm.mbar + (Jw & 1)), (uint32_t)((Jw >> 1) & 1));
+            mbar_wait(bar_tma, tma_phase);
+            tma_phase ^= 1u;
             PH_END(0);
-            // ---- next tile on its way while the tensor cores work on this one ----
-            {
-                int s2, J2;
-                if (tile_of_step(k + 1, NJ, ok1, s2, J2)) issue_load(s2, J2);
-                else if (tile_of_step(k + 2, NJ, ok1, s2, J2)) issue_load(s2, J2);
-            }
-            PH_END(1);
-            // ---- STHT of the tile: the hi-piece chain into accumulator 0, the lo-piece chain into accumulator 1
-            //      (independent chains pipeline in the tensor core; the epilogue adds them) ----
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t d0 = tmem_cols + (uint32_t)((slot * 2 + (J & 1)) * kColsPerTile);
-                int pos = (kTile * J) % g.R - g.lag;
-                if (pos < 0) pos += g.R;
-                const uint32_t ra_hi = smem_u32(sm.ring + (size_t)((slot * 2 + 0) * 2 * M) * g.pitch_b);
-                const uint32_t ra_lo = smem_u32(sm.ring + (size_t)((slot * 2 + 1) * 2 * M) * g.pitch_b);
-                const uint64_t a_fix = make_desc(0u, 16u, (uint32_t)g.pitch_b);
-                uint64_t bd = make_desc(tapsB, 128u, (uint32_t)(2 * g.ksteps) * 128u);
-#pragma unroll 2
-                for (int ks = 0; ks < g.ksteps; ++ks) {
-                    const uint32_t off = (2u * (uint32_t)pos) >> 4;
-                    tc_mma_f16(d0, a_fix | (uint64_t)(((ra_hi >> 4) + off) & 0x3FFFu), bd, kIdesc, ks ? 1u : 0u);
-                    tc_mma_f16(d0 + 16u, a_fix | (uint64_t)(((ra_lo >> 4) + off) & 0x3FFFu), bd, kIdesc, ks ? 1u : 0u);
-                    bd += 16u;                          // next K step of the tap matrix: 256 bytes on
-                    pos += 16;
-                    if (pos >= g.R) pos -= g.R;
-                }
-                tc_commit(smem_u32(sm.mbar + slot * 2 + (J & 1)));
-            }
-            __syncwarp();
-            PH_END(2);
-        }
-        if (scan) {
-            PH_START();
-            const long long i_end = scan_i + per_step < n4 ? scan_i + per_step : n4;
+            const int f0 = kMac * J;
+            const int cb = (8 * J) % g.RC;          // ring chunk of the tile's first stream position
+            const float s_x = sx[slot];
+            // thread (j, parity, mic) builds chunk j of its stream: samples 8 j .. 8 j + 7 = frames
+            // 16 j - parity + 2 i (O[n] = x[2n-1]: the odd stream's first sample is the previous tile's last frame)
+            if (t128 < 8 * C2) {
+                const int j = t128 / C2, sidx = t128 - j * C2;
+                const int par = sidx >= M ? 1 : 0, mic = sidx - par * M;
+                const IN_T *sp = stin + (16 * j - par) * M + mic;
+                float u[8];
+                if (f0 + kMac <= T) {
 #pragma unroll
-            for (int c = 0; c < kSlots; ++c) {
-                if (c == 1 && !scan_ok1) break;
-                for (long long i = scan_i + lane; i < i_end; i += 32) {
-                    const float4 v = __ldg(scan_src[c] + i);
-                    mx[c] = fmaxf(fmaxf(mx[c], fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-                    if (i + per_step < n4) asm volatile("prefetch.global.L2 [%0];" ::"l"(scan_src[c] + i + per_step));
+                    for (int i = 0; i < 8; ++i) u[i] = (i > 0 || j > 0 || par == 0) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int f = 16 * j - par + 2 * i;
+                        u[i] = (f >= 0 && f0 + f < T) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
+                    }
+                }
+                if (j == 0 && par == 1) u[0] = J > 0 ? sm.carry[(slot * 2 + ((J + 1) & 1)) * 8 + mic] : 0.f;   // x[128 J - 1]
+                uint4 h4, l4;
+                unsigned int *hp = &h4.x, *lp = &l4.x;
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2) {
+                    const __half2 hh = __floats2half2_rn(u[2 * i2], u[2 * i2 + 1]);
+                    const float2 hf = __half22float2(hh);
+                    const __half2 ll = __floats2half2_rn(u[2 * i2] - hf.x, u[2 * i2 + 1] - hf.y);
+                    hp[i2] = *reinterpret_cast<const unsigned int *>(&hh);
+                    lp[i2] = *reinterpret_cast<const unsigned int *>(&ll);
+                }
+                int ch = cb + j;
+                if (ch >= g.RC) ch -= g.RC;
+                const int off = (ch * g.NSP + slot * C2 + 2 * mic + par) * 16;
+                *reinterpret_cast<uint4 *>(sm.ring + off) = h4;
+                *reinterpret_cast<uint4 *>(sm.ring + g.piece_b + off) = l4;
+            }
+            if (t128 < M) sm.carry[(slot * 2 + (J & 1)) * 8 + t128] = (f0 + kMac - 1 < T) ? to_f32<IN_T>(stin[(kMac - 1) * M + t128]) * s_x : 0.f;
+            fence_proxy_async();
+        }
+        PH_END(1);
+        front_sync();
+        // ---- (b) next audio tile (warp 0); MMAs (warp 3, one lane).  The K steps of MMA tile Jb are issued as their
+        //      samples arrive: behind the tile's 2nd audio tile the steps over the history (the accumulator buffer was
+        //      read out at the previous step), behind the 3rd those over the first 64 new samples, behind the 4th the
+        //      rest + commit.  (tcgen05.mma blocks its warp while the tensor core's queue is full.) ----
+        if (quarter == 0 && valid) {
+            int i2, s2, J2;
+            if (tile_of_step(k + 1, NJ, ok1, i2, s2, J2)) issue_load(s2, J2);
+            else if (tile_of_step(k + 2, NJ, ok1, i2, s2, J2)) issue_load(s2, J2);
+        }
+        if (quarter == 3) {
+            const int Jb = it >> 2, part = it & 3;
+            if (part >= 1 && Jb < NJb) {
+                const int hist = g.lag / 16;              // K steps over samples before the tile
+                const int b1 = (hist * 3) / 4, b2 = hist + 4;
+                const int ks0 = part == 1 ? 0 : (part == 2 ? b1 : b2), ks1 = part == 1 ? b1 : (part == 2 ? b2 : g.ksteps);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d = tmem_d + (uint32_t)((Jb & 1) * kMmaN);
+                    int c = ((16 * Jb) % g.RC - g.lag / 8 + 2 * ks0) % g.RC;          // chunk of K step ks0
+                    if (c < 0) c += g.RC;
+                    const uint32_t rb_hi = smem_u32(sm.ring), rb_lo = rb_hi + (uint32_t)g.piece_b;
+                    const uint32_t chunk_b = (uint32_t)g.NSP * 16u;
+                    // B: K-major, no swizzle: 8 streams x 16 bytes per core matrix, next 8 streams 128 bytes on,
+                    // next chunk (K) NSP * 16 bytes on
+                    const uint64_t b_fix = make_desc(0u, chunk_b, 128u);
+                    const uint32_t a_lo = tmem_a + 8u * (uint32_t)g.ksteps;
+#pragma unroll 2
+                    for (int ks = ks0; ks < ks1; ++ks) {
+                        const uint32_t off = ((uint32_t)c * chunk_b) >> 4;
+                        const uint64_t b_hi = b_fix | (uint64_t)(((rb_hi >> 4) + off) & 0x3FFFu);
+                        const uint64_t b_lo = b_fix | (uint64_t)(((rb_lo >> 4) + off) & 0x3FFFu);
+                        tc_mma_f16_ts(d, tmem_a + 8u * (uint32_t)ks, b_hi, kIdesc, ks ? 1u : 0u);
+                        tc_mma_f16_ts(d, tmem_a + 8u * (uint32_t)ks, b_lo, kIdesc, 1u);
+                        tc_mma_f16_ts(d, a_lo + 8u * (uint32_t)ks, b_hi, kIdesc, 1u);
+                        c += 2;
+                        if (c >= g.RC) c -= g.RC;
+                    }
+                    if (part == 3) tc_commit(smem_u32(sm.mbar + (Jb & 1)));
+                }
+                __syncwarp();
+            }
+        }
+        PH_END(2);
+        // ---- (c) sub-tile s = k - 1 -> q rows ----
+        const int s = k - 1;
+        if (s >= 0 && s < NT) {
+            // Q: accumulator row a = stream sample a of MMA tile Jb, column n = stream; the 32 samples of this
+            // sub-tile are lanes 32 (s & 3) ..: the warp that owns them stores column after column
+            if ((s & 3) == quarter) {
+                const int Jb = s >> 2;
+                mbar_wait(smem_u32(sm.mbar + (Jb & 1)), (uint32_t)((Jb >> 1) & 1));
+                tc_fence_after();
+                uint32_t r[32];
+                tc_ld32(tmem_d + (uint32_t)((Jb & 1) * kMmaN) + ((uint32_t)(32 * quarter) << 16), r);
+                tc_fence_before();
+                float *qb = sm.q + (s & 1) * kSlots * C2 * kQRow + lane;
+#pragma unroll
+                for (int n = 0; n < 2 * kRows * kSlots; ++n) {
+                    // stream n = slot * 2M + 2 mic + parity: even stream -> Q at odd times, odd stream -> Q at even times
+                    if (n < kSlots * C2) {
+                        const int slot2 = n / C2, rem = n - slot2 * C2;
+                        if (clip0 + slot2 < B)
+                            qb[(slot2 * C2 + M + (rem >> 1)) * kQRow + ((rem & 1) ? 0 : 32)] = __uint_as_float(r[n]);
+                    }
                 }
             }
-            scan_i = i_end;
             PH_END(3);
+            // I[t] = x[(t - K/2) mod T] (scaled like the ring samples; the band-pass warp applies the 2^14 of the
+            // taps): warp quarter = (clip slot, parity); a lane rebuilds 8 consecutive samples of one microphone
+            const int islot = quarter >> 1, ipar = quarter & 1;
+            if (lane < 4 * M && clip0 + islot < B) {
+                const int mic = lane >> 2, chunk = lane & 3;
+                float v[8];
+                if (s < g.tiles_is) {
+                    // np.roll: the first K/2 in-phase samples are the clip's last ones (snn_beamformer.py:325)
+                    const IN_T *clip = src[islot];
+                    const float sc = sx[islot];
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {
+                        const int t = kTile * s + 2 * (8 * chunk + i) + ipar;
+                        float x = 0.f;
+                        if (t < T) {
+                            int srci = (t - p.half) % T;
+                            if (srci < 0) srci += T;
+                            x = to_f32<IN_T>(clip[(long long)srci * M + mic]) * sc;
+                        }
+                        v[i] = x;
+                    }
+                } else {
+                    // I[2n] = E[n - H], I[2n+1] = O[n - H + 1]: 8 samples from ring position q0 on
+                    const int q0 = (kTile / 2) * s + 8 * chunk - g.H + ipar;
+                    const int n = islot * C2 + 2 * mic + ipar;
+                    const int c0 = (q0 >> 3) % g.RC, c1 = c0 + 1 == g.RC ? 0 : c0 + 1, b0 = q0 & 7;
+                    const unsigned char *r0 = sm.ring + (c0 * g.NSP + n) * 16, *r1 = sm.ring + (c1 * g.NSP + n) * 16;
+                    if (b0 <= 1) {      // (warp-uniform) K/2 a multiple of 16: the 8 samples start at half 0 or 1 of a chunk
+                        const uint4 h4 = *reinterpret_cast<const uint4 *>(r0), l4 = *reinterpret_cast<const uint4 *>(r0 + g.piece_b);
+                        const unsigned int hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+                        float a[9];
+#pragma unroll
+                        for (int w2 = 0; w2 < 4; ++w2) {
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hw[w2]));
+                            const float2 lf = __half22float2(*reinterpret_cast<const __half2 *>(&lw[w2]));
+                            a[2 * w2] = hf.x + lf.x; a[2 * w2 + 1] = hf.y + lf.y;
+                        }
+                        a[8] = 0.f;
+                        if (b0 == 1)
+                            a[8] = __half2float(*reinterpret_cast<const __half *>(r1)) + __half2float(*reinterpret_cast<const __half *>(r1 + g.piece_b));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = b0 ? a[i + 1] : a[i];
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = b0 + i;
+                            const unsigned char *r = (e < 8 ? r0 : r1) + 2 * (e & 7);
+                            v[i] = __half2float(*reinterpret_cast<const __half *>(r)) + __half2float(*reinterpret_cast<const __half *>(r + g.piece_b));
+                        }
+                    }
+                }
+                float *dst = sm.q + (((s & 1) * kSlots + islot) * C2 + mic) * kQRow + ipar * 32 + 8 * chunk;
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        PH_END(4);
+        // ---- (d) amax scan of the next pair: the slice loaded at the previous step is folded in now, this step's
+        //      slice is requested and not waited for ----
+        if (scan) {
+#pragma unroll
+            for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                for (int u = 0; u < kScanLd; ++u)
+                    mx[c] = fmaxf(fmaxf(mx[c], fmaxf(fabsf(sv[c][u].x), fabsf(sv[c][u].y))), fmaxf(fabsf(sv[c][u].z), fabsf(sv[c][u].w)));
+#pragma unroll
+            for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                for (int u = 0; u < kScanLd; ++u) {
+                    const long long i = scan_i + 32 * u + lane;
+                    sv[c][u] = (i < n4 && (c == 0 || scan_ok1)) ? __ldg(scan_src[c] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            scan_i += 32 * kScanLd;
         }
         ROLE_BARRIER();
     }
-    // amax of the next pair (bit pattern order = magnitude order); ~0 = "not scanned"
+    if (quarter == 1) {
+        // amax of the next pair (bit pattern order = magnitude order); ~0 = "not scanned"
 #pragma unroll
-    for (int c = 0; c < kSlots; ++c) {
-        unsigned int mb = __float_as_uint(mx[c]);
+        for (int c = 0; c < kSlots; ++c) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned int ot = __shfl_xor_sync(0xffffffffu, mb, o); mb = ot > mb ? ot : mb; }
-        if (lane == 0) sm.amax_next[c] = scan ? mb : 0xffffffffu;
+            for (int u = 0; u < kScanLd; ++u)
+                mx[c] = fmaxf(fmaxf(mx[c], fmaxf(fabsf(sv[c][u].x), fabsf(sv[c][u].y))), fmaxf(fabsf(sv[c][u].z), fabsf(sv[c][u].w)));
+            unsigned int mb = __float_as_uint(mx[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned int ot = __shfl_xor_sync(0xffffffffu, mb, o); mb = ot > mb ? ot : mb; }
+            if (lane == 0) sm.amax_next[c] = scan ? mb : 0xffffffffu;
+        }
     }
-    ROLE_TIMER_FLUSH(0);
-    PH_FLUSH(sm.dbg, 0, 4);
+    ROLE_TIMER_FLUSH(quarter);
+    if (quarter == 0) PH_FLUSH(sm.dbg, 0, 5);
 }
-
-// ===== top of a step, serial warps: quadrature tile out of tensor memory, in-phase samples out of the rings, the
-// ===== next audio tile from the staging buffer into the rings =====
-template <typename IN_T, int MM>
-struct StepHook {
-    const TcSmem &sm;
-    const ChainParams &p;
-    const TcGeom &g;
-    const IN_T *__restrict__ audio;
-    long long clip0, B, T64;
-    int role, lane, NT, NJ;
-    uint32_t tmem_cols;
-    uint32_t &tma_phase;
-
-    __device__ __forceinline__ void operator()(int k) const {
-        const int M = MM ? MM : p.M, C2 = 2 * M;
-        const int T = (int)T64;
-        const int s = k - 1;                  // sub-tile the band-pass warp takes at the next step
-        if (s >= 0 && s < NT) {
-            const int J = s >> 1, h = s & 1, buf = J & 1;
-            // ---- Q: row m = 8 (2 mic + parity) + r holds y[8 r + a] of that stream: columns a / 8 + a (taps hi / lo)
-            //      of the hi-piece accumulator and the same of the lo-piece accumulator ----
-            {
-                const int m = 32 * role + lane;
-                const int mic = m >> 4, par = (m >> 3) & 1, r8 = m & 7;
-#pragma unroll
-                for (int slot = 0; slot < kSlots; ++slot) {
-                    if (clip0 + slot >= B) continue;
-                    if (h == 0) mbar_wait(smem_u32(sm.mbar + slot * 2 + buf), (uint32_t)((J >> 1) & 1));
-                    tc_fence_after();
-                    uint32_t r[32];
-                    tc_ld32(tmem_cols + (uint32_t)((slot * 2 + buf) * kColsPerTile) + ((uint32_t)(32 * role) << 16), r);
-                    if ((r8 >> 2) == h && mic < M) {
-                        // even stream -> Q at odd times, odd stream -> Q at even times
-                        float *dst = sm.q + (((s & 1) * kSlots + slot) * C2 + M + mic) * kQRow + (par ? 0 : 32) + 8 * (r8 & 3);
-                        float v[8];
-#pragma unroll
-                        for (int a = 0; a < 8; ++a)
-                            v[a] = (__uint_as_float(r[a]) + __uint_as_float(r[16 + a])) + (__uint_as_float(r[8 + a]) + __uint_as_float(r[24 + a]));
-                        reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    }
-                }
-                tc_fence_before();
-            }
-            // ---- I[t] = x[(t - K/2) mod T] (x 2^14 like Q): warps 0, 1 serve clip slot 0, warps 2, 3 slot 1;
-            //      a lane rebuilds 8 consecutive samples of one (microphone, parity) ----
-            {
-                const int gid = (role & 1) * 32 + lane, slot = role >> 1;
-                if (gid < 8 * M && clip0 + slot < B) {
-                    const int mic = gid >> 3, ipar = (gid >> 2) & 1, chunk = gid & 3;
-                    float v[8];
-                    if (s < g.tiles_is) {
-                        // np.roll: the first K/2 in-phase samples are the clip's last ones (snn_beamformer.py:325)
-                        const IN_T *clip = audio + (clip0 + slot) * T64 * M;
-                        const float sc = sm.scale[slot] * kTapScale;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int t = kTile * s + 2 * (8 * chunk + i) + ipar;
-                            float x = 0.f;
-                            if (t < T) {
-                                int srci = (t - p.half) % T;
-                                if (srci < 0) srci += T;
-                                x = to_f32<IN_T>(clip[(long long)srci * M + mic]) * sc;
-                            }
-                            v[i] = x;
-                        }
-                    } else {
-                        // I[2n] = E[n - H], I[2n+1] = O[n - H + 1]
-                        const int q0 = (kTile / 2) * s + 8 * chunk - g.H + ipar;
-                        const int pos = q0 % g.R;
-                        const __half *hi = reinterpret_cast<const __half *>(sm.ring + (size_t)((slot * 2 + 0) * C2 + 2 * mic + ipar) * g.pitch_b) + pos;
-                        const __half *lo = reinterpret_cast<const __half *>(sm.ring + (size_t)((slot * 2 + 1) * C2 + 2 * mic + ipar) * g.pitch_b) + pos;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = (__half2float(hi[i]) + __half2float(lo[i])) * kTapScale;
-                    }
-                    float *dst = sm.q + (((s & 1) * kSlots + slot) * C2 + mic) * kQRow + ipar * 32 + 8 * chunk;
-                    reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
-                }
-            }
-        }
-        // ---- staging -> rings for the tile of this step: a thread owns two consecutive samples of one stream
-        //      (one 32-bit store per piece).  The positions written were last read by the MMAs of tile J - 1, whose
-        //      completion every serial warp has observed in its epilogue above (this step or the one before). ----
-        {
-            int slot, J;
-            if (tile_of_step(k, NJ, clip0 + 1 < B, slot, J)) {
-                mbar_wait(smem_u32(sm.mbar + 4), tma_phase);
-                tma_phase ^= 1u;
-                const IN_T *stin = reinterpret_cast<const IN_T *>(sm.stin);
-                const int f0 = kMac * J;
-                const int pb = (kTile * J) % g.R;
-                unsigned char *rhi = sm.ring + (size_t)((slot * 2 + 0) * C2) * g.pitch_b;
-                unsigned char *rlo = sm.ring + (size_t)((slot * 2 + 1) * C2) * g.pitch_b;
-                const float s_x = sm.scale[slot];
-                const float *cin = sm.carry + (slot * 2 + ((J + 1) & 1)) * 8;       // x[128 J - 1]: last frame of tile J - 1
-                const int t128 = role * 32 + lane;
-                for (int q = t128; q < M * kTile; q += 128) {
-                    const int mic = q % M, rest = q / M;
-                    const int par = rest & 1, pi = rest >> 1;
-                    const int fa = 4 * pi - par, fb = fa + 2;          // frames of the pair inside the tile (O[n] = x[2n-1])
-                    float u0, u1;
-                    if (fa >= 0) u0 = (f0 + fa < T) ? to_f32<IN_T>(stin[fa * M + mic]) * s_x : 0.f;
-                    else u0 = J > 0 ? cin[mic] : 0.f;
-                    u1 = (f0 + fb < T) ? to_f32<IN_T>(stin[fb * M + mic]) * s_x : 0.f;
-                    const __half2 h2 = __floats2half2_rn(u0, u1);
-                    const float2 hf = __half22float2(h2);
-                    const __half2 l2 = __floats2half2_rn(u0 - hf.x, u1 - hf.y);
-                    const int pos = pb + 2 * pi;
-                    const size_t off = (size_t)(2 * mic + par) * g.pitch_b + 2 * pos;
-                    *reinterpret_cast<__half2 *>(rhi + off) = h2;
-                    *reinterpret_cast<__half2 *>(rlo + off) = l2;
-                    if (pos < kMirror) {
-                        *reinterpret_cast<__half2 *>(rhi + off + 2 * g.R) = h2;
-                        *reinterpret_cast<__half2 *>(rlo + off + 2 * g.R) = l2;
-                    }
-                }
-                if (t128 < M) sm.carry[(slot * 2 + (J & 1)) * 8 + t128] = (f0 + kMac - 1 < T) ? to_f32<IN_T>(stin[(kMac - 1) * M + t128]) * s_x : 0.f;
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(sm.mbar + 5));
-            }
-        }
-    }
-};
 
 // ============ band-pass warp: SOS cascade + running sum + sign / zero masks, lane = slot*16 + channel ============
 // Inputs of sub-tile k-2 come from its q rows (even-time samples, then odd-time samples), in-phase and quadrature alike.
-template <int MM, typename HOOK>
+template <int MM>
 __device__ __forceinline__ void bandpass_role(const TcSmem &sm, const ChainParams &p, long long clip0, long long B,
-                                              long long T64, int lane, int k_last, HOOK hook) {
+                                              long long T64, int lane, int k_last) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
     const int c_slot = lane >> 4, c_ch = lane & 15;
@@ -408,12 +462,14 @@ __device__ __forceinline__ void bandpass_role(const TcSmem &sm, const ChainParam
         sos.b0[k] = p.sos[k][0]; sos.b1[k] = p.sos[k][1]; sos.b2[k] = p.sos[k][2];
         sos.a1[k] = p.sos[k][3]; sos.a2[k] = p.sos[k][4];
     }
+    if (c_ch < M) {     // in-phase rows of q are plain ring samples, quadrature rows carry the 2^14 of the tap matrix:
+        sos.b0[0] *= kTapScale; sos.b1[0] *= kTapScale; sos.b2[0] *= kTapScale;      // exact (power of two)
+    }
     BiquadState bq; biquad_reset(bq);
     float csum = 0.f;
     ROLE_TIMER_DECL;
 
-    for (int k = -1; k <= k_last; ++k) {
-        hook(k);
+    for (int k = sm.k_first; k <= k_last; ++k) {
         const int kc = k - 2;
         const int t0 = kc * kTile;
         if (kc >= 0 && t0 < T && c_valid) {
@@ -474,7 +530,7 @@ __device__ __forceinline__ void bandpass_role(const TcSmem &sm, const ChainParam
 }
 
 // GROUPS = 2: warps 0..3 / 4..7 are the serial roles of group 0 / 1 (warp id mod 4 = role = tensor-memory lane
-// quarter), warps 8, 9 the producers.  GROUPS = 1: warps 0..3 + producer warp 4.
+// quarter), warps 4..7 / 12..15 its front-end warps.
 template <typename IN_T, int MM, int GROUPS>
 __global__ void __launch_bounds__(kGThreads * GROUPS, 1)
 k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const double *__restrict__ Wd,
@@ -487,9 +543,12 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = MM ? MM : p.M, C2 = 2 * M;
-    const int group = warp < 4 * GROUPS ? warp >> 2 : warp - 4 * GROUPS;
-    const int role = warp < 4 * GROUPS ? warp & 3 : kRoleProducer;
-    const int tid = role * 32 + lane;       // thread index inside the group
+    // group = warps 8 group .. + 7: four serial-role warps, then four front-end warps
+    const int group = warp >> 3;
+    const int quarter = warp & 3;           // tensor-memory lanes 32 quarter .. + 31 are this warp's
+    // group 1 runs its serial roles in the opposite order: a sub-partition then holds band-pass + Gram or RZCC + neuron
+    const int role = (warp & 4) ? kRoleFront + quarter : (group == 0 ? quarter : 3 - quarter);
+    const int tid = (warp & 7) * 32 + lane;       // thread index inside the group
     const int bar_id = 1 + group;
     auto group_sync = [&]() { tile_barrier(bar_id, kGThreads); };
 
@@ -516,47 +575,60 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
     sm.rec = GROUPS * (int)blockIdx.x + group;
     double *red_v = reinterpret_cast<double *>(smem_raw + g.off_cs);         // [kGThreads], clip epilogue only
     int *red_i = reinterpret_cast<int *>(smem_raw + g.off_cs + kGThreads * sizeof(double));
-    __half *tapsB = reinterpret_cast<__half *>(smem_all + (size_t)GROUPS * g.smem_group);
 
-    // ---- once per CTA: tap matrix, barriers, tensor memory ----
+    // ---- once per CTA: barriers, tensor memory, the Toeplitz tap matrix into tensor memory ----
     {
-        // B[n][e] = g'[a + lag - e] x 2^14, n = 8 piece + a; g'[d0 + j] = taps[j].  Canonical K-major no-swizzle
-        // layout: element (n, e) at core matrix ((n / 8) (2 ksteps) + e / 8), row n % 8, column e % 8
-        const int Kp = 16 * g.ksteps;
-        for (int e = threadIdx.x; e < kMmaN * Kp; e += blockDim.x) {
-            const int n = e / Kp, kk = e - n * Kp;
-            const int j = (n & 7) + g.lag - kk - g.d0;
-            float v = 0.f;
-            if (j >= 0 && j < p.n_taps) {
-                const float gs = taps[j] * kTapScale;
-                const float hi = __half2float(__float2half_rn(gs));
-                v = (n >> 3) == 0 ? hi : gs - hi;
-            }
-            tapsB[((n >> 3) * 2 * g.ksteps + (kk >> 3)) * 64 + (n & 7) * 8 + (kk & 7)] = __float2half_rn(v);
-        }
         if (tid == 0) {
             mbar_init(smem_u32(sm.mbar + 4), 1);
-            mbar_init(smem_u32(sm.mbar + 5), 4);        // one arrival per serial warp
-            for (int i = 0; i < 4; ++i) mbar_init(smem_u32(sm.mbar + i), 1);
+            for (int i = 0; i < 2; ++i) mbar_init(smem_u32(sm.mbar + i), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(4 * kColsPerTile * GROUPS) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem)) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
-        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // A[a][e] = g'[a + lag - e] x 2^14 (g'[d0 + j] = taps[j]) as fp16 hi (columns 8 ks + c) and lo (columns
+        // 8 (ksteps + ks) + c): lane a, column c of K step ks holds e = 16 ks + 2 c (low half) and e + 1
+        if (warp < 4) {       // (warp w writes tensor-memory lanes 32 (w % 4) ..)
+            const int a = 32 * warp + lane;
+            for (int ks = 0; ks < g.ksteps; ++ks) {
+                uint32_t rh[8], rl[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    unsigned short hh[2], ll[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = a + g.lag - (16 * ks + 2 * c + u) - g.d0;
+                        const float gs = (j >= 0 && j < p.n_taps) ? taps[j] * kTapScale : 0.f;
+                        const __half hi = __float2half_rn(gs);
+                        hh[u] = __half_as_ushort(hi);
+                        ll[u] = __half_as_ushort(__float2half_rn(gs - __half2float(hi)));
+                    }
+                    rh[c] = (uint32_t)hh[0] | ((uint32_t)hh[1] << 16);
+                    rl[c] = (uint32_t)ll[0] | ((uint32_t)ll[1] << 16);
+                }
+                tc_st8(s_tmem + 8u * (uint32_t)ks + ((uint32_t)(32 * warp) << 16), rh);
+                tc_st8(s_tmem + 8u * (uint32_t)(g.ksteps + ks) + ((uint32_t)(32 * warp) << 16), rl);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
     }
-    const uint32_t tmem_cols = s_tmem + (uint32_t)(group * 4 * kColsPerTile);
-    uint32_t tma_phase = 0, ring_phase = 0;
+    const uint32_t tmem_a = s_tmem;
+    const uint32_t tmem_d = s_tmem + 16u * (uint32_t)g.ksteps + (uint32_t)(group * 2 * kMmaN);
+    uint32_t tma_phase = 0;
 
     const int NT = (int)((T + kTile - 1) / kTile);
     const int NJ = (int)((T + kMac - 1) / kMac);
     const int k_last = NT + g.dtile;    // the Gram warp runs dtile + 1 steps behind
+    sm.k_first = -1 - kLead;            // the producer side starts kLead steps ahead
     const long long npairs = (B + kSlots - 1) / kSlots;
-    const int ring_words = (4 * C2 + 2) * g.pitch_b / 4;
+    const int ring_words = 2 * g.piece_b / 4;
 
     // Clip pairs are handed out dynamically, one ahead: while a group works on a pair its producer warp scans the
     // next one for its largest magnitude (the fp16 scale of float32 clips)
@@ -578,7 +650,7 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
             for (int i = tid; i < 2 * kRingWords * 32; i += kGThreads) sm.bits[i] = 0u;
             for (int i = tid; i < 2 * 2 * kVmRows * kVmPitch / 2; i += kGThreads) reinterpret_cast<unsigned int *>(sm.vms)[i] = 0u;
             if (tid == 0) {
-                for (int i = 0; i < 4; ++i) { mbar_inval(smem_u32(sm.mbar + i)); mbar_init(smem_u32(sm.mbar + i), 1); }
+                for (int i = 0; i < 2; ++i) { mbar_inval(smem_u32(sm.mbar + i)); mbar_init(smem_u32(sm.mbar + i), 1); }
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
         }
@@ -613,14 +685,13 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
         if (tid < kSlots) sm.scale[tid] = clip_scale<IN_T>(scanned ? sm.amax_next[tid] : sm.amax[tid]);
         group_sync();
 
-        const StepHook<IN_T, MM> hook{sm, p, g, audio, clip0, B, T, role, lane, NT, NJ, tmem_cols, tma_phase};
-        if (role == kRoleProducer)
-            producer_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, lane, NJ, k_last, tmem_cols, smem_u32(tapsB), ring_phase,
-                                    next_pair < npairs ? next_pair * kSlots : -1);
-        else if (role == 0) bandpass_role<MM>(sm, p, clip0, B, T, lane, k_last, hook);
-        else if (role == 1) rzcc_role<TcSmem, kRingWords>(sm, p, flags, clip0, B, T, M, lane, k_last, hook);
-        else if (role == 2) neuron_role<TcSmem, TcGeom, kRingWords>(sm, p, g, clip0, B, T, M, lane, k_last, hook);
-        else gram_role<TcSmem, TcGeom>(sm, g, spikes, clip0, B, T, M, lane, k_last, hook);
+        if (role >= kRoleFront)
+            front_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, quarter, lane, NT, NJ, k_last, tmem_a, tmem_d, tma_phase,
+                                 3 + group, next_pair < npairs ? next_pair * kSlots : -1);
+        else if (role == 0) bandpass_role<MM>(sm, p, clip0, B, T, lane, k_last);
+        else if (role == 1) rzcc_role<TcSmem, kRingWords>(sm, p, flags, clip0, B, T, M, lane, k_last);
+        else if (role == 2) neuron_role<TcSmem, TcGeom, kRingWords>(sm, p, g, clip0, B, T, M, lane, k_last);
+        else gram_role<TcSmem, TcGeom>(sm, g, spikes, clip0, B, T, M, lane, k_last);
         group_sync();
         // ---- clip epilogue: power[g] = w_g^T C w_g / T (float64), DoA = first argmax ----
         const double inv_T = 1.0 / (double)T;
@@ -670,7 +741,7 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "n"(4 * kColsPerTile * GROUPS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(s_tmem) : "memory");
 }
 
 static bool make_geom(const ChainParams &p, int dtype, int groups, TcGeom &g) {
@@ -679,16 +750,18 @@ static bool make_geom(const ChainParams &p, int dtype, int groups, TcGeom &g) {
     g.H = p.half / 2;
     const int ntd = g.d0 + p.n_taps;                    // dense polyphase taps incl. leading zeros
     g.lag = (ntd - 1 + 15) / 16 * 16;
-    g.ksteps = (g.lag + 8 + 15) / 16;
-    int need = g.lag + kTile;                           // MMA window of the tile being filled
-    if (g.H + 2 * kTile > need) need = g.H + 2 * kTile; // in-phase read-back of the serial warps
-    g.R = (need + kTile - 1) / kTile * kTile;
-    g.pitch_b = 2 * (g.R + kMirror);
+    g.ksteps = (g.lag + kBlk) / 16;
+    // a window (lag + 128 samples) plus the audio tile being converted; the in-phase read-back needs less
+    g.RC = (g.lag + kBlk) / 8 + kTile / 8;
+    if (g.RC * 8 < g.H + 3 * kTile) g.RC = (g.H + 3 * kTile + 7) / 8;
+    g.RC = (g.RC + 1) & ~1;
+    g.NSP = kSlots * p.C2;
+    g.piece_b = g.RC * g.NSP * 16;
     g.dtile = 4 + (rzcc_lag(p.w) - 1 + kTile - 1) / kTile;
     g.tiles_is = (p.half + kTile - 1) / kTile;
     const int esz = dtype == MICLOC_I16 ? 2 : 4;
     int off = 0;
-    g.off_ring = off; off += (4 * p.C2 + 2) * g.pitch_b;
+    g.off_ring = off; off += 2 * g.piece_b + 128;       // (the last stream group of the last chunk reads a few bytes on)
     off = (off + 127) & ~127;
     g.off_stin = off; off += kMac * p.M * esz;
     off = (off + 15) & ~15;
@@ -701,7 +774,7 @@ static bool make_geom(const ChainParams &p, int dtype, int groups, TcGeom &g) {
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
     g.off_misc = off; off += 256;
     g.smem_group = (off + 127) & ~127;
-    g.smem_bytes = groups * g.smem_group + kMmaN * 16 * g.ksteps * (int)sizeof(__half);
+    g.smem_bytes = groups * g.smem_group;
     return true;
 }
 
@@ -744,8 +817,11 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
     // the spike-bit ring must hold the back warp's oldest read and the front warp's newest write
     if (kTile * (g.dtile - 2) + p.nL + kSeg > kRingWords * 32)
         return set_error(MICLOC_ERR_UNSUPPORTED, "robust_width %d / neuron length %d exceed the tensor-core kernel's spike ring", p.w, p.nL);
-    if (kSlots * 256 * (int)sizeof(double) > 4 * p.C2 * g.pitch_b)
+    if (kSlots * 256 * (int)sizeof(double) > 2 * g.piece_b)
         return set_error(MICLOC_ERR_UNSUPPORTED, "shared-memory rings too small for the epilogue");
+    // tensor memory: the tap matrix (two pieces of 8 columns per K step) + two accumulator buffers per group
+    if (16 * g.ksteps + groups * 2 * kMmaN > 512)
+        return set_error(MICLOC_ERR_UNSUPPORTED, "STHT kernel of %d taps does not fit the tensor memory", p.n_taps);
     if (T + 16 * kTile >= (1ll << 31)) return set_error(MICLOC_ERR_SHAPE, "T too large for the fused kernel");
 #define MICLOC_TC_CASE(IN, MMV)                                                                                   \
     do {                                                                                                          \
