@@ -47,6 +47,13 @@ class XyloConfig(C.Structure):
     ]
 
 
+class SynthConfig(C.Structure):
+    _fields_ = [
+        ("num_mic", _i32), ("r_vec", _dp), ("theta_vec", _dp), ("fs", C.c_double), ("speed", C.c_double),
+        ("clip_len", _i64), ("n_targets", _i32), ("mode", _i32), ("source_kind", _i32), ("sine_freq", C.c_double),
+    ]
+
+
 # every symbol include/micloc_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "micloc_snn_create": (C.c_int, [C.POINTER(SnnConfig), C.c_int, C.POINTER(_vp)]),
@@ -57,6 +64,8 @@ SYMBOLS = {
     "micloc_snn_run_host": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, C.c_int]),
     "micloc_snn_gram": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp]),
     "micloc_doa_histogram": (C.c_int, [_vp, _i64, _i32, _vp, C.c_int, _vp]),
+    "micloc_synth_clips": (C.c_int, [C.POINTER(SynthConfig), _i64, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp,
+                                     C.c_float, _vp, C.c_int, _vp]),
     "micloc_rzcc_encode_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, C.c_int, _vp]),
     "micloc_hilbert_beamform": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _dp, _dp, _i32, _vp, _vp, _vp, _vp]),
     "micloc_xylo_create": (C.c_int, [C.POINTER(XyloConfig), C.c_int, C.POINTER(_vp)]),

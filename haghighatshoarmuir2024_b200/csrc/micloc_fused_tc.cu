@@ -232,6 +232,12 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
     float mx[kSlots] = {0.f, 0.f};
     long long scan_i = 0;
 
+    // ring coordinates kept incrementally (a runtime modulo costs ~25 instructions and this loop is instruction-fetch bound)
+    int cbase[kSlots] = {0, 0};               // ring chunk of the next audio tile's first sample, per clip slot
+    int cwin = -(g.lag / 8) % g.RC;           // ring chunk of the first window sample of the MMA tile being issued
+    if (cwin < 0) cwin += g.RC;
+    int ibase = ((4 * (sm.k_first - 2) - g.H / 8) % g.RC + g.RC) % g.RC;     // chunk of stream sample 32 s - H of the step before the first (s = k - 1)
+
     if (quarter == 0) issue_load(0, 0);
     for (int k = sm.k_first; k <= k_last; ++k) {
         int it, slot, J;
@@ -246,7 +252,9 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
             tma_phase ^= 1u;
             PH_END(0);
             const int f0 = kMac * J;
-            const int cb = (8 * J) % g.RC;          // ring chunk of the tile's first stream position
+            const int cb = slot ? cbase[1] : cbase[0];      // ring chunk of the tile's first stream position
+            if (slot) { cbase[1] += 8; if (cbase[1] >= g.RC) cbase[1] -= g.RC; }
+            else { cbase[0] += 8; if (cbase[0] >= g.RC) cbase[0] -= g.RC; }
             const float s_x = sx[slot];
             // thread (j, parity, mic) builds chunk j of its stream: samples 8 j .. 8 j + 7 = frames
             // 16 j - parity + 2 i (O[n] = x[2n-1]: the odd stream's first sample is the previous tile's last frame)
@@ -255,15 +263,11 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 const int par = sidx >= M ? 1 : 0, mic = sidx - par * M;
                 const IN_T *sp = stin + (16 * j - par) * M + mic;
                 float u[8];
-                if (f0 + kMac <= T) {
+                const int fmax = T - f0;                  // frames of the tile inside the clip (>= kMac for whole tiles)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) u[i] = (i > 0 || j > 0 || par == 0) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int f = 16 * j - par + 2 * i;
-                        u[i] = (f >= 0 && f0 + f < T) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const int f = 16 * j - par + 2 * i;
+                    u[i] = (f >= 0 && f < fmax) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
                 }
                 if (j == 0 && par == 1) u[0] = J > 0 ? sm.carry[(slot * 2 + ((J + 1) & 1)) * 8 + mic] : 0.f;   // x[128 J - 1]
                 uint4 h4, l4;
@@ -293,8 +297,9 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
         //      rest + commit.  (tcgen05.mma blocks its warp while the tensor core's queue is full.) ----
         if (quarter == 0 && valid) {
             int i2, s2, J2;
-            if (tile_of_step(k + 1, NJ, ok1, i2, s2, J2)) issue_load(s2, J2);
-            else if (tile_of_step(k + 2, NJ, ok1, i2, s2, J2)) issue_load(s2, J2);
+            bool have = tile_of_step(k + 1, NJ, ok1, i2, s2, J2);
+            if (!have) have = tile_of_step(k + 2, NJ, ok1, i2, s2, J2);
+            if (have) issue_load(s2, J2);
         }
         if (quarter == 3) {
             const int Jb = it >> 2, part = it & 3;
@@ -305,15 +310,15 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t d = tmem_d + (uint32_t)((Jb & 1) * kMmaN);
-                    int c = ((16 * Jb) % g.RC - g.lag / 8 + 2 * ks0) % g.RC;          // chunk of K step ks0
-                    if (c < 0) c += g.RC;
+                    int c = cwin + 2 * ks0;          // chunk of K step ks0
+                    if (c >= g.RC) c -= g.RC;
                     const uint32_t rb_hi = smem_u32(sm.ring), rb_lo = rb_hi + (uint32_t)g.piece_b;
                     const uint32_t chunk_b = (uint32_t)g.NSP * 16u;
                     // B: K-major, no swizzle: 8 streams x 16 bytes per core matrix, next 8 streams 128 bytes on,
                     // next chunk (K) NSP * 16 bytes on
                     const uint64_t b_fix = make_desc(0u, chunk_b, 128u);
                     const uint32_t a_lo = tmem_a + 8u * (uint32_t)g.ksteps;
-#pragma unroll 2
+#pragma unroll 1
                     for (int ks = ks0; ks < ks1; ++ks) {
                         const uint32_t off = ((uint32_t)c * chunk_b) >> 4;
                         const uint64_t b_hi = b_fix | (uint64_t)(((rb_hi >> 4) + off) & 0x3FFFu);
@@ -328,10 +333,13 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 }
                 __syncwarp();
             }
+            if (part == 3) { cwin += 16; if (cwin >= g.RC) cwin -= g.RC; }
         }
         PH_END(2);
         // ---- (c) sub-tile s = k - 1 -> q rows ----
         const int s = k - 1;
+        ibase += 4;
+        if (ibase >= g.RC) ibase -= g.RC;
         if (s >= 0 && s < NT) {
             // Q: accumulator row a = stream sample a of MMA tile Jb, column n = stream; the 32 samples of this
             // sub-tile are lanes 32 (s & 3) ..: the warp that owns them stores column after column
@@ -379,7 +387,10 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                     // I[2n] = E[n - H], I[2n+1] = O[n - H + 1]: 8 samples from ring position q0 on
                     const int q0 = (kTile / 2) * s + 8 * chunk - g.H + ipar;
                     const int n = islot * C2 + 2 * mic + ipar;
-                    const int c0 = (q0 >> 3) % g.RC, c1 = c0 + 1 == g.RC ? 0 : c0 + 1, b0 = q0 & 7;
+                    const int b0 = q0 & 7;
+                    int c0 = (g.H & 7) == 0 ? ibase + chunk : (q0 >> 3) % g.RC;
+                    if (c0 >= g.RC) c0 -= g.RC;
+                    const int c1 = c0 + 1 == g.RC ? 0 : c0 + 1;
                     const unsigned char *r0 = sm.ring + (c0 * g.NSP + n) * 16, *r1 = sm.ring + (c1 * g.NSP + n) * 16;
                     if (b0 <= 1) {      // (warp-uniform) K/2 a multiple of 16: the 8 samples start at half 0 or 1 of a chunk
                         const uint4 h4 = *reinterpret_cast<const uint4 *>(r0), l4 = *reinterpret_cast<const uint4 *>(r0 + g.piece_b);
@@ -546,8 +557,9 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
     // group = warps 8 group .. + 7: four serial-role warps, then four front-end warps
     const int group = warp >> 3;
     const int quarter = warp & 3;           // tensor-memory lanes 32 quarter .. + 31 are this warp's
-    // group 1 runs its serial roles in the opposite order: a sub-partition then holds band-pass + Gram or RZCC + neuron
-    const int role = (warp & 4) ? kRoleFront + quarter : (group == 0 ? quarter : 3 - quarter);
+    // the same role of both groups runs on the same SM sub-partition (warp id mod 4): the two warps share the lines of the
+    // sub-partition's instruction cache -- instruction fetch is what the warps of this kernel stall on first
+    const int role = (warp & 4) ? kRoleFront + quarter : quarter;
     const int tid = (warp & 7) * 32 + lane;       // thread index inside the group
     const int bar_id = 1 + group;
     auto group_sync = [&]() { tile_barrier(bar_id, kGThreads); };

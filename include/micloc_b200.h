@@ -110,6 +110,37 @@ int micloc_snn_gram(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B
 int micloc_doa_histogram(const int32_t *doa_dev, int64_t B, int32_t G, int64_t *hist_dev, int device,
                          void *stream);
 
+/* ---- Monte-Carlo input synthesis ------------------------------ */
+/* Synthetic array clips on the device, as the reference builds them on the host:
+ *   mode 0  SNNBeamformer.apply_to_template (micloc/snn_beamformer.py:243-275): per-microphone delays
+ *           -r cos(theta_m - doa)/c minus their minimum, x[t][m] = interp(t - delay_m) clamped at t_min
+ *   mode 1  signal_multiple_targets (paper_plots/multiple_targets_snn.py:87-159): x[t][m] = sum_k gain_k
+ *           interp(t + delay_{k,m}), un-normalised delays, np.interp's clamping at both ends
+ * followed by AWGN of sigma = sqrt(mean(x^2)) / sqrt(snr) per clip (snn_beamformer.py:270-275).
+ *   source_kind 0: table src_dev [S][clip_len] f32 on the clip's own sample grid (chirp, filtered noise, ...);
+ *                  clip b uses row src_index_dev[b] (row 0 when src_index_dev is NULL)
+ *   source_kind 1: sine of sine_freq sampled at fs (paper_plots/target_snn_localization.py:439-441)
+ *   doa_dev [B][n_targets] f64 rad; gain_dev [B][n_targets] f32 (NULL = 1); snr_lin_dev [B] f32 linear SNR (NULL = no noise)
+ *   out_f32_dev [B][clip_len][num_mic] always written; out_i16_dev (nullable) = round(x * int16_peak / max|x|) per clip
+ *   scratch_dev: B * 12 bytes (8-byte aligned).  B <= 65535 per call.  Noise: Philox4x32-10, `seed`. */
+typedef struct {
+    int32_t num_mic;
+    const double *r_vec;        /* [num_mic] radius of every microphone   array_geometry.py:32-37 */
+    const double *theta_vec;    /* [num_mic] angle of every microphone                            */
+    double fs;
+    double speed;               /* 340 m/s                                array_geometry.py:14    */
+    int64_t clip_len;           /* T */
+    int32_t n_targets;
+    int32_t mode;               /* 0 apply_to_template, 1 signal_multiple_targets */
+    int32_t source_kind;        /* 0 table, 1 sine */
+    double sine_freq;
+} micloc_synth_config;
+
+int micloc_synth_clips(const micloc_synth_config *cfg, int64_t B, const float *src_dev,
+                       const int32_t *src_index_dev, const double *doa_dev, const float *gain_dev,
+                       const float *snr_lin_dev, uint64_t seed, float *out_f32_dev, int16_t *out_i16_dev,
+                       float int16_peak, double *scratch_dev, int device, void *stream);
+
 /* ---- stand-alone stages ---------------------------------------------------- */
 /* ZeroCrossingSpikeEncoder.evolve on arbitrary float64 input, exact find_peaks
  * semantics (unbounded clusters).  sig_dev [B][T][C] f64 -> spikes_dev [B][T][C] int8. */
