@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # MICLOC_B200_LIB points the loader at an instrumented build of the same library (tools/role_timing.py)
 LIB_PATH = os.environ.get("MICLOC_B200_LIB") or os.path.join(CSRC, "libmicloc_b200.so")
 
-F32, I16 = 0, 1
+F32, I16, I32 = 0, 1, 2
 ERR_SHAPE, ERR_CONFIG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = -1, -2, -3, -4, -5
 
 _dp = C.POINTER(C.c_double)
@@ -64,6 +64,13 @@ SYMBOLS = {
     "micloc_snn_run_host": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, C.c_int]),
     "micloc_snn_gram": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp]),
     "micloc_doa_histogram": (C.c_int, [_vp, _i64, _i32, _vp, C.c_int, _vp]),
+    "micloc_snn_stream_create": (C.c_int, [_vp, _i64, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "micloc_snn_stream_destroy": (C.c_int, [_vp]),
+    "micloc_snn_stream_reset": (C.c_int, [_vp, _vp]),
+    "micloc_snn_stream_latency": (C.c_int, [_vp]),
+    "micloc_snn_stream_push": (C.c_int, [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "micloc_snn_stream_flush": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i32), _vp]),
+    "micloc_envelope": (C.c_int, [_vp, _i64, _i32, C.c_double, C.c_double, C.c_double, _vp, _vp, C.c_int, _vp]),
     "micloc_synth_clips": (C.c_int, [C.POINTER(SynthConfig), _i64, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp,
                                      C.c_float, _vp, C.c_int, _vp]),
     "micloc_rzcc_encode_f64": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, C.c_int, _vp]),

@@ -185,6 +185,12 @@ extern "C" int micloc_snn_destroy(micloc_snn *c) {
     return MICLOC_OK;
 }
 
+int micloc_snn_get_params(micloc_snn *c, micloc_snn_params *out) {
+    if (!c || !out) return set_error(MICLOC_ERR_CONFIG, "null context");
+    out->chain = c->p; out->taps_dev = c->d_taps; out->bf_f32_dev = c->d_W; out->bf_f64_dev = c->d_Wd; out->device = c->device;
+    return MICLOC_OK;
+}
+
 extern "C" int micloc_snn_set_bf(micloc_snn *c, const double *bf, int32_t G) {
     if (!c || !bf || G < 1) return set_error(MICLOC_ERR_CONFIG, "bad bf_mat");
     MICLOC_CUDA(cudaSetDevice(c->device));

@@ -56,6 +56,19 @@ constexpr size_t kSlotWords = kSlotCta + 2 * 16 * 512;
 constexpr int kSlotResetWords = kSlotDbg;
 
 int setup_stht(ChainParams &p, const double *h, int K, float **d_taps);
+}  // namespace micloc
+
+// what a stream (micloc_stream.cu) takes over from its parent context; valid until the context's bf_mat is replaced
+struct micloc_snn_params {
+    micloc::ChainParams chain;
+    const void *taps_dev;       // float [n_taps]
+    const void *bf_f32_dev;     // float [2M][G]
+    const void *bf_f64_dev;     // double [2M][G]
+    int device;
+};
+int micloc_snn_get_params(micloc_snn *ctx, micloc_snn_params *out);
+
+namespace micloc {
 int sos_to_f32(const double *sos, int nsec, float *out);
 int launch_stht_any(const ChainParams &p, const float *d_taps, const void *audio, int dtype, float *q,
                     long long B, long long T, cudaStream_t st);

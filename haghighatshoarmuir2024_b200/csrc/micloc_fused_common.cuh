@@ -289,7 +289,7 @@ __device__ __forceinline__ void gram_role(const SMEM &sm, const GEOM &g, int8_t 
             for (int s = 0; s < kSlots; ++s) {
                 const unsigned addr = (unsigned)__cvta_generic_to_shared(vm + s * 16 * kVmPitch);
                 const unsigned lo_off = 2 * kVmRows * kVmPitch * (unsigned)sizeof(__half);
-#pragma unroll
+#pragma unroll 1     // (a rolled loop: the fused kernels stall on instruction fetch before anything else)
                 for (int ks = 0; ks < kTile / 16; ++ks) {
                     unsigned hi[4], lo[4];
                     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -324,9 +324,11 @@ __device__ __forceinline__ void gram_role(const SMEM &sm, const GEOM &g, int8_t 
                 const int nbytes = nrow * C2;
                 if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nbytes & 15) == 0 &&
                     ((kTile * C2) & 15) == 0) {
+#pragma unroll 1
                     for (int v = lane; v < nbytes / 16; v += 32)
                         reinterpret_cast<int4 *>(dst)[v] = reinterpret_cast<const int4 *>(src)[v];
                 } else {
+#pragma unroll 1
                     for (int e = lane; e < nbytes; e += 32) dst[e] = src[e];
                 }
             }

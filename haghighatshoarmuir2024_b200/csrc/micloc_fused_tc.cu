@@ -92,11 +92,38 @@ struct TcSmem {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_inval(uint32_t a) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok)
+// (a wait that never completes is a pipeline bug: trap after a few seconds instead of hanging the GPU)
+#ifdef MICLOC_WAIT_DEBUG
+__device__ unsigned long long g_wait_dbg[8];      // first wait that timed out: tag, block, thread, parity
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity, int tag = 0) {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#ifdef MICLOC_WAIT_DEBUG
+        if (!ok && *(volatile unsigned long long *)&g_wait_dbg[0] != 0ull) return;      // somebody timed out: let the kernel drain
+#endif
+        if (!ok && ++spins > (1u << 21)) {
+#ifdef MICLOC_WAIT_DEBUG
+            if (atomicCAS(&g_wait_dbg[0], 0ull, (unsigned long long)(tag + 1)) == 0ull) {
+                g_wait_dbg[1] = blockIdx.x; g_wait_dbg[2] = threadIdx.x; g_wait_dbg[3] = parity; g_wait_dbg[4] = a;
+                unsigned long long w;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(a));
+                g_wait_dbg[5] = w;
+                // progress words of the group's MMA thread sit 16 and 24 bytes behind mbarrier 4 (misc + 48, + 56)
+                const uint32_t base = a & ~127u;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(base + 48u));
+                g_wait_dbg[6] = w;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(base + 56u));
+                g_wait_dbg[7] = w;
+            }
+            return;
+#else
+            __trap();
+#endif
+        }
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
@@ -173,12 +200,42 @@ __device__ __forceinline__ bool tile_of_step(int k, int NJ, bool ok1, int &it, i
     return J < NJ && (slot == 0 || ok1);
 }
 
+// Rare paths of the front end, kept out of line (the loop below runs once per step and is instruction-fetch bound):
+// an audio tile that is ragged or not 16-byte aligned goes to the staging buffer with plain loads, zero-filled
+// behind the clip end
+template <typename IN_T>
+__device__ __noinline__ void stage_tile_plain(IN_T *stin, const IN_T *s, int nvalid, int total, int lane) {
+    for (int e = lane; e < total; e += 32) stin[e] = e < nvalid ? s[e] : (IN_T)0;
+}
+// in-phase samples of the first K/2 frames come from the clip's tail (np.roll, snn_beamformer.py:325)
+template <typename IN_T>
+__device__ __noinline__ void inphase_from_tail(float *dst, const IN_T *clip, int t0, int T, int half, int M, int mic, float sc) {
+    for (int i = 0; i < 8; ++i) {
+        const int t = t0 + 2 * i;
+        float x = 0.f;
+        if (t < T) {
+            int srci = (t - half) % T;
+            if (srci < 0) srci += T;
+            x = to_f32<IN_T>(clip[(long long)srci * M + mic]) * sc;
+        }
+        dst[i] = x;
+    }
+}
+// in-phase samples from the rings when K/2 is not a multiple of 16 (the 8 samples start anywhere in a chunk)
+__device__ __noinline__ void inphase_from_ring_any(float *dst, const unsigned char *r0, const unsigned char *r1, int piece_b, int b0) {
+    for (int i = 0; i < 8; ++i) {
+        const int e = b0 + i;
+        const unsigned char *r = (e < 8 ? r0 : r1) + 2 * (e & 7);
+        dst[i] = __half2float(*reinterpret_cast<const __half *>(r)) + __half2float(*reinterpret_cast<const __half *>(r + piece_b));
+    }
+}
+
 template <typename IN_T, int MM>
 __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &p, const TcGeom &g,
                                            const IN_T *__restrict__ audio, long long clip0, long long B,
                                            long long T64, int quarter, int lane, int NT, int NJ, int k_last,
-                                           uint32_t tmem_a, uint32_t tmem_d, uint32_t &tma_phase, int front_bar,
-                                           long long next_clip0) {
+                                           uint32_t tmem_a, uint32_t tmem_d, uint32_t &tma_phase, uint32_t (&mma_base)[2],
+                                           int front_bar, long long next_clip0) {
     const int M = MM ? MM : p.M, C2 = 2 * M;
     const int T = (int)T64;
     const bool ok1 = clip0 + 1 < B;
@@ -207,8 +264,7 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 tma_bulk_g2s(stin_a, s, tile_bytes, bar_tma);
             }
         } else {
-            const int nvalid = (T - f0 < kMac ? T - f0 : kMac) * M;
-            for (int e = lane; e < kMac * M; e += 32) stin[e] = e < nvalid ? s[e] : (IN_T)0;
+            stage_tile_plain<IN_T>(stin, s, (T - f0 < kMac ? T - f0 : kMac) * M, kMac * M, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tma);
         }
@@ -247,8 +303,8 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
         //      Jb) or Jb - 2 (first half): issued 3 or more steps ago, observed here ----
         if (valid) {
             const int Jw = (it >> 2) - ((it & 2) ? 1 : 2);
-            if (Jw >= 0) mbar_wait(smem_u32(sm.mbar + (Jw & 1)), (uint32_t)((Jw >> 1) & 1));
-            mbar_wait(bar_tma, tma_phase);
+            if (Jw >= 0) mbar_wait(smem_u32(sm.mbar + (Jw & 1)), (mma_base[Jw & 1] + (uint32_t)(Jw >> 1)) & 1u, 100000 + (k + 8));
+            mbar_wait(bar_tma, tma_phase, 200000 + (k + 8));
             tma_phase ^= 1u;
             PH_END(0);
             const int f0 = kMac * J;
@@ -291,22 +347,91 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
         }
         PH_END(1);
         front_sync();
-        // ---- (b) next audio tile (warp 0); MMAs (warp 3, one lane).  The K steps of MMA tile Jb are issued as their
-        //      samples arrive: behind the tile's 2nd audio tile the steps over the history (the accumulator buffer was
-        //      read out at the previous step), behind the 3rd those over the first 64 new samples, behind the 4th the
-        //      rest + commit.  (tcgen05.mma blocks its warp while the tensor core's queue is full.) ----
+        // ---- (b) next audio tile on its way (warp 0) ----
         if (quarter == 0 && valid) {
             int i2, s2, J2;
             bool have = tile_of_step(k + 1, NJ, ok1, i2, s2, J2);
             if (!have) have = tile_of_step(k + 2, NJ, ok1, i2, s2, J2);
             if (have) issue_load(s2, J2);
         }
+        PH_END(2);
+        // ---- (c) sub-tile s = k - 1 -> q rows ----
+        const int s = k - 1;
+        ibase += 4;
+        if (ibase >= g.RC) ibase -= g.RC;
+        if (s >= 0 && s < NT) {
+            // Q: accumulator row a = stream sample a of MMA tile Jb, column n = stream; the 32 samples of this
+            // sub-tile are lanes 32 (s & 3) ..: the warp that owns them stores column after column
+            if ((s & 3) == quarter) {
+                const int Jb = s >> 2;
+                mbar_wait(smem_u32(sm.mbar + (Jb & 1)), (mma_base[Jb & 1] + (uint32_t)(Jb >> 1)) & 1u, 300000 + (k + 8));
+                tc_fence_after();
+                uint32_t r[32];
+                tc_ld32(tmem_d + (uint32_t)((Jb & 1) * kMmaN) + ((uint32_t)(32 * quarter) << 16), r);
+                tc_fence_before();
+                float *qb = sm.q + (s & 1) * kSlots * C2 * kQRow + lane;
+#pragma unroll
+                for (int n = 0; n < 2 * kRows * kSlots; ++n) {
+                    // stream n = slot * 2M + 2 mic + parity: even stream -> Q at odd times, odd stream -> Q at even times
+                    if (n < kSlots * C2) {
+                        const int slot2 = n / C2, rem = n - slot2 * C2;
+                        if (clip0 + slot2 < B)
+                            qb[(slot2 * C2 + M + (rem >> 1)) * kQRow + ((rem & 1) ? 0 : 32)] = __uint_as_float(r[n]);
+                    }
+                }
+            }
+            PH_END(3);
+            // I[t] = x[(t - K/2) mod T] (scaled like the ring samples; the band-pass warp applies the 2^14 of the
+            // taps): warp quarter = (clip slot, parity); a lane rebuilds 8 consecutive samples of one microphone
+            const int islot = quarter >> 1, ipar = quarter & 1;
+            if (lane < 4 * M && clip0 + islot < B) {
+                const int mic = lane >> 2, chunk = lane & 3;
+                float *dst = sm.q + (((s & 1) * kSlots + islot) * C2 + mic) * kQRow + ipar * 32 + 8 * chunk;
+                if (s < g.tiles_is) {
+                    inphase_from_tail<IN_T>(dst, src[islot], kTile * s + 16 * chunk + ipar, T, p.half, M, mic, sx[islot]);
+                } else {
+                    // I[2n] = E[n - H], I[2n+1] = O[n - H + 1]: 8 samples from ring position q0 on
+                    const int q0 = (kTile / 2) * s + 8 * chunk - g.H + ipar;
+                    const int n = islot * C2 + 2 * mic + ipar;
+                    const int b0 = q0 & 7;
+                    int c0 = (g.H & 7) == 0 ? ibase + chunk : (q0 >> 3) % g.RC;
+                    if (c0 >= g.RC) c0 -= g.RC;
+                    const int c1 = c0 + 1 == g.RC ? 0 : c0 + 1;
+                    const unsigned char *r0 = sm.ring + (c0 * g.NSP + n) * 16, *r1 = sm.ring + (c1 * g.NSP + n) * 16;
+                    if (b0 <= 1) {      // (warp-uniform) K/2 a multiple of 16: the 8 samples start at half 0 or 1 of a chunk
+                        const uint4 h4 = *reinterpret_cast<const uint4 *>(r0), l4 = *reinterpret_cast<const uint4 *>(r0 + g.piece_b);
+                        const unsigned int hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+                        float a[9];
+#pragma unroll
+                        for (int w2 = 0; w2 < 4; ++w2) {
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hw[w2]));
+                            const float2 lf = __half22float2(*reinterpret_cast<const __half2 *>(&lw[w2]));
+                            a[2 * w2] = hf.x + lf.x; a[2 * w2 + 1] = hf.y + lf.y;
+                        }
+                        a[8] = 0.f;
+                        if (b0 == 1)
+                            a[8] = __half2float(*reinterpret_cast<const __half *>(r1)) + __half2float(*reinterpret_cast<const __half *>(r1 + g.piece_b));
+                        reinterpret_cast<float4 *>(dst)[0] = b0 ? make_float4(a[1], a[2], a[3], a[4]) : make_float4(a[0], a[1], a[2], a[3]);
+                        reinterpret_cast<float4 *>(dst)[1] = b0 ? make_float4(a[5], a[6], a[7], a[8]) : make_float4(a[4], a[5], a[6], a[7]);
+                    } else {
+                        inphase_from_ring_any(dst, r0, r1, g.piece_b, b0);
+                    }
+                }
+            }
+        }
+        PH_END(4);
+        // ---- (b') MMAs (warp 3, one lane), last in the step: tcgen05.mma blocks its warp while the tensor core's queue
+        //      is full.  The K steps of MMA tile Jb are issued as their samples arrive, a quarter per step: behind the
+        //      tile's 1st and 2nd audio tile the steps over the history (warp 3 itself has just read the last quarter
+        //      of the accumulator buffer's previous tile), behind the 3rd those up to the first 64 new samples,
+        //      behind the 4th the rest + commit ----
         if (quarter == 3) {
             const int Jb = it >> 2, part = it & 3;
-            if (part >= 1 && Jb < NJb) {
+            if (Jb < NJb) {
                 const int hist = g.lag / 16;              // K steps over samples before the tile
-                const int b1 = (hist * 3) / 4, b2 = hist + 4;
-                const int ks0 = part == 1 ? 0 : (part == 2 ? b1 : b2), ks1 = part == 1 ? b1 : (part == 2 ? b2 : g.ksteps);
+                const int e0 = (hist * 2) / 5, e1 = (hist * 4) / 5, e2 = hist + 4;
+                const int ks0 = part == 0 ? 0 : (part == 1 ? e0 : (part == 2 ? e1 : e2));
+                const int ks1 = part == 0 ? e0 : (part == 1 ? e1 : (part == 2 ? e2 : g.ksteps));
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t d = tmem_d + (uint32_t)((Jb & 1) * kMmaN);
@@ -330,98 +455,15 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                         if (c >= g.RC) c -= g.RC;
                     }
                     if (part == 3) tc_commit(smem_u32(sm.mbar + (Jb & 1)));
+#ifdef MICLOC_WAIT_DEBUG
+                    sm.mbar[6] = ((unsigned long long)(unsigned)it << 32) | (unsigned)(ks1 - ks0);     // last part issued
+                    if (part == 3) sm.mbar[7] = sm.mbar[7] + 1ull;                                 // commits so far
+#endif
                 }
                 __syncwarp();
             }
             if (part == 3) { cwin += 16; if (cwin >= g.RC) cwin -= g.RC; }
         }
-        PH_END(2);
-        // ---- (c) sub-tile s = k - 1 -> q rows ----
-        const int s = k - 1;
-        ibase += 4;
-        if (ibase >= g.RC) ibase -= g.RC;
-        if (s >= 0 && s < NT) {
-            // Q: accumulator row a = stream sample a of MMA tile Jb, column n = stream; the 32 samples of this
-            // sub-tile are lanes 32 (s & 3) ..: the warp that owns them stores column after column
-            if ((s & 3) == quarter) {
-                const int Jb = s >> 2;
-                mbar_wait(smem_u32(sm.mbar + (Jb & 1)), (uint32_t)((Jb >> 1) & 1));
-                tc_fence_after();
-                uint32_t r[32];
-                tc_ld32(tmem_d + (uint32_t)((Jb & 1) * kMmaN) + ((uint32_t)(32 * quarter) << 16), r);
-                tc_fence_before();
-                float *qb = sm.q + (s & 1) * kSlots * C2 * kQRow + lane;
-#pragma unroll
-                for (int n = 0; n < 2 * kRows * kSlots; ++n) {
-                    // stream n = slot * 2M + 2 mic + parity: even stream -> Q at odd times, odd stream -> Q at even times
-                    if (n < kSlots * C2) {
-                        const int slot2 = n / C2, rem = n - slot2 * C2;
-                        if (clip0 + slot2 < B)
-                            qb[(slot2 * C2 + M + (rem >> 1)) * kQRow + ((rem & 1) ? 0 : 32)] = __uint_as_float(r[n]);
-                    }
-                }
-            }
-            PH_END(3);
-            // I[t] = x[(t - K/2) mod T] (scaled like the ring samples; the band-pass warp applies the 2^14 of the
-            // taps): warp quarter = (clip slot, parity); a lane rebuilds 8 consecutive samples of one microphone
-            const int islot = quarter >> 1, ipar = quarter & 1;
-            if (lane < 4 * M && clip0 + islot < B) {
-                const int mic = lane >> 2, chunk = lane & 3;
-                float v[8];
-                if (s < g.tiles_is) {
-                    // np.roll: the first K/2 in-phase samples are the clip's last ones (snn_beamformer.py:325)
-                    const IN_T *clip = src[islot];
-                    const float sc = sx[islot];
-#pragma unroll 1
-                    for (int i = 0; i < 8; ++i) {
-                        const int t = kTile * s + 2 * (8 * chunk + i) + ipar;
-                        float x = 0.f;
-                        if (t < T) {
-                            int srci = (t - p.half) % T;
-                            if (srci < 0) srci += T;
-                            x = to_f32<IN_T>(clip[(long long)srci * M + mic]) * sc;
-                        }
-                        v[i] = x;
-                    }
-                } else {
-                    // I[2n] = E[n - H], I[2n+1] = O[n - H + 1]: 8 samples from ring position q0 on
-                    const int q0 = (kTile / 2) * s + 8 * chunk - g.H + ipar;
-                    const int n = islot * C2 + 2 * mic + ipar;
-                    const int b0 = q0 & 7;
-                    int c0 = (g.H & 7) == 0 ? ibase + chunk : (q0 >> 3) % g.RC;
-                    if (c0 >= g.RC) c0 -= g.RC;
-                    const int c1 = c0 + 1 == g.RC ? 0 : c0 + 1;
-                    const unsigned char *r0 = sm.ring + (c0 * g.NSP + n) * 16, *r1 = sm.ring + (c1 * g.NSP + n) * 16;
-                    if (b0 <= 1) {      // (warp-uniform) K/2 a multiple of 16: the 8 samples start at half 0 or 1 of a chunk
-                        const uint4 h4 = *reinterpret_cast<const uint4 *>(r0), l4 = *reinterpret_cast<const uint4 *>(r0 + g.piece_b);
-                        const unsigned int hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-                        float a[9];
-#pragma unroll
-                        for (int w2 = 0; w2 < 4; ++w2) {
-                            const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hw[w2]));
-                            const float2 lf = __half22float2(*reinterpret_cast<const __half2 *>(&lw[w2]));
-                            a[2 * w2] = hf.x + lf.x; a[2 * w2 + 1] = hf.y + lf.y;
-                        }
-                        a[8] = 0.f;
-                        if (b0 == 1)
-                            a[8] = __half2float(*reinterpret_cast<const __half *>(r1)) + __half2float(*reinterpret_cast<const __half *>(r1 + g.piece_b));
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = b0 ? a[i + 1] : a[i];
-                    } else {
-#pragma unroll 1
-                        for (int i = 0; i < 8; ++i) {
-                            const int e = b0 + i;
-                            const unsigned char *r = (e < 8 ? r0 : r1) + 2 * (e & 7);
-                            v[i] = __half2float(*reinterpret_cast<const __half *>(r)) + __half2float(*reinterpret_cast<const __half *>(r + g.piece_b));
-                        }
-                    }
-                }
-                float *dst = sm.q + (((s & 1) * kSlots + islot) * C2 + mic) * kQRow + ipar * 32 + 8 * chunk;
-                reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-                reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-        }
-        PH_END(4);
         // ---- (d) amax scan of the next pair: the slice loaded at the previous step is folded in now, this step's
         //      slice is requested and not waited for ----
         if (scan) {
@@ -454,6 +496,9 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
             if (lane == 0) sm.amax_next[c] = scan ? mb : 0xffffffffu;
         }
     }
+    // the MMA barriers are never re-initialised: tile Jb of a pair is completion mma_base[Jb & 1] + Jb / 2 of its barrier
+    mma_base[0] += (uint32_t)((NJb + 1) >> 1);
+    mma_base[1] += (uint32_t)(NJb >> 1);
     ROLE_TIMER_FLUSH(quarter);
     if (quarter == 0) PH_FLUSH(sm.dbg, 0, 5);
 }
@@ -633,7 +678,7 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
     }
     const uint32_t tmem_a = s_tmem;
     const uint32_t tmem_d = s_tmem + 16u * (uint32_t)g.ksteps + (uint32_t)(group * 2 * kMmaN);
-    uint32_t tma_phase = 0;
+    uint32_t tma_phase = 0, mma_base[2] = {0u, 0u};
 
     const int NT = (int)((T + kTile - 1) / kTile);
     const int NJ = (int)((T + kMac - 1) / kMac);
@@ -661,10 +706,9 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
             for (int i = tid; i < ring_words; i += kGThreads) r4[i] = 0u;
             for (int i = tid; i < 2 * kRingWords * 32; i += kGThreads) sm.bits[i] = 0u;
             for (int i = tid; i < 2 * 2 * kVmRows * kVmPitch / 2; i += kGThreads) reinterpret_cast<unsigned int *>(sm.vms)[i] = 0u;
-            if (tid == 0) {
-                for (int i = 0; i < 2; ++i) { mbar_inval(smem_u32(sm.mbar + i)); mbar_init(smem_u32(sm.mbar + i), 1); }
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
+#ifdef MICLOC_WAIT_DEBUG
+            if (tid == 0) { sm.mbar[6] = 0ull; sm.mbar[7] = 0ull; }
+#endif
         }
         const bool scanned = sm.amax_next[0] != 0xffffffffu;        // (written before the barriers above)
         if (sizeof(IN_T) == 4 && !scanned) {
@@ -699,7 +743,7 @@ k_fused_tc(const IN_T *__restrict__ audio, const float *__restrict__ taps, const
 
         if (role >= kRoleFront)
             front_role<IN_T, MM>(sm, p, g, audio, clip0, B, T, quarter, lane, NT, NJ, k_last, tmem_a, tmem_d, tma_phase,
-                                 3 + group, next_pair < npairs ? next_pair * kSlots : -1);
+                                 mma_base, 3 + group, next_pair < npairs ? next_pair * kSlots : -1);
         else if (role == 0) bandpass_role<MM>(sm, p, clip0, B, T, lane, k_last);
         else if (role == 1) rzcc_role<TcSmem, kRingWords>(sm, p, flags, clip0, B, T, M, lane, k_last);
         else if (role == 2) neuron_role<TcSmem, TcGeom, kRingWords>(sm, p, g, clip0, B, T, M, lane, k_last);
@@ -784,6 +828,7 @@ static bool make_geom(const ChainParams &p, int dtype, int groups, TcGeom &g) {
     g.off_clus = off; off += 4 * kClusterMax * 32 * (int)sizeof(int);
     g.off_bits = off; off += 2 * kRingWords * 32 * (int)sizeof(int);
     g.off_stage = off; off += (2 * kSlots * kTile * p.C2 + 15) & ~15;
+    off = (off + 127) & ~127;
     g.off_misc = off; off += 256;
     g.smem_group = (off + 127) & ~127;
     g.smem_bytes = groups * g.smem_group;
@@ -851,3 +896,13 @@ int launch_fused(const ChainParams &p, const float *d_taps, const double *d_Wd, 
 
 }  // namespace tc
 }  // namespace micloc
+
+#ifdef MICLOC_WAIT_DEBUG
+extern "C" int micloc_debug_wait(unsigned long long out[8]) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, micloc::tc::g_wait_dbg, 8 * sizeof(unsigned long long));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(micloc::tc::g_wait_dbg, z, sizeof z);
+    return 0;
+}
+#endif

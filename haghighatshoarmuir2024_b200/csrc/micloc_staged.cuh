@@ -103,7 +103,7 @@ k_chain(const IN_T *__restrict__ audio, const float *__restrict__ q, const float
 // S3: neuron filter   vmem[b][t][c] = sum_{n<L} h[n] * spikes[b][t-n][c]
 //     (snn_beamformer.py:364)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
          const __grid_constant__ ChainParams p, long long B, long long T) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,7 +125,7 @@ k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
 //      mean_t (v[t] . w_g)^2 == w_g^T (C/T) w_g, so the per-DoA power of
 //      snn_beamformer.py:368 + target_snn_localization.py:462 needs no T x G pass.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_gram(const float *__restrict__ vmem, double *__restrict__ gram, int C2, long long T, long long t_start) {
     const long long b = blockIdx.x;
     const int pair = blockIdx.y * blockDim.x + threadIdx.x;
@@ -143,7 +143,7 @@ k_gram(const float *__restrict__ vmem, double *__restrict__ gram, int C2, long l
 // S4b: power[b][g] = w_g^T C_b w_g / T (float64), doa[b] = first argmax.
 // One block per clip; dynamic smem: C2*C2 doubles + reduction scratch.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_power_argmax(const double *__restrict__ gram, const double *__restrict__ Wd, float *__restrict__ power,
                int32_t *__restrict__ doa, int C2, int G, double inv_T) {
     extern __shared__ __align__(16) double sm_d[];
@@ -221,7 +221,7 @@ k_dense(const float *__restrict__ vmem, const float *__restrict__ W, float *__re
 // Beamformer.apply_to_signal tail (micloc/beamformer.py:290):
 //   y[b][t][g] = sum_m (zr + i zi)[t][m] * conj(bf[m][g]),  z = [T][2M] (real | imag)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_cproject(const float *__restrict__ z, const float *__restrict__ bfr, const float *__restrict__ bfi,
            float2 *__restrict__ y, int M, int G, long long T, int slab) {
     const long long b = blockIdx.z;
@@ -243,7 +243,7 @@ k_cproject(const float *__restrict__ z, const float *__restrict__ bfr, const flo
 }
 
 // power[b][g] = mean_t |y|^2 in float64 + argmax; one block per (clip), thread per g
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_cpower_argmax(const float2 *__restrict__ y, float *__restrict__ power, int32_t *__restrict__ doa,
                 int G, long long T) {
     __shared__ double red_v[256];

@@ -200,6 +200,97 @@ class SnnEngine:
         return ms.value, n.value
 
 
+class SnnStream:
+    """Stateful frames of one continuous recording (micloc_snn_stream_*): N pushed frames give what one clip of their
+    concatenation gives (STHT history, band-pass, RZCC and neuron state carry over), with the results lagging the
+    input by `latency` samples.  The live loop of micloc/localization_demo_snn.py:125-193 restarts from zero state at
+    every frame instead.  Frames are [n, channels] device tensors, float32 / int16 / int32 (the recorder's `T x 8`
+    wav frames: channels beyond the microphones are dropped, localization_demo_snn.py:145)."""
+
+    def __init__(self, engine: SnnEngine, max_frame_len: int, fs: float = 48_000.0, rise_time: float = 10e-3,
+                 fall_time: float = 100e-3):
+        self.engine = engine
+        self._lib = engine._lib
+        self.max_frame_len = int(max_frame_len)
+        h = C.c_void_p()
+        N.check(self._lib.micloc_snn_stream_create(engine._h, self.max_frame_len, float(fs), float(rise_time),
+                                                   float(fall_time), C.byref(h)))
+        self._h = h
+        self.latency = int(self._lib.micloc_snn_stream_latency(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.micloc_snn_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        N.check(self._lib.micloc_snn_stream_reset(self._h, _stream_ptr(self.engine.device)))
+
+    def _outputs(self, rows, want_env):
+        e = self.engine
+        dev = e.device
+        return {"spikes": torch.empty((rows, e.C2), dtype=torch.int8, device=dev),
+                "power": torch.empty(e.G, dtype=torch.float32, device=dev),
+                "doa": torch.empty(1, dtype=torch.int32, device=dev),
+                "env": torch.empty((rows, e.G), dtype=torch.float32, device=dev) if want_env else None,
+                "doa_t": torch.empty(rows, dtype=torch.int32, device=dev) if want_env else None}
+
+    def _trim(self, out, n):
+        res = {"n_out": n, "spikes": out["spikes"][:n], "power": out["power"] if n else None,
+               "doa": out["doa"] if n else None}
+        if out["env"] is not None:
+            res["env"], res["doa_t"] = out["env"][:n], out["doa_t"][:n]
+        return res
+
+    def push(self, frame: torch.Tensor, want_env: bool = False) -> Dict[str, torch.Tensor]:
+        """One frame in, the samples that became final out: dict(n_out, spikes [n_out, 2M], power [G] and doa [1]
+        over those samples, env [n_out, G] + doa_t [n_out] when `want_env`)."""
+        e = self.engine
+        if frame.dim() != 2 or frame.shape[1] < e.M:
+            raise ValueError(
+                f"number of channels in the input siganl {frame.shape[-1]} should be the same as the number of microphones {e.M}!")
+        if frame.device != e.device:
+            raise ValueError(f"frame lives on {frame.device}, engine on {e.device}")
+        dt = {torch.float32: N.F32, torch.int16: N.I16, torch.int32: N.I32}.get(frame.dtype)
+        if dt is None:
+            raise ValueError(f"frame must be float32, int16 or int32, got {frame.dtype}")
+        frame = frame.contiguous()
+        n = frame.shape[0]
+        out = self._outputs(n + self.latency, want_env)
+        n_out = C.c_int64()
+        N.check(self._lib.micloc_snn_stream_push(self._h, _ptr(frame), dt, n, frame.shape[1], _ptr(out["spikes"]),
+                                                 _ptr(out["power"]), _ptr(out["doa"]), _ptr(out["env"]), _ptr(out["doa_t"]),
+                                                 C.byref(n_out), _stream_ptr(e.device)))
+        return self._trim(out, n_out.value)
+
+    def flush(self, want_env: bool = False) -> Dict[str, torch.Tensor]:
+        """End of the recording: the remaining `latency` samples (+ 'flags': RZCC overflow bit of the whole stream)."""
+        out = self._outputs(self.max_frame_len + self.latency, want_env)
+        n_out, flags = C.c_int64(), C.c_int32()
+        N.check(self._lib.micloc_snn_stream_flush(self._h, _ptr(out["spikes"]), _ptr(out["power"]), _ptr(out["doa"]),
+                                                  _ptr(out["env"]), _ptr(out["doa_t"]), C.byref(n_out), C.byref(flags),
+                                                  _stream_ptr(self.engine.device)))
+        res = self._trim(out, n_out.value)
+        res["flags"] = flags.value
+        return res
+
+
+def envelope(x: torch.Tensor, fs: float, rise_time: float, fall_time: float, want_argmax: bool = False):
+    """Envelope(rise_time, fall_time, fs).evolve on a device array [T, C] float32 (micloc/utils.py:15-81);
+    with `want_argmax` also the per-row argmax (tests/test_snn_hilbert_localization.py:284-293)."""
+    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
+        raise ValueError("x must be a CUDA float32 tensor of shape [T, C]")
+    x = x.contiguous()
+    T, Cc = x.shape
+    env = torch.empty_like(x)
+    idx = torch.empty(T, dtype=torch.int32, device=x.device) if want_argmax else None
+    N.check(N.lib().micloc_envelope(_ptr(x), T, Cc, float(fs), float(rise_time), float(fall_time), _ptr(env), _ptr(idx),
+                                    x.device.index or 0, _stream_ptr(x.device)))
+    return (env, idx) if want_argmax else env
+
+
 def rzcc_encode(sig: torch.Tensor, robust_width: int, bipolar: bool) -> torch.Tensor:
     """Exact ZeroCrossingSpikeEncoder.evolve on float64 device input [B,T,C] -> int8 spikes."""
     if sig.dtype != torch.float64 or not sig.is_cuda or sig.dim() != 3:

@@ -33,6 +33,20 @@ class Envelope:
         self.win_lens = np.asarray([int(fs * fall_time), int(fs * rise_time)])
 
     def evolve(self, sig_in: np.ndarray) -> np.ndarray:
+        """`T x num_chan` in, envelopes out, on the GPU (micloc_envelope); float32 arithmetic."""
+        import torch
+        from .engine import envelope
+        sig_in = np.asarray(sig_in)
+        T, channel = sig_in.shape
+        if T < channel:
+            warnings.warn("number of channels in the input signal is larger than number of samples in each channel!")
+        if not torch.cuda.is_available():
+            raise RuntimeError("Envelope.evolve needs a CUDA device (evolve_host is the numpy restatement used by the CPU tests)")
+        x = torch.from_numpy(np.ascontiguousarray(sig_in, dtype=np.float32)).cuda()
+        return envelope(x, self.fs, self.rise_time, self.fall_time).cpu().numpy().astype(np.float64)
+
+    def evolve_host(self, sig_in: np.ndarray) -> np.ndarray:
+        """numpy restatement of micloc/utils.py:49-81 (test infrastructure; `evolve` is the product path)."""
         T, channel = sig_in.shape
         if T < channel:
             warnings.warn("number of channels in the input signal is larger than number of samples in each channel!")

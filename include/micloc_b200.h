@@ -44,10 +44,11 @@ typedef enum {
     MICLOC_ERR_OVERFLOW = -5     /* RZCC cluster buffer overflow in the fused path: rerun staged */
 } micloc_status;
 
-typedef enum { MICLOC_F32 = 0, MICLOC_I16 = 1 } micloc_dtype;
+typedef enum { MICLOC_F32 = 0, MICLOC_I16 = 1, MICLOC_I32 = 2 /* streams only: wav frames of micloc/record.py */ } micloc_dtype;
 
 typedef struct micloc_snn micloc_snn;   /* float SNN chain   */
 typedef struct micloc_xylo micloc_xylo; /* Xylo integer chain */
+typedef struct micloc_stream micloc_stream; /* stateful frames of one continuous recording */
 
 /* ---- float SNN chain ------------------------------------------------------ */
 typedef struct {
@@ -109,6 +110,37 @@ int micloc_snn_gram(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B
  * GPUs (paper_plots/target_snn_localization.py:447-467 keeps per-trial DoA errors). */
 int micloc_doa_histogram(const int32_t *doa_dev, int64_t B, int32_t G, int64_t *hist_dev, int device,
                          void *stream);
+
+/* ---- stateful frames + Envelope tracker -------------------------- */
+/* The live loop of micloc/localization_demo_snn.py:125-193 records a frame, runs the chain from ZERO state and
+ * repeats.  A stream carries the state instead (STHT history, band-pass, RZCC running sum and open clusters, neuron,
+ * envelope): N pushed frames give exactly what one clip of their concatenation gives.  By nature of a stream the
+ * in-phase branch is the causal delay x[t - K/2] (np.roll's wrap-around needs the clip's end; identical whenever the
+ * last K/2 samples of the clip are zero) and results lag the input by micloc_snn_stream_latency() samples (the RZCC
+ * distance rule decides a spike only that much later).
+ *   frame_dev  [n][in_channels] interleaved float32 / int16 / int32 PCM (the recorder's `T x 8` int32 wav frames with
+ *              in_channels = 8: channels >= num_mic are dropped, localization_demo_snn.py:145); n <= max_frame_len
+ *   outputs describe the n_out samples that became final with this call (all nullable, device pointers):
+ *     spikes_dev [n_out][2M] int8;  power_dev [G] = mean over those samples of y^2, doa_dev [1] its first argmax;
+ *     env_dev [n_out][G] = Envelope(rise_time, fall_time, fs).evolve(y) continued across calls (micloc/utils.py:15-81),
+ *     doa_t_dev [n_out] = per-sample argmax of the envelope (tests/test_snn_hilbert_localization.py:284-293)
+ *   buffers must hold max_frame_len + latency rows.  micloc_snn_stream_flush ends the stream like a clip end and
+ *   returns the remaining samples (+ the RZCC overflow flag); after it only micloc_snn_stream_reset is allowed.
+ * The stream uses its parent context's constants: destroy it before the context, re-create it after micloc_snn_set_bf. */
+int micloc_snn_stream_create(micloc_snn *ctx, int64_t max_frame_len, double fs, double rise_time, double fall_time,
+                             micloc_stream **out);
+int micloc_snn_stream_destroy(micloc_stream *s);
+int micloc_snn_stream_reset(micloc_stream *s, void *stream);
+int micloc_snn_stream_latency(micloc_stream *s);
+int micloc_snn_stream_push(micloc_stream *s, const void *frame_dev, int dtype, int64_t n, int32_t in_channels,
+                           int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, float *env_dev, int32_t *doa_t_dev,
+                           int64_t *n_out, void *stream);
+int micloc_snn_stream_flush(micloc_stream *s, int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, float *env_dev,
+                            int32_t *doa_t_dev, int64_t *n_out, int32_t *flags_host, void *stream);
+/* Envelope.evolve on a whole device array x_dev [T][C] float32 (fresh state) -> env_dev [T][C]; argmax_dev [T]
+ * (nullable) = first argmax over the C channels of every row. */
+int micloc_envelope(const float *x_dev, int64_t T, int32_t C, double fs, double rise_time, double fall_time,
+                    float *env_dev, int32_t *argmax_dev, int device, void *stream);
 
 /* ---- Monte-Carlo input synthesis ------------------------------ */
 /* Synthetic array clips on the device, as the reference builds them on the host:
