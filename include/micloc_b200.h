@@ -142,6 +142,27 @@ int micloc_snn_stream_flush(micloc_stream *s, int8_t *spikes_dev, float *power_d
 int micloc_envelope(const float *x_dev, int64_t T, int32_t C, double fs, double rise_time, double fall_time,
                     float *env_dev, int32_t *argmax_dev, int device, void *stream);
 
+/* ---- multi-band localiser: filterbank, power summed over bands, estimators ---- */
+/* ButterworthFilterbank.evolve (micloc/filterbank.py:25-46) on raw frames: F band-pass filters given as SOS sections
+ * (sos [F][n_sections][6], host) on every microphone channel, zero state.
+ *   audio_dev [B][T][in_channels] float32 / int16 / int32 (wav frames: channels >= M are dropped,
+ *             micloc/localization_demo_snn.py:145);  out_dev [F][B][T][M] float32: band f is the [B][T][M] batch a
+ *             per-band context's micloc_snn_run takes;  sumsq_dev [B] float64 (nullable) = sum of x^2 over the kept
+ *             channels of a clip (activity detection, localization_demo_snn.py:151-163). */
+int micloc_filterbank(const void *audio_dev, int dtype, int64_t B, int64_t T, int32_t in_channels, int32_t M,
+                      int32_t F, int32_t n_sections, const double *sos, float *out_dev, double *sumsq_dev,
+                      int device, void *stream);
+/* power_grid = sum over bands (micloc/localization_demo_snn.py:172-189) + the estimators of
+ * micloc/xylo_snn_localization.py:400-444 on it:
+ *   power_dev [F][B][G] float32 (the per-band power outputs of micloc_snn_run);  doa_list_dev [G] float64 (nullable
+ *   when no ML estimate is wanted);  outputs, all nullable: power_sum_dev [B][G] float32, doa_dev [B] first argmax
+ *   ("peak"), periodic_ml_dev [B] float64 = angle(mean(p e^{j doa})), trimmed_ml_dev [B] float64 = the same over the
+ *   reference's window around the peak; where the reference's indexing raises IndexError (peak index > 3G/4) the
+ *   estimate is NaN and flags_dev [B] gets bit 1. */
+int micloc_power_fuse(const float *power_dev, int32_t F, int64_t B, int32_t G, const double *doa_list_dev,
+                      float *power_sum_dev, int32_t *doa_dev, double *periodic_ml_dev, double *trimmed_ml_dev,
+                      int32_t *flags_dev, int device, void *stream);
+
 /* ---- Monte-Carlo input synthesis ------------------------------ */
 /* Synthetic array clips on the device, as the reference builds them on the host:
  *   mode 0  SNNBeamformer.apply_to_template (micloc/snn_beamformer.py:243-275): per-microphone delays

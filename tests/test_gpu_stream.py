@@ -56,7 +56,7 @@ def test_frames_equal_one_clip_bit_for_bit(dtype):
     torch.cuda.synchronize()
     st = SnnStream(eng, max_frame_len=4096)
     assert st.latency > 0
-    for lens in ([T // 3] * 3, [1, 31, 32, 33, 700, 4096, 2, T - 4895], [4096, 4096, T - 8192]):
+    for lens in ([T // 3] * 3, [1, 31, 32, 33, 700, 4096, 2, 609, T - 5504], [4096, 4096, T - 8192]):
         st.reset()
         cat, frames, flags = stream_all(st, xd, lens)
         assert flags == 0

@@ -24,7 +24,23 @@ def test_snn_chain_matches_reference(name):
     assert out["doa"] == int(g["doa"])
 
 
-@pytest.mark.parametrize("name", H.SNN_CASES)
+@pytest.mark.parametrize("name", H.FULL_CASES)
+def test_snn_chain_matches_reference_at_full_length(name):
+    """One-second clips (T = 48 000, configs[0] and one clip per band of configs[1]): the neuron kernel's
+    normalisation over T and a whole second of spikes."""
+    g = H.load(name)
+    assert g["x"].shape[0] == 48_000
+    out = O.snn_apply(H.oracle_cfg(g), g["x"].astype(np.float64))
+    rows = g["rows"]
+    assert H.rel_err(out["q"][rows], g["q_rows"]) < 1e-13
+    assert np.array_equal(out["spikes"].astype(np.int8), g["spikes"])          # bit-exact spikes
+    assert H.rel_err(out["vmem"][rows], g["vmem_rows"]) < 1e-12
+    assert H.rel_err(out["y"][g["yrows"]], g["y_rows"]) < 1e-12
+    assert H.rel_err(out["power"], g["power"]) < 1e-12
+    assert out["doa"] == int(g["doa"])
+
+
+@pytest.mark.parametrize("name", H.SNN_CASES + H.FULL_CASES)
 def test_neuron_kernel_matches_reference(name):
     g = H.load(name)
     T = g["x"].shape[0]
