@@ -185,22 +185,27 @@ __device__ __forceinline__ void rzcc_reset(RzccState &s) {
 // Cluster buffers of one channel.  `stride` is the distance between consecutive
 // entries (1 for a private array, 32 for arrays interleaved across the lanes of a
 // warp in shared memory).
-struct RzccStore {
-    int *cl_pos;              // [2][kClusterMax]
-    float *cl_h;              // [2][kClusterMax]  height, sign-adjusted so that higher wins
+// HT = float (float32 chain) or double (the Xylo chain's exact front end, heights of a float64 np.cumsum).
+// CAP = candidates buffered per open cluster.
+template <typename HT, int CAP = kClusterMax> struct RzccStoreT {
+    int *cl_pos;              // [2][CAP]
+    HT *cl_h;                 // [2][CAP]  height, sign-adjusted so that higher wins
     int stride;
 };
+using RzccStore = RzccStoreT<float>;
 
 // scipy's greedy distance rule on one closed cluster of n >= 2 candidates: returns the bit mask of
 // the candidates that stay.  Rare (band-limited signals give single-candidate clusters), so it is
 // kept out of line: the fused kernel's instruction footprint matters more than this call.
-static __device__ __noinline__ unsigned rzcc_select(const int *cp, const float *ch, int stride, int n, int w) {
-    unsigned und = (1u << n) - 1u, kept = 0u;
+template <typename HT, int CAP>
+static __device__ __noinline__ unsigned rzcc_select(const int *cp, const HT *ch, int stride, int n, int w) {
+    static_assert(CAP <= 32, "one bit per candidate");
+    unsigned und = (CAP == 32 && n == 32) ? 0xffffffffu : (1u << n) - 1u, kept = 0u;
     while (und) {
-        int best = -1; float hb = 0.f;
+        int best = -1; HT hb = (HT)0;
         for (int i = 0; i < n; ++i)
             if ((und >> i) & 1u) {
-                const float h = ch[i * stride];
+                const HT h = ch[i * stride];
                 if (best < 0 || h >= hb) { best = i; hb = h; }
             }
         const int pb = cp[best * stride];
@@ -216,15 +221,15 @@ static __device__ __noinline__ unsigned rzcc_select(const int *cp, const float *
 
 // POL 1 = peaks (+1 spikes), 0 = valleys (-1 spikes); compile-time so that the cluster state stays in
 // named registers
-template <int POL, typename Emit>
-__device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, int w, Emit &&emit) {
+template <int POL, typename Emit, typename HT, int CAP>
+__device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStoreT<HT, CAP> &st, int w, Emit &&emit) {
     const int n = POL ? s.n1 : s.n0;
-    const int *cp = st.cl_pos + POL * kClusterMax * st.stride;
-    const float *ch = st.cl_h + POL * kClusterMax * st.stride;
+    const int *cp = st.cl_pos + POL * CAP * st.stride;
+    const HT *ch = st.cl_h + POL * CAP * st.stride;
     constexpr int sign = POL ? 1 : -1;
     if (POL) s.n1 = 0; else s.n0 = 0;
     if (n == 1) { emit(cp[0], sign); return; }
-    unsigned kept = rzcc_select(cp, ch, st.stride, n, w);
+    unsigned kept = rzcc_select<HT, CAP>(cp, ch, st.stride, n, w);
     while (kept) {
         const int i = __ffs(kept) - 1;
         kept &= kept - 1;
@@ -233,18 +238,18 @@ __device__ __forceinline__ void rzcc_resolve(RzccState &s, const RzccStore &st, 
 }
 
 // a new candidate (candidates of one polarity arrive in time order)
-template <int POL, typename Emit>
-__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int pos, float h, int w, Emit &&emit) {
+template <int POL, typename Emit, typename HT, int CAP>
+__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStoreT<HT, CAP> &st, int pos, HT h, int w, Emit &&emit) {
     if ((POL ? s.n1 : s.n0) > 0 && pos - (POL ? s.last1 : s.last0) >= w) rzcc_resolve<POL>(s, st, w, emit);
     const int n = POL ? s.n1 : s.n0;
-    if (n == kClusterMax) { s.overflow = 1; return; }
-    st.cl_pos[(POL * kClusterMax + n) * st.stride] = pos;
-    st.cl_h[(POL * kClusterMax + n) * st.stride] = h;
+    if (n == CAP) { s.overflow = 1; return; }
+    st.cl_pos[(POL * CAP + n) * st.stride] = pos;
+    st.cl_h[(POL * CAP + n) * st.stride] = h;
     if (POL) { s.last1 = pos; s.n1 = n + 1; } else { s.last0 = pos; s.n0 = n + 1; }
 }
 
-template <typename Emit>
-__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int pol, int pos, float h, int w,
+template <typename Emit, typename HT, int CAP>
+__device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStoreT<HT, CAP> &st, int pol, int pos, HT h, int w,
                                           Emit &&emit) {
     if (pol) rzcc_push<1>(s, st, pos, h, w, emit); else rzcc_push<0>(s, st, pos, h, w, emit);
 }
@@ -252,17 +257,17 @@ __device__ __forceinline__ void rzcc_push(RzccState &s, const RzccStore &st, int
 // every kSeg samples (t_end = last sample seen): close the clusters that can no longer
 // grow; everything when `final`.  A spike at position p is emitted at the latest by the
 // close check at t_end >= p + kPlateauMax/2 + (kClusterMax-1)*(w-1) + w + kSeg - 1.
-template <typename Emit>
-__device__ __forceinline__ void rzcc_close(RzccState &s, const RzccStore &st, int w, int t_end, bool final,
+template <typename Emit, typename HT, int CAP>
+__device__ __forceinline__ void rzcc_close(RzccState &s, const RzccStoreT<HT, CAP> &st, int w, int t_end, bool final,
                                            Emit &&emit) {
     if (s.n1 > 0 && (final || t_end - s.last1 >= w)) rzcc_resolve<1>(s, st, w, emit);
     if (s.n0 > 0 && (final || t_end - s.last0 >= w)) rzcc_resolve<0>(s, st, w, emit);
 }
 
 // candidate test for sample t with value class (nz, positive) and the running sum before it
-template <typename Emit>
-__device__ __forceinline__ void rzcc_sample(RzccState &s, const RzccStore &st, int bipolar, int w, int t, bool nz,
-                                            bool positive, float cprev, Emit &&emit) {
+template <typename Emit, typename HT, int CAP>
+__device__ __forceinline__ void rzcc_sample(RzccState &s, const RzccStoreT<HT, CAP> &st, int bipolar, int w, int t, bool nz,
+                                            bool positive, HT cprev, Emit &&emit) {
     const bool ev = nz && (s.r >= 1) && (positive != (s.sgn != 0)) && (bipolar || s.sgn);
     if (ev) {
         if (t - 1 - s.r > kPlateauMax) s.overflow = 1;

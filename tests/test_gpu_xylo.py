@@ -118,6 +118,42 @@ def test_batch_exact_equals_oracle(name, int16):
     assert agree >= 0.999, agree
 
 
+@pytest.mark.parametrize("name,int16", [("xylo_c3_bipolar", True), ("xylo_3band_o2", False)])
+def test_one_kernel_exact_front_end_equals_staged_float64(name, int16, monkeypatch):
+    """The exact front end as ONE kernel per clip (STHT, band filters, cumsum, RZCC in float64, nothing in HBM but the
+    spikes) against the staged float64 kernels with unbounded candidate clusters, on whole seconds."""
+    g = H.load(name)
+    eng = H.xylo_engine(g)
+    x = dev(H.xylo_synth_clips(g, 5, 48_000, seed=77, int16=int16))
+    a = eng.run(x, exact=True, want_spikes_in=True)
+    monkeypatch.setenv("MICLOC_XYLO_STAGED_F64", "1")
+    b = eng.run(x, exact=True, want_spikes_in=True)
+    monkeypatch.setenv("MICLOC_XYLO_DENSE_F64", "1")          # and the dense 480-tap FIR in lfilter's order
+    c = eng.run(x[:2], exact=True, want_spikes_in=True)
+    assert torch.equal(a["spikes_in"], b["spikes_in"]) and torch.equal(a["counts"], b["counts"])
+    assert torch.equal(a["spikes_in"][:2], c["spikes_in"]) and torch.equal(a["counts"][:2], c["counts"])
+    assert int(a["flags"].sum()) == 0 and int(b["flags"].sum()) == 0
+
+
+def test_long_digital_silence_falls_back_to_the_unbounded_encoder():
+    """Hundreds of milliseconds of exact zeros let the float64 band filter underflow to exact 0.0: flat tops longer
+    than the streaming encoder follows.  The library redoes such clips with the unbounded kernels by itself: the
+    result is still bit-exact and no flag is left set."""
+    g = H.load("xylo_c3_bipolar")
+    net = H.xylo_network(g)
+    eng = H.xylo_engine(g, net)
+    x = H.xylo_synth_clips(g, 3, 48_000, seed=12, int16=True)
+    x[1, 1500:44_000] = 0
+    x[2, :] = 0
+    ref = O.xylo_run_batch(H.xylo_oracle_cfg(g, net), x, float(g["fs"]), win=15, nthreads=3, want_spikes=True)
+    out = eng.run(dev(x), exact=True, want_spikes_in=True, peak_win=15)
+    s = out["spikes_in"].cpu().numpy().astype(np.int8)
+    assert np.array_equal(s[..., :14] - s[..., 14:], ref["spikes_signed"])
+    assert np.array_equal(out["counts"].cpu().numpy(), ref["counts"])
+    assert np.array_equal(out["doa"].cpu().numpy(), ref["doa"])
+    assert int(out["flags"].sum()) == 0
+
+
 def test_full_size_clip_config3():
     """T = 48 000 (1 s) bipolar, G = 449: exact chain == oracle on whole clips."""
     g = H.load("xylo_c3_bipolar")
