@@ -149,181 +149,117 @@ k_stht_f64_sparse(const IN_T *__restrict__ audio, const double *__restrict__ g, 
         if (tb + r < T) q[(b * T + tb + r) * M + m0 + mm] = acc[r];
 }
 
-// ---- the whole exact front end of one clip in one CTA: STHT -> band filters -> np.cumsum -> find_peaks, float64 ----
-// Warps 0..M-1 are the STHT warps (one microphone each, the register-blocked sum of k_stht_f64_sparse) and produce
-// the quadrature tile + the in-phase samples x[(t - K/2) mod T] of time tile `it` in shared memory; warp M is the chain
-// warp, one lane per (band, channel): it runs the band filter of tile it-1 in lfilter's operation order
-// (k_iir_f64), the float64 running sum and the streaming RZCC encoder (micloc_device.cuh, heights in float64) and
-// writes the signed spikes.  Neither q nor z ever reach HBM.  Clips whose candidate clusters overflow the streaming
-// encoder's buffers are flagged (bit 0) and redone by the host with the unbounded kernels.
-constexpr int kQPitch = kSTile + 2;     // doubles per microphone row of a q tile (lanes of the chain warp: distinct banks)
+// ---- band filters -> np.cumsum -> find_peaks in float64, one WARP per clip, one lane per (band, channel) ------------
+// The chain is sequential in time and bit-exactness forbids re-association, so its speed is the number of chains in
+// flight: a warp needs 5 KB of shared memory (64-step tiles of q and of the in-phase samples x[(t - K/2) mod T], loaded
+// coalesced) and its candidate clusters live in per-thread local memory, i.e. 32 clips per SM.  The band filter runs in
+// lfilter's operation order (as k_iir_f64), the running sum is np.cumsum's left-to-right float64 sum, and peaks are
+// detected on that sum itself (acc > prev / acc < prev with scipy's plateau-midpoint rule, as k_rzcc_scan does), not
+// on the sign of z: once |z| drops below half an ulp of the sum (decaying filters in digital silence) the sum stops
+// moving although z still alternates, and find_peaks sees one flat top.  Clusters are resolved by the streaming
+// encoder of micloc_device.cuh with float64 heights; a cluster of more than kF64Cluster candidates flags the clip
+// (bit 0) and the host redoes it with the unbounded kernels.  z never reaches HBM.
 constexpr int kF64Cluster = 32;         // candidates buffered per open cluster (noisy order-1 bands chain up to ~12)
-// Peaks are detected on the float64 running sum itself (acc > prev / acc < prev with scipy's plateau-midpoint rule, as
-// k_rzcc_scan does), not on the sign of z: once |z| drops below half an ulp of the running sum (decaying filters in
-// digital silence) the sum stops moving although z still alternates, and find_peaks sees one flat top.
+constexpr int kChainTile = 64;          // time steps staged per warp
+constexpr int kChainWarps = 8;          // clips per CTA
 
 template <typename IN_T, int NBA>
-__global__ void __launch_bounds__(256, 2)
-k_xylo_front_f64(const IN_T *__restrict__ audio, const double *__restrict__ g, const double *__restrict__ ba_b,
+__global__ void __launch_bounds__(32 * kChainWarps, 3)
+k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, const double *__restrict__ ba_b,
                  const double *__restrict__ ba_a, int8_t *__restrict__ spikes, int32_t *__restrict__ flags,
-                 int M, int K, int ntap, int nba, int F, int w, int bipolar, long long T) {
+                 int M, int half, int nba, int F, int w, int bipolar, long long B, long long T) {
     extern __shared__ __align__(16) double smd[];
-    const int npos = kSTile + K - 1;
-    const int pitch = (f64_pad(npos) + 9) & ~1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * kChainWarps + warp;
+    if (b >= B) return;
     const int C2 = 2 * M, CT = C2 * F;
     const int passes = (CT + 31) >> 5;
-    double *gs = smd;                                   // [ntap]
-    double *xs = gs + ntap;                             // [M][pitch]
-    double *qs = xs + (size_t)M * pitch;                // [2][M][kQPitch]
-    double *clh = qs + 2 * (size_t)M * kQPitch;         // [2 kF64Cluster][CT] candidate heights
-    int *clp = reinterpret_cast<int *>(clh + (size_t)2 * kF64Cluster * CT);            // [2 kF64Cluster][CT] positions
-    float *xi = reinterpret_cast<float *>(clp + (((size_t)2 * kF64Cluster * CT + 3) & ~(size_t)3));  // [2][M][kSTile] in-phase samples
-
-    const long long b = blockIdx.x;
+    double *qs = smd + (size_t)warp * kChainTile * M;                                                       // [tile][M]
+    float *xs = reinterpret_cast<float *>(smd + (size_t)kChainWarps * kChainTile * M) + (size_t)warp * kChainTile * M;   // [tile][M]
     const IN_T *clip = audio + b * T * M;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int half = K / 2;
-    const int NT = (int)((T + kSTile - 1) / kSTile);
-    for (int i = threadIdx.x; i < ntap; i += blockDim.x) gs[i] = g[i];
+    const double *qc = q + b * T * M;
 
-    // chain warp state: one (band, channel) per lane and pass, parked in shared memory between tiles so that only
-    // one pass lives in registers (the STHT warps need theirs for the window)
-    struct ChanSave { double zs[NBA]; double cs; RzccState rz; int rise, fall; };
-    ChanSave *save = reinterpret_cast<ChanSave *>(xi + 2 * (size_t)M * kSTile);          // [passes][32]
-    if (warp == M) {
-        for (int ps = 0; ps < passes; ++ps) {
-            ChanSave &sv = save[ps * 32 + lane];
+    // per-pass chain state (CT <= 64: at most two (band, channel) per lane)
+    // (parked in local memory between tiles: only the pass at work lives in registers)
+    struct Save { double zs[NBA]; double cs; int rise, fall; RzccState rz; } sv[2];
+    int cl_pos[2][2 * kF64Cluster];
+    double cl_h[2][2 * kF64Cluster];
+#pragma unroll 1
+    for (int ps = 0; ps < 2; ++ps) {
 #pragma unroll
-            for (int k = 0; k < NBA; ++k) sv.zs[k] = 0.0;
-            sv.cs = 0.0;
-            rzcc_reset(sv.rz);
-            sv.rise = sv.fall = -1;
-        }
+        for (int k = 0; k < NBA; ++k) sv[ps].zs[k] = 0.0;
+        sv[ps].cs = 0.0; sv[ps].rise = sv[ps].fall = -1;
+        rzcc_reset(sv[ps].rz);
     }
-    __syncthreads();
-
-    for (int it = 0; it <= NT; ++it) {
-        if (warp < M) {
-            if (it < NT) {
-                const long long t0 = (long long)it * kSTile;
-                // (1) audio tile + history -> float64 rows (all STHT warps together, coalesced)
-                for (int e = threadIdx.x; e < npos * M; e += 32 * M) {
-                    const int l = e / M, mm = e - l * M;
-                    const long long t = t0 - (K - 1) + l;
-                    xs[mm * pitch + f64_pad(l)] = (t >= 0 && t < T) ? (double)clip[t * M + mm] : 0.0;
-                }
-                asm volatile("bar.sync 1, %0;" ::"r"(32 * M) : "memory");
-                // (2) in-phase samples of the tile: x[(t - K/2) mod T] (np.roll)
-                float *xrow = xi + ((it & 1) * M + warp) * kSTile;
-                for (int i = lane; i < kSTile; i += 32) {
-                    const long long t = t0 + i;
-                    float v = 0.f;
-                    if (t < T) {
-                        if (t >= half) v = (float)xs[warp * pitch + f64_pad(i + (K - 1) - half)];
-                        else { long long src = (t - half) % T; if (src < 0) src += T; v = (float)clip[src * M + warp]; }
-                    }
-                    xrow[i] = v;
-                }
-                // (3) quadrature tile
-                const double *row = xs + warp * pitch;
-                double acc[kSR], W[2 * kSR], gg[4];
-                auto load8 = [&](int grp, double *dst) {
-                    const double2 *p2 = reinterpret_cast<const double2 *>(row + 10 * grp);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) { const double2 d = p2[v]; dst[2 * v] = d.x; dst[2 * v + 1] = d.y; }
-                };
-                load8(lane, W);
-                const int nit = ntap >> 2;
+    const int NT = (int)((T + kChainTile - 1) / kChainTile);
+    for (int tile = 0; tile < NT; ++tile) {
+        const long long t0 = (long long)tile * kChainTile;
+        const int len = (int)min((long long)kChainTile, T - t0);
+        __syncwarp();
+        for (int e = lane; e < len * M; e += 32) {
+            qs[e] = qc[t0 * M + e];
+            const int i = e / M, m = e - i * M;
+            long long src = t0 + i - half;                       // np.roll: x[(t - K/2) mod T]
+            if (src < 0) { src %= T; if (src < 0) src += T; }
+            xs[e] = (float)clip[src * M + m];
+        }
+        __syncwarp();
 #pragma unroll 1
-                for (int I = 0; I < nit; ++I) {
-                    load8(lane + I + 1, W + kSR);
-                    {
-                        const double2 a = reinterpret_cast<const double2 *>(gs + 4 * I)[0], c = reinterpret_cast<const double2 *>(gs + 4 * I)[1];
-                        gg[0] = a.x; gg[1] = a.y; gg[2] = c.x; gg[3] = c.y;
-                    }
-                    if (I == 0) stht_f64_taps4<true>(acc, W, gg); else stht_f64_taps4<false>(acc, W, gg);
+        for (int ps = 0; ps < passes; ++ps) {
+            const int cc = lane + 32 * ps;
+            if (cc < CT) {
+                const int c = cc % C2, band = cc / C2;
+                const bool inphase = c < M;
+                const int col = inphase ? c : c - M;
+                const RzccStoreT<double, kF64Cluster> store{cl_pos[ps], cl_h[ps], 1};
+                int8_t *out = spikes + b * T * CT + cc;
+                auto emit = [&](int pos, int sign) { out[(long long)pos * CT] = (int8_t)sign; };
+                double bb[NBA], aa[NBA], zs[NBA];
 #pragma unroll
-                    for (int r = 0; r < kSR; ++r) W[r] = W[kSR + r];
+                for (int k = 0; k < NBA; ++k) {
+                    bb[k] = k < nba ? ba_b[band * nba + k] : 0.0;
+                    aa[k] = k < nba ? ba_a[band * nba + k] : 0.0;
+                    zs[k] = sv[ps].zs[k];
                 }
-                double2 *qrow = reinterpret_cast<double2 *>(qs + ((it & 1) * M + warp) * kQPitch + kSR * lane);
+                RzccState s = sv[ps].rz;
+                double acc = sv[ps].cs;
+                int rs = sv[ps].rise, fl = sv[ps].fall;    // start of the running sum's current flat top / bottom (-1: none)
+#pragma unroll 4
+                for (int i = 0; i < len; ++i) {
+                    const double x = inphase ? (double)xs[i * M + col] : qs[i * M + col];
+                    const double y = __dadd_rn(zs[0], __dmul_rn(bb[0], x));
 #pragma unroll
-                for (int v = 0; v < 4; ++v) qrow[v] = make_double2(acc[2 * v], acc[2 * v + 1]);
-            }
-        } else if (it >= 1) {
-            // ---- chain warp: tile it-1 ----
-            const int tile = it - 1;
-            const long long t0 = (long long)tile * kSTile;
-            const int len = (int)min((long long)kSTile, T - t0);
-#pragma unroll 1
-            for (int ps = 0; ps < passes; ++ps) {
-                const int cc = lane + 32 * ps;
-                if (cc < CT) {
-                    const int c = cc % C2, band = cc / C2;
-                    const bool inphase = c < M;
-                    const double *qrow = qs + ((tile & 1) * M + (inphase ? 0 : c - M)) * kQPitch;
-                    const float *xrow = xi + ((tile & 1) * M + (inphase ? c : 0)) * kSTile;
-                    const RzccStoreT<double, kF64Cluster> store{clp + cc, clh + cc, CT};
-                    int8_t *out = spikes + b * T * CT + cc;
-                    auto emit = [&](int pos, int sign) { out[(long long)pos * CT] = (int8_t)sign; };
-                    ChanSave &sv = save[ps * 32 + lane];
-                    double bb[NBA], aa[NBA], zs[NBA];
-#pragma unroll
-                    for (int k = 0; k < NBA; ++k) {
-                        bb[k] = k < nba ? ba_b[band * nba + k] : 0.0;
-                        aa[k] = k < nba ? ba_a[band * nba + k] : 0.0;
-                        zs[k] = sv.zs[k];
-                    }
-                    RzccState s = sv.rz;
-                    double cs = sv.cs;
-                    int rise = sv.rise, fall = sv.fall;     // start of the running sum's current flat top / bottom (-1: none)
-#pragma unroll 1
-                    for (int i0 = 0; i0 < len; i0 += 8) {
-                        double xv[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) xv[u] = inphase ? (double)xrow[i0 + u] : qrow[i0 + u];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (i0 + u < len) {
-                                const double x = xv[u];
-                                const double y = __dadd_rn(zs[0], __dmul_rn(bb[0], x));
-#pragma unroll
-                                for (int k = 0; k < NBA - 1; ++k)
-                                    zs[k] = __dsub_rn(__dadd_rn(zs[k + 1], __dmul_rn(x, bb[k + 1])), __dmul_rn(y, aa[k + 1]));
-                                const double cprev = cs;
-                                cs = __dadd_rn(cs, y);
-                                const int t = (int)t0 + i0 + u;
-                                if (t >= 1) {
-                                    if (cs > cprev) {
-                                        if (bipolar && fall >= 0) { rzcc_push<0>(s, store, (fall + t - 1) >> 1, -cprev, w, emit); fall = -1; }
-                                        rise = t;
-                                    } else if (cs < cprev) {
-                                        if (rise >= 0) { rzcc_push<1>(s, store, (rise + t - 1) >> 1, cprev, w, emit); rise = -1; }
-                                        fall = t;
-                                    }
-                                }
-                                if ((t & (kSeg - 1)) == kSeg - 1) {
-                                    // a cluster is closed once no later candidate can fall within w of its newest one:
-                                    // a candidate still to come sits at the midpoint of a flat stretch that began at rise / fall
-                                    const int e1 = rise >= 0 ? (rise + t) >> 1 : t, e0 = fall >= 0 ? (fall + t) >> 1 : t;
-                                    if (s.n1 > 0 && e1 - s.last1 >= w) rzcc_resolve<1>(s, store, w, emit);
-                                    if (s.n0 > 0 && e0 - s.last0 >= w) rzcc_resolve<0>(s, store, w, emit);
-                                }
-                            }
+                    for (int k = 0; k < NBA - 1; ++k)
+                        zs[k] = __dsub_rn(__dadd_rn(zs[k + 1], __dmul_rn(x, bb[k + 1])), __dmul_rn(y, aa[k + 1]));
+                    const double prev = acc;
+                    acc = __dadd_rn(acc, y);
+                    const int t = (int)t0 + i;
+                    if (t >= 1) {
+                        if (acc > prev) {
+                            if (bipolar && fl >= 0) { rzcc_push<0>(s, store, (fl + t - 1) >> 1, -prev, w, emit); fl = -1; }
+                            rs = t;
+                        } else if (acc < prev) {
+                            if (rs >= 0) { rzcc_push<1>(s, store, (rs + t - 1) >> 1, prev, w, emit); rs = -1; }
+                            fl = t;
                         }
                     }
-                    if (tile == NT - 1) {
-                        rzcc_close(s, store, w, (int)(T - 1), true, emit);
-                        if (s.overflow) atomicOr(flags + b, 1);
+                    if ((t & (kSeg - 1)) == kSeg - 1) {
+                        // a cluster is closed once no later candidate can fall within w of its newest one: a candidate
+                        // still to come sits at the midpoint of a flat stretch that began at rs / fl
+                        const int e1 = rs >= 0 ? (rs + t) >> 1 : t, e0 = fl >= 0 ? (fl + t) >> 1 : t;
+                        if (s.n1 > 0 && e1 - s.last1 >= w) rzcc_resolve<1>(s, store, w, emit);
+                        if (s.n0 > 0 && e0 - s.last0 >= w) rzcc_resolve<0>(s, store, w, emit);
                     }
-#pragma unroll
-                    for (int k = 0; k < NBA; ++k) sv.zs[k] = zs[k];
-                    sv.rz = s;
-                    sv.cs = cs;
-                    sv.rise = rise; sv.fall = fall;
                 }
+                if (tile == NT - 1) {
+                    rzcc_close(s, store, w, (int)(T - 1), true, emit);
+                    if (s.overflow) atomicOr(flags + b, 1);
+                }
+#pragma unroll
+                for (int k = 0; k < NBA; ++k) sv[ps].zs[k] = zs[k];
+                sv[ps].rz = s; sv[ps].cs = acc; sv[ps].rise = rs; sv[ps].fall = fl;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -642,6 +578,7 @@ struct micloc_xylo {
     double *d_h = nullptr;          // [K] float64 STHT kernel (exact front end)
     double *d_g = nullptr;          // [n_g] its non-zero taps, oldest sample first, when every other tap is exactly zero
     int n_g = 0;
+    long long n_fallback = 0;       // clips the fast exact front end handed to the unbounded kernels so far
     double *d_ba_b = nullptr, *d_ba_a = nullptr;   // [F][nba]
     int16_t *d_w = nullptr;         // [N_in][N] input weights, shift applied
     int16_t *d_thr = nullptr, *d_bias = nullptr;
@@ -878,39 +815,42 @@ static int exact_front_staged(micloc_xylo *c, const void *a, int dtype, long lon
     return micloc_rzcc_encode_f64((const double *)c->zd.ptr, nb, T, CT, p.w, p.bipolar, sgn, c->device, st);
 }
 
-static size_t front_f64_smem(const micloc_xylo *c) {
-    const ChainParams &p = c->p;
-    const int pitch = (f64_pad(kSTile + p.K - 1) + 9) & ~1;
-    const int passes = (c->CT + 31) / 32;
-    return ((size_t)c->n_g + (size_t)p.M * pitch + 2 * (size_t)p.M * kQPitch + (size_t)2 * kF64Cluster * c->CT) * sizeof(double) +
-           (((size_t)2 * kF64Cluster * c->CT + 3) & ~(size_t)3) * sizeof(int) + 2 * (size_t)p.M * kSTile * sizeof(float) +
-           (size_t)passes * 32 * (6 * sizeof(double) + sizeof(RzccState) + 16);      // ChanSave<NBA <= 5>
-}
-
-// the one-kernel exact front end (k_xylo_front_f64) where it applies; clips it flags are redone by the staged kernels
-static bool front_f64_supported(const micloc_xylo *c) {
-    return c->n_g > 0 && c->n_g % 4 == 0 && c->p.M <= 7 && c->nba >= 1 && c->nba <= 5 && c->CT <= 64 &&
-           front_f64_smem(c) <= 227 * 1024 && !getenv("MICLOC_XYLO_STAGED_F64");
+// exact float64 front end, fast form: register-blocked STHT (q in HBM) + one warp per clip for everything behind it;
+// clips whose clusters overflow the streaming encoder are redone by the unbounded staged kernels
+static bool chain_f64_supported(const micloc_xylo *c) {
+    return c->n_g > 0 && c->n_g % 4 == 0 && c->nba >= 1 && c->nba <= 5 && c->CT <= 64 && c->p.M <= 32 &&
+           !getenv("MICLOC_XYLO_STAGED_F64");
 }
 
 template <typename IN_T>
 static int launch_front_f64(micloc_xylo *c, const IN_T *a, long long nb, long long T, int8_t *sgn, int32_t *flg, cudaStream_t st) {
     const ChainParams &p = c->p;
-    const size_t smem = front_f64_smem(c);
-    const int threads = 32 * (p.M + 1);
-    MICLOC_CUDA(cudaMemsetAsync(sgn, 0, (size_t)nb * T * c->CT, st));
-    if (c->nba <= 3) {
-        MICLOC_CUDA(cudaFuncSetAttribute(k_xylo_front_f64<IN_T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_xylo_front_f64<IN_T, 3><<<(unsigned)nb, threads, smem, st>>>(a, c->d_g, c->d_ba_b, c->d_ba_a, sgn, flg, p.M, p.K, c->n_g,
-                                                                   c->nba, c->F, p.w, p.bipolar, T);
-    } else {
-        MICLOC_CUDA(cudaFuncSetAttribute(k_xylo_front_f64<IN_T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_xylo_front_f64<IN_T, 5><<<(unsigned)nb, threads, smem, st>>>(a, c->d_g, c->d_ba_b, c->d_ba_a, sgn, flg, p.M, p.K, c->n_g,
-                                                                   c->nba, c->F, p.w, p.bipolar, T);
+    MICLOC_TRY(c->qd.reserve((size_t)nb * T * p.M * sizeof(double)));
+    double *qd = (double *)c->qd.ptr;
+    {
+        const int ntiles = (int)((T + kSTile - 1) / kSTile);
+        const int mgmax = p.M < kF64MG ? p.M : kF64MG;
+        const size_t smem = ((size_t)c->n_g + (size_t)mgmax * ((f64_pad(kSTile + p.K - 1) + 9) & ~1)) * sizeof(double);
+        if (smem > 227 * 1024) return set_error(MICLOC_ERR_UNSUPPORTED, "exact STHT tile needs %zu B of shared memory", smem);
+        dim3 grid((unsigned)(nb * ntiles), (unsigned)((p.M + kF64MG - 1) / kF64MG));
+        MICLOC_CUDA(cudaFuncSetAttribute(k_stht_f64_sparse<IN_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stht_f64_sparse<IN_T><<<grid, 256, smem, st>>>(a, c->d_g, qd, p.M, p.K, c->n_g, T, ntiles);
     }
-    count_launch(1);
+    MICLOC_CUDA(cudaMemsetAsync(sgn, 0, (size_t)nb * T * c->CT, st));
+    const size_t smem = (size_t)kChainWarps * kChainTile * p.M * (sizeof(double) + sizeof(float));
+    const unsigned grid = (unsigned)((nb + kChainWarps - 1) / kChainWarps);
+    if (c->nba <= 3) {
+        MICLOC_CUDA(cudaFuncSetAttribute(k_xylo_chain_f64<IN_T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_xylo_chain_f64<IN_T, 3><<<grid, 32 * kChainWarps, smem, st>>>(a, qd, c->d_ba_b, c->d_ba_a, sgn, flg, p.M, p.half, c->nba,
+                                                                     c->F, p.w, p.bipolar, nb, T);
+    } else {
+        MICLOC_CUDA(cudaFuncSetAttribute(k_xylo_chain_f64<IN_T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_xylo_chain_f64<IN_T, 5><<<grid, 32 * kChainWarps, smem, st>>>(a, qd, c->d_ba_b, c->d_ba_a, sgn, flg, p.M, p.half, c->nba,
+                                                                     c->F, p.w, p.bipolar, nb, T);
+    }
+    count_launch(2);
     MICLOC_CUDA(cudaGetLastError());
-    // overflowed clips (rare: more than kClusterMax candidates in one cluster, long flat tops) take the unbounded kernels
+    // overflowed clips (rare: more than kF64Cluster candidates in one cluster) take the unbounded kernels
     std::vector<int32_t> hf((size_t)nb);
     MICLOC_CUDA(cudaMemcpyAsync(hf.data(), flg, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MICLOC_CUDA(cudaStreamSynchronize(st));
@@ -919,6 +859,7 @@ static int launch_front_f64(micloc_xylo *c, const IN_T *a, long long nb, long lo
             MICLOC_TRY(exact_front_staged(c, a + (size_t)i * T * p.M, sizeof(IN_T) == 2 ? MICLOC_I16 : MICLOC_F32, 1, T,
                                           sgn + (size_t)i * T * c->CT, st));
             MICLOC_CUDA(cudaMemsetAsync(flg + i, 0, sizeof(int32_t), st));
+            c->n_fallback++;
         }
     return MICLOC_OK;
 }
@@ -940,8 +881,8 @@ extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int
     if (!flg) { MICLOC_TRY(c->flags.reserve((size_t)B * sizeof(int32_t))); flg = (int32_t *)c->flags.ptr; }
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     // the batch goes through in chunks that bound the scratch (float64 intermediates of the exact front end)
-    const bool staged_f64 = exact && !front_f64_supported(c);       // float64 q and z in HBM
-    const size_t per_clip = (size_t)T * (staged_f64 ? (size_t)p.M * 8 + (size_t)CT * 8 * 2 + (size_t)CT * 3 : (size_t)p.M * 4 + CT);
+    const bool staged_f64 = exact && !chain_f64_supported(c);       // float64 q AND z in HBM (else q only)
+    const size_t per_clip = (size_t)T * (staged_f64 ? (size_t)p.M * 8 + (size_t)CT * 8 * 2 + (size_t)CT * 3 : (size_t)p.M * (exact ? 8 : 4) + CT);
     long long chunk = (long long)(((size_t)6 << 30) / per_clip);
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
@@ -953,7 +894,7 @@ extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int
         const char *a = (const char *)audio + (size_t)b0 * T * p.M * esz;
         int8_t *sgn = (int8_t *)c->signed_spk.ptr;
         if (exact) {
-            if (front_f64_supported(c)) {
+            if (chain_f64_supported(c)) {
                 if (dtype == MICLOC_I16) MICLOC_TRY(launch_front_f64(c, (const int16_t *)a, nb, T, sgn, flg + b0, st));
                 else MICLOC_TRY(launch_front_f64(c, (const float *)a, nb, T, sgn, flg + b0, st));
             } else {

@@ -119,9 +119,10 @@ def test_batch_exact_equals_oracle(name, int16):
 
 
 @pytest.mark.parametrize("name,int16", [("xylo_c3_bipolar", True), ("xylo_3band_o2", False)])
-def test_one_kernel_exact_front_end_equals_staged_float64(name, int16, monkeypatch):
-    """The exact front end as ONE kernel per clip (STHT, band filters, cumsum, RZCC in float64, nothing in HBM but the
-    spikes) against the staged float64 kernels with unbounded candidate clusters, on whole seconds."""
+def test_fast_exact_front_end_equals_staged_float64(name, int16, monkeypatch):
+    """The fast exact front end (register-blocked float64 STHT over the non-zero taps + one warp per clip for band
+    filters, cumsum and streaming find_peaks) against the staged float64 kernels (dense FIR in lfilter's order,
+    unbounded candidate clusters), on whole seconds."""
     g = H.load(name)
     eng = H.xylo_engine(g)
     x = dev(H.xylo_synth_clips(g, 5, 48_000, seed=77, int16=int16))
