@@ -163,6 +163,33 @@ constexpr int kF64Cluster = 32;         // candidates buffered per open cluster 
 constexpr int kChainTile = 64;          // time steps staged per warp
 constexpr int kChainWarps = 8;          // clips per CTA
 
+using F64Store = RzccStoreT<double, kF64Cluster>;
+
+// cluster of POL candidates closed: one candidate stays; of two (always nearer than w) the higher one, the later one on
+// a tie; three or more go through the greedy rule of micloc_device.cuh
+template <int POL, typename Emit>
+__device__ __forceinline__ void f64_resolve(RzccState &s, const F64Store &st, int w, Emit &&emit) {
+    const int n = POL ? s.n1 : s.n0;
+    if (n <= 2) {
+        const int *cp = st.cl_pos + POL * kF64Cluster;
+        const double *ch = st.cl_h + POL * kF64Cluster;
+        const int keep = (n == 2 && ch[1] >= ch[0]) ? 1 : 0;
+        emit(cp[keep], POL ? 1 : -1);
+        if (POL) s.n1 = 0; else s.n0 = 0;
+        return;
+    }
+    rzcc_resolve<POL>(s, st, w, emit);
+}
+template <int POL, typename Emit>
+__device__ __forceinline__ void f64_push(RzccState &s, const F64Store &st, int pos, double h, int w, Emit &&emit) {
+    if ((POL ? s.n1 : s.n0) > 0 && pos - (POL ? s.last1 : s.last0) >= w) f64_resolve<POL>(s, st, w, emit);
+    const int n = POL ? s.n1 : s.n0;
+    if (n == kF64Cluster) { s.overflow = 1; return; }
+    st.cl_pos[POL * kF64Cluster + n] = pos;
+    st.cl_h[POL * kF64Cluster + n] = h;
+    if (POL) { s.last1 = pos; s.n1 = n + 1; } else { s.last0 = pos; s.n0 = n + 1; }
+}
+
 template <typename IN_T, int NBA>
 __global__ void __launch_bounds__(32 * kChainWarps, 3)
 k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, const double *__restrict__ ba_b,
@@ -184,6 +211,8 @@ k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, c
     struct Save { double zs[NBA]; double cs; int rise, fall; RzccState rz; } sv[2];
     int cl_pos[2][2 * kF64Cluster];
     double cl_h[2][2 * kF64Cluster];
+    int q_pos[kChainTile + 1];          // candidates of the tile at work, in time order (+ the scratch slot behind a full queue)
+    double q_h[kChainTile + 1];
 #pragma unroll 1
     for (int ps = 0; ps < 2; ++ps) {
 #pragma unroll
@@ -211,7 +240,7 @@ k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, c
                 const int c = cc % C2, band = cc / C2;
                 const bool inphase = c < M;
                 const int col = inphase ? c : c - M;
-                const RzccStoreT<double, kF64Cluster> store{cl_pos[ps], cl_h[ps], 1};
+                const F64Store store{cl_pos[ps], cl_h[ps], 1};
                 int8_t *out = spikes + b * T * CT + cc;
                 auto emit = [&](int pos, int sign) { out[(long long)pos * CT] = (int8_t)sign; };
                 double bb[NBA], aa[NBA], zs[NBA];
@@ -224,6 +253,10 @@ k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, c
                 RzccState s = sv[ps].rz;
                 double acc = sv[ps].cs;
                 int rs = sv[ps].rise, fl = sv[ps].fall;    // start of the running sum's current flat top / bottom (-1: none)
+                // (a) the sequential part, the same instructions in every lane: filter, running sum, candidate
+                //     detection; candidates are only queued here
+                int nq = 0;
+                unsigned long long qpol = 0ull;
 #pragma unroll 4
                 for (int i = 0; i < len; ++i) {
                     const double x = inphase ? (double)xs[i * M + col] : qs[i * M + col];
@@ -234,22 +267,33 @@ k_xylo_chain_f64(const IN_T *__restrict__ audio, const double *__restrict__ q, c
                     const double prev = acc;
                     acc = __dadd_rn(acc, y);
                     const int t = (int)t0 + i;
-                    if (t >= 1) {
-                        if (acc > prev) {
-                            if (bipolar && fl >= 0) { rzcc_push<0>(s, store, (fl + t - 1) >> 1, -prev, w, emit); fl = -1; }
-                            rs = t;
-                        } else if (acc < prev) {
-                            if (rs >= 0) { rzcc_push<1>(s, store, (rs + t - 1) >> 1, prev, w, emit); rs = -1; }
-                            fl = t;
-                        }
+                    // candidate test without branches (the lanes' events fall on different samples): slot nq of the
+                    // queue is written at every step and kept when the step closed a flat top (peak) or bottom (valley)
+                    const bool up = acc > prev, down = acc < prev;           // sample 0 has no predecessor: rs = fl = -1 there
+                    const bool peak = down && rs >= 0, valley = up && fl >= 0 && bipolar;
+                    q_pos[nq] = ((peak ? rs : fl) + t - 1) >> 1;
+                    q_h[nq] = peak ? prev : -prev;
+                    qpol |= (unsigned long long)peak << nq;
+                    nq += (peak || valley) ? 1 : 0;
+                    rs = up ? t : (down ? -1 : rs);
+                    fl = down ? t : (up ? -1 : fl);
+                    if (t == 0) { rs = -1; fl = -1; }
+                }
+                // (b) the queued candidates enter the clusters, the lanes of the warp in step (each lane's events fall
+                //     on different samples: handled where they occur, every one of them would run with one lane active)
+                const unsigned am = __activemask();
+                for (int j = 0; __any_sync(am, j < nq); ++j)
+                    if (j < nq) {
+                        if ((qpol >> j) & 1ull) f64_push<1>(s, store, q_pos[j], q_h[j], w, emit);
+                        else f64_push<0>(s, store, q_pos[j], q_h[j], w, emit);
                     }
-                    if ((t & (kSeg - 1)) == kSeg - 1) {
-                        // a cluster is closed once no later candidate can fall within w of its newest one: a candidate
-                        // still to come sits at the midpoint of a flat stretch that began at rs / fl
-                        const int e1 = rs >= 0 ? (rs + t) >> 1 : t, e0 = fl >= 0 ? (fl + t) >> 1 : t;
-                        if (s.n1 > 0 && e1 - s.last1 >= w) rzcc_resolve<1>(s, store, w, emit);
-                        if (s.n0 > 0 && e0 - s.last0 >= w) rzcc_resolve<0>(s, store, w, emit);
-                    }
+                {
+                    // a cluster is closed once no later candidate can fall within w of its newest one: a candidate
+                    // still to come sits at the midpoint of a flat stretch that began at rs / fl
+                    const int t = (int)t0 + len - 1;
+                    const int e1 = rs >= 0 ? (rs + t) >> 1 : t, e0 = fl >= 0 ? (fl + t) >> 1 : t;
+                    if (s.n1 > 0 && e1 - s.last1 >= w) f64_resolve<1>(s, store, w, emit);
+                    if (s.n0 > 0 && e0 - s.last0 >= w) f64_resolve<0>(s, store, w, emit);
                 }
                 if (tile == NT - 1) {
                     rzcc_close(s, store, w, (int)(T - 1), true, emit);
