@@ -64,7 +64,34 @@ struct micloc_snn {
     size_t ev_used = 0;            // events recorded since the last micloc_snn_last_kernel_ms
     int last_kernels = 0;
     int sm_count = 148;
+    double pole_radius = 1.0;      // largest pole modulus of the band-pass: how fast it forgets (time-segmented kernels)
+    long long seg_reruns = 0;      // clips a segmented run handed back to the sequential kernel so far
 };
+
+// Few long clips (BASELINE config 5): cut the sequential stages into time segments (k_chain_seg / k_neuron_seg).
+struct SegPlan { int seg_len, warm, tail, nseg, nwarm, nseg_neuron, seg_len_neuron; };
+static bool plan_segments(const micloc_snn *c, long long B, long long T, int nb, SegPlan &sp) {
+    const ChainParams &p = c->p;
+    if (getenv("MICLOC_NO_SEGMENTS")) return false;
+    const long long chains = B * p.C2 * nb;
+    if (chains >= 16384 || T < 32768) return false;             // enough sequential chains to fill the GPU already
+    if (!(c->pole_radius > 0.0 && c->pole_radius < 0.9995)) return false;
+    // band-pass transient below 1e-9 of full scale, the decision latency of the RZCC encoder on top
+    int warm = (int)std::ceil(std::log(1e-9) / std::log(c->pole_radius)) + 2 * rzcc_lag(p.w);
+    warm = (warm + 31) & ~31;
+    long long seg = 4ll * warm;                                  // 25 % redundant work at most
+    const long long want = (65536 + chains - 1) / chains;        // segments per chain that fill the GPU
+    if (T / seg > want) seg = (T + want - 1) / want;
+    seg = (seg + 31) & ~31ll;
+    if (seg * 2 > T) return false;
+    sp.seg_len = (int)seg; sp.warm = warm; sp.tail = rzcc_lag(p.w) + kSeg;
+    sp.nseg = (int)((T + seg - 1) / seg);
+    // alpha kernel h[n] = c n a^n: below 1e-12 of its peak
+    sp.nwarm = (int)std::ceil(std::log(1e-12) / std::log((double)p.na)) + p.nL + 64;
+    sp.seg_len_neuron = 1024 > 4 * sp.nwarm ? 1024 : 4 * sp.nwarm;
+    sp.nseg_neuron = (int)((T + sp.seg_len_neuron - 1) / sp.seg_len_neuron);
+    return true;
+}
 
 static int upload_bf(micloc_snn *c, const double *bf, int G) {
     const int C2 = c->p.C2;
@@ -148,6 +175,13 @@ extern "C" int micloc_snn_create(const micloc_snn_config *cfg, int device, miclo
     p.nsec = cfg->n_sections;
     rc = sos_to_f32(cfg->sos, cfg->n_sections, &p.sos[0][0]);
     if (rc) { micloc_snn_destroy(c); return rc; }
+    c->pole_radius = 0.0;
+    for (int k = 0; k < cfg->n_sections; ++k) {
+        const double a1 = cfg->sos[k * 6 + 4] / cfg->sos[k * 6 + 3], a2 = cfg->sos[k * 6 + 5] / cfg->sos[k * 6 + 3];
+        const double disc = a1 * a1 - 4.0 * a2;
+        const double r = disc < 0.0 ? std::sqrt(a2) : (std::fabs(a1) + std::sqrt(disc)) / 2.0;
+        if (r > c->pole_radius) c->pole_radius = r;
+    }
     p.w = cfg->robust_width; p.bipolar = cfg->bipolar ? 1 : 0;
     p.na = (float)cfg->neuron_decay; p.nc = (float)cfg->neuron_scale; p.nL = cfg->neuron_len;
     p.ncT = (float)(cfg->neuron_scale * std::pow(cfg->neuron_decay, (double)cfg->neuron_len));
@@ -313,7 +347,20 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     const ChainParams &p = c->p;
     MICLOC_TRY(c->gram.reserve((size_t)B * p.C2 * p.C2 * sizeof(double)));
     dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
-    k_gram<<<gg, 256, 0, st>>>(vmem, (double *)c->gram.ptr, p.C2, T, 0);
+    if ((long long)gg.x * gg.y < 2ll * c->sm_count && T >= 65536 && !getenv("MICLOC_NO_SEGMENTS")) {
+        // few long clips: time slabs so that the sum fills the GPU
+        int nslab = (int)((4ll * c->sm_count + (long long)gg.x * gg.y - 1) / ((long long)gg.x * gg.y));
+        if (nslab > 64) nslab = 64;
+        const long long slab_len = (T + nslab - 1) / nslab;
+        MICLOC_TRY(c->part.reserve((size_t)nslab * B * p.C2 * p.C2 * sizeof(double)));
+        gg.z = (unsigned)nslab;
+        k_gram_slab<<<gg, 256, 0, st>>>(vmem, (double *)c->part.ptr, p.C2, B, T, 0, slab_len);
+        const long long ne = B * p.C2 * p.C2;
+        k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, nslab);
+        count_launch(1);
+    } else {
+        k_gram<<<gg, 256, 0, st>>>(vmem, (double *)c->gram.ptr, p.C2, T, 0);
+    }
     const size_t smem = (size_t)p.C2 * p.C2 * sizeof(double);
     MICLOC_CUDA(cudaFuncSetAttribute(k_power_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_power_argmax<<<(unsigned)B, 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
@@ -341,11 +388,44 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
     const long long l0 = g_launches.load();
     MICLOC_CUDA(cudaMemsetAsync(flg, 0, (size_t)B * sizeof(int32_t), st));
     MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, q, B, T, st));
-    MICLOC_TRY(launch_chain_any(p, audio, dtype, q, c->d_sos, 1, z_dev, spk, flg, B, T, st));
+    SegPlan sp{};
+    const bool segmented = plan_segments(c, B, T, 1, sp);
+    if (segmented) {
+        const long long n = B * sp.nseg * p.C2;
+        const unsigned grid = (unsigned)((n + 127) / 128);
+        if (dtype == MICLOC_I16)
+            k_chain_seg<int16_t><<<grid, 128, 0, st>>>((const int16_t *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
+                                                       sp.seg_len, sp.warm, sp.tail, sp.nseg);
+        else
+            k_chain_seg<float><<<grid, 128, 0, st>>>((const float *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
+                                                     sp.seg_len, sp.warm, sp.tail, sp.nseg);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+        // what the segments could not vouch for (or an overflowed cluster) is redone by the sequential kernel: its own
+        // overflow flag is then the clip's
+        std::vector<int32_t> hf((size_t)B);
+        MICLOC_CUDA(cudaMemcpyAsync(hf.data(), flg, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MICLOC_CUDA(cudaStreamSynchronize(st));
+        const size_t esz = dtype == MICLOC_I16 ? 2 : 4;
+        for (long long i = 0; i < B; ++i)
+            if (hf[(size_t)i] & 1) {
+                MICLOC_CUDA(cudaMemsetAsync(flg + i, 0, sizeof(int32_t), st));
+                MICLOC_TRY(launch_chain_any(p, (const char *)audio + (size_t)i * T * p.M * esz, dtype, q + (size_t)i * T * p.M, c->d_sos, 1,
+                                            z_dev ? z_dev + (size_t)i * T * p.C2 : nullptr, spk + (size_t)i * T * p.C2, flg + i, 1, T, st));
+                c->seg_reruns++;
+            }
+    } else {
+        MICLOC_TRY(launch_chain_any(p, audio, dtype, q, c->d_sos, 1, z_dev, spk, flg, B, T, st));
+    }
     const bool need_vmem = vmem_dev || y_dev || power_dev || doa_dev;
     if (need_vmem) {
-        const long long n = B * p.C2;
-        k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T);
+        if (segmented) {
+            const long long n = B * sp.nseg_neuron * p.C2;
+            k_neuron_seg<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T, sp.seg_len_neuron, sp.nwarm, sp.nseg_neuron);
+        } else {
+            const long long n = B * p.C2;
+            k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T);
+        }
         count_launch(1);
         MICLOC_CUDA(cudaGetLastError());
     }

@@ -121,6 +121,120 @@ k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
 }
 
 // ---------------------------------------------------------------------------
+// S2' / S3': the same two stages cut into TIME SEGMENTS, for few long clips (BASELINE config 5: one 10 s clip of 64
+// microphones is 128 sequential chains of 480 000 steps -- 128 threads).  Band-pass and alpha kernel forget their
+// past geometrically and the RZCC decisions are local (a cluster ends at the first gap >= w), so segment s starts
+// from zero state `warm` samples early, runs `tail` samples past its end and keeps only the spikes / membrane values
+// of its own range: (clip, channel, segment) chains run in parallel.  What a segment cannot vouch for sets the
+// clip's flag bit 0 and the clip is redone sequentially by the host code: a cluster still open at the segment start
+// that began inside the settling half of the warm-up, or one that holds a spike of the segment and is still open at
+// the end of the tail.  The running sum restarts at every warm-up: heights are only compared inside a cluster, where
+// a common offset cancels (up to float32 rounding of the sum, i.e. within the path's tolerance, not bit for bit).
+// RZCC is scale-free: in digital silence the band-pass's decaying tail IS the signal and keeps spiking for tens of
+// milliseconds, so "forgetting" only holds relative to a live input -- a run of kSilenceRun exactly-zero input samples
+// anywhere in a segment's span flags the clip as well.
+constexpr int kSilenceRun = 64;
+// ---------------------------------------------------------------------------
+template <typename IN_T>
+__global__ void __launch_bounds__(128)
+k_chain_seg(const IN_T *__restrict__ audio, const float *__restrict__ q, const float *__restrict__ band_sos,
+            float *__restrict__ z_out, int8_t *__restrict__ spikes, int32_t *__restrict__ flags,
+            const __grid_constant__ ChainParams p, long long B, long long T, int nb, int seg_len, int warm, int tail,
+            int nseg) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CT = p.C2 * nb;
+    if (idx >= B * nseg * CT) return;
+    const int cc = (int)(idx % CT);
+    const int seg = (int)((idx / CT) % nseg);
+    const long long b = idx / ((long long)CT * nseg);
+    const int band = cc / p.C2, c = cc % p.C2;
+
+    float sos[kMaxSections][5];
+#pragma unroll
+    for (int k = 0; k < kMaxSections; ++k)
+#pragma unroll
+        for (int e = 0; e < 5; ++e) sos[k][e] = band_sos[(band * kMaxSections + k) * 5 + e];
+
+    const long long start = (long long)seg * seg_len;
+    const long long end = min(T, start + seg_len);
+    const long long t_begin = max(0ll, start - warm);
+    const long long t_stop = min(T, end + tail);
+    BiquadState bq; biquad_reset(bq);
+    RzccState rz; rzcc_reset(rz);
+    int cl_pos[2 * kClusterMax]; float cl_h[2 * kClusterMax];
+    const RzccStore store{cl_pos, cl_h, 1};
+    int8_t *sp = spikes + b * T * CT + cc;
+    auto emit = [&](int pos, int sign) { if (pos >= start && pos < end) sp[(long long)pos * CT] = (int8_t)sign; };
+
+    const bool inphase = c < p.M;
+    const IN_T *xa = audio + b * T * p.M + (inphase ? c : 0);
+    const float *xq = q + b * T * p.M + (inphase ? 0 : c - p.M);
+    long long src = ((t_begin - (long long)p.half) % T + T) % T;      // (t - K/2) mod T at t = t_begin
+    auto fetch = [&](long long t) -> float {
+        if (t >= t_stop) return 0.f;
+        if (!inphase) return xq[t * p.M];
+        long long s2 = src + (t - t_begin);
+        if (s2 >= T) s2 -= T;
+        return to_f32<IN_T>(xa[s2 * p.M]);
+    };
+    bool unsynced = false;
+    int zrun = 0;
+    float xc[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xc[u] = fetch(t_begin + u);
+    for (long long t4 = t_begin; t4 < t_stop; t4 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xn[u] = fetch(t4 + 4 + u);       // next inputs on their way while these 4 steps run
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long t = t4 + u;
+            if (t < t_stop) {
+                if (t == start && seg > 0) {
+                    // decisions from here on are this segment's: every open cluster must have begun after the filters settled
+                    const long long settled = t_begin + (warm >> 1);
+                    if ((rz.n1 > 0 && cl_pos[kClusterMax] < settled) || (rz.n0 > 0 && cl_pos[0] < settled)) unsynced = true;
+                }
+                zrun = xc[u] == 0.f ? zrun + 1 : 0;
+                if (zrun >= kSilenceRun) unsynced = true;
+                const float z = biquad_step(sos, p.nsec, bq, xc[u]);
+                if (t >= start && t < end) {
+                    if (z_out) z_out[(b * T + t) * CT + cc] = z;
+                    sp[t * CT] = 0;
+                }
+                rzcc_detect(rz, store, p.bipolar, p.w, (int)t, z, emit);
+                const bool last = t == T - 1;
+                if (last || (t & (kSeg - 1)) == kSeg - 1) rzcc_close(rz, store, p.w, (int)t, last, emit);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xc[u] = xn[u];
+    }
+    // a cluster that is still open behind the tail and holds a candidate of this segment was not decided
+    if (t_stop < T && ((rz.n1 > 0 && cl_pos[kClusterMax] < end) || (rz.n0 > 0 && cl_pos[0] < end))) unsynced = true;
+    if ((rz.overflow || unsynced) && flags) atomicOr(flags + b, 1);
+}
+
+static __global__ void __launch_bounds__(128)
+k_neuron_seg(const int8_t *__restrict__ spikes, float *__restrict__ vmem, const __grid_constant__ ChainParams p,
+             long long B, long long T, int seg_len, int warm, int nseg) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * nseg * p.C2) return;
+    const int c = (int)(idx % p.C2);
+    const int seg = (int)((idx / p.C2) % nseg);
+    const long long b = idx / ((long long)p.C2 * nseg);
+    const int8_t *sp = spikes + b * T * p.C2 + c;
+    float *vm = vmem + b * T * p.C2 + c;
+    const long long start = (long long)seg * seg_len, end = min(T, start + seg_len);
+    NeuronState n; neuron_reset(n);
+    for (long long t = max(0ll, start - warm); t < end; ++t) {
+        const float s = (float)sp[t * p.C2];
+        const float sd = t >= p.nL ? (float)sp[(t - p.nL) * p.C2] : 0.f;
+        const float v = neuron_step(p, n, s, sd);
+        if (t >= start) vm[t * p.C2] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // S4a: Gram matrix of the membrane signals   C[b][i][j] = sum_t v[t][i] v[t][j]
 //      mean_t (v[t] . w_g)^2 == w_g^T (C/T) w_g, so the per-DoA power of
 //      snn_beamformer.py:368 + target_snn_localization.py:462 needs no T x G pass.
@@ -137,6 +251,34 @@ k_gram(const float *__restrict__ vmem, double *__restrict__ gram, int C2, long l
     for (long long t = t_start; t < T; ++t) acc = fma((double)v[t * C2 + i], (double)v[t * C2 + j], acc);
     gram[(b * C2 + i) * C2 + j] = acc;
     gram[(b * C2 + j) * C2 + i] = acc;
+}
+
+// the same sum cut into time slabs (few long clips): part[slab][b][i][j], added up in slab order by k_gram_reduce
+// (a fixed order: the result does not depend on scheduling)
+static __global__ void __launch_bounds__(256)
+k_gram_slab(const float *__restrict__ vmem, double *__restrict__ part, int C2, long long B, long long T, long long t_start,
+            long long slab_len) {
+    const long long b = blockIdx.x;
+    const int pair = blockIdx.y * blockDim.x + threadIdx.x;
+    if (pair >= C2 * C2) return;
+    const int i = pair / C2, j = pair % C2;
+    if (j < i) return;
+    const long long t0 = t_start + (long long)blockIdx.z * slab_len, t1 = min(T, t0 + slab_len);
+    const float *v = vmem + b * T * C2;
+    double acc = 0.0;
+    for (long long t = t0; t < t1; ++t) acc = fma((double)v[t * C2 + i], (double)v[t * C2 + j], acc);
+    part[((long long)blockIdx.z * B + b) * C2 * C2 + i * C2 + j] = acc;
+}
+static __global__ void __launch_bounds__(256)
+k_gram_reduce(const double *__restrict__ part, double *__restrict__ gram, int C2, long long B, int nslab) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * C2 * C2) return;
+    const int j = (int)(e % C2), i = (int)((e / C2) % C2);
+    const long long b = e / ((long long)C2 * C2);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    double acc = 0.0;
+    for (int s = 0; s < nslab; ++s) acc += part[((long long)s * B + b) * C2 * C2 + lo * C2 + hi];
+    gram[e] = acc;
 }
 
 // ---------------------------------------------------------------------------

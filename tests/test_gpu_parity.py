@@ -268,21 +268,50 @@ def test_full_size_config4_multi_source_360_grid():
     assert int(out["flags"].sum()) == 0
 
 
-def test_full_size_config5_64_mics_10s_512_grid():
-    """Config 5 size: one 10 s clip (T = 480 000) on the 64-microphone random array, G = 512 (staged path:
-    the fused kernel covers up to 7 microphones) against the oracle."""
-    g = H.load("snn_c5_random64")
+@pytest.mark.parametrize("name", ["snn_c5_random64", "snn_c5_linear64"])
+def test_full_size_config5_64_mics_10s_512_grid(name):
+    """Config 5 size: one 10 s clip (T = 480 000) on the 64-microphone arrays, G = 512, against the oracle.  Few long
+    clips take the time-segmented kernels (k_chain_seg / k_neuron_seg / k_gram_slab)."""
+    import time
+    g = H.load(name)
     T = 480_000
     x, _ = H.synth_clips(g, 1, T, seed=51, snrs_db=(10.0,))
     eng = engine_for(g, T)
-    out = eng.run(to_dev(x), want_spikes=True, fused=False)
+    xd = to_dev(x)
+    out = eng.run(xd, want_spikes=True, fused=False)
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = eng.run(xd, want_spikes=True, fused=False)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    print(f"config 5 ({name}): {ms:.1f} ms per 10 s clip")
+    assert ms < 100.0                                     # (tens of seconds per clip before the segmented kernels)
     cfg = H.oracle_cfg(g)
     cfg.nir = O.neuron_kernel(np.arange(T) / float(g["fs"]), float(g["tau"]), float(g["tau"]))
     ref = O.snn_run_batch(cfg, x, nthreads=1, want_spikes=True)
     assert H.spike_agreement(out["spikes"].cpu().numpy(), ref["spikes"]) >= SPIKE_AGREE
     assert int(out["doa"][0]) == int(ref["doa"][0])
     assert H.rel_err(out["power"].cpu().numpy(), ref["power"]) < 2e-3
+    assert int(out["flags"].sum()) == 0
+
+
+def test_time_segmented_kernels_equal_the_sequential_ones(monkeypatch):
+    """Few long clips: (clip, channel, time segment) chains with warm-up against one chain per (clip, channel)."""
+    for name, B, T in (("snn_c5_random64", 1, 100_000), ("snn_c1_bipolar", 3, 70_001), ("snn_c1_unipolar", 2, 48_000)):
+        g = H.load(name)
+        x, _ = H.synth_clips(g, B, T, seed=7, snrs_db=(0.0, 15.0))
+        x[-1, T // 3: T // 3 + 9000] = 0                                # a stretch of digital silence inside one clip
+        eng = engine_for(g, T)
+        xd = to_dev(x)
+        monkeypatch.delenv("MICLOC_NO_SEGMENTS", raising=False)
+        seg = eng.run_taps(xd, want=("spikes", "vmem", "power", "doa"))
+        monkeypatch.setenv("MICLOC_NO_SEGMENTS", "1")
+        one = eng.run_taps(xd, want=("spikes", "vmem", "power", "doa"))
+        torch.cuda.synchronize()
+        assert H.spike_agreement(seg["spikes"].cpu().numpy(), one["spikes"].cpu().numpy()) >= 0.9999, name
+        assert H.rel_err(seg["power"].cpu().numpy(), one["power"].cpu().numpy()) < 1e-3
+        assert torch.equal(seg["doa"], one["doa"])
+        assert torch.equal(seg["flags"], one["flags"])
 
 
 def test_stht_linearity_and_zero_input():
