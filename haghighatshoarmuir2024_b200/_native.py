@@ -60,6 +60,8 @@ SYMBOLS = {
     "micloc_snn_destroy": (C.c_int, [_vp]),
     "micloc_snn_set_bf": (C.c_int, [_vp, _dp, _i32]),
     "micloc_snn_run": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "micloc_snn_refine": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "micloc_snn_refined_count": (_i64, [_vp]),
     "micloc_snn_run_taps": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "micloc_snn_run_host": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, C.c_int]),
     "micloc_snn_gram": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp]),

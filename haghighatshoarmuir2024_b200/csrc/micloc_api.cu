@@ -56,6 +56,10 @@ struct micloc_snn {
     cudaEvent_t ev_last = nullptr;       // recorded behind the last launch of micloc_snn_run / run_taps / gram: run_host's
                                          // private streams wait for it before they touch the shared scratch
     DevBuf q, spikes, vmem, gram, flags, part;
+    DevBuf rz, rzd, rspk, rflag;            // one clip's worth of scratch of the overflow path (heal_overflow)
+    long long refined = 0;                  // clips redone with the unbounded encoder so far
+    int32_t *h_flags_all = nullptr;         // pinned host copy of a run_host batch's flags
+    size_t h_flags_cap = 0;
     // host staging for run_host
     DevBuf h_audio[2], h_spk[2], h_pow[2], h_doa[2], h_flg[2];
     cudaStream_t hs[2] = {nullptr, nullptr};
@@ -209,6 +213,8 @@ extern "C" int micloc_snn_destroy(micloc_snn *c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_taps); cudaFree(c->d_sos); cudaFree(c->d_W); cudaFree(c->d_Wd); cudaFree(c->d_sm_slots);
     c->q.release(); c->spikes.release(); c->vmem.release(); c->gram.release(); c->flags.release(); c->part.release();
+    c->rz.release(); c->rzd.release(); c->rspk.release(); c->rflag.release();
+    if (c->h_flags_all) cudaFreeHost(c->h_flags_all);
     for (int i = 0; i < 2; ++i) {
         c->h_audio[i].release(); c->h_spk[i].release(); c->h_pow[i].release(); c->h_doa[i].release(); c->h_flg[i].release();
         if (c->hs[i]) cudaStreamDestroy(c->hs[i]);
@@ -370,6 +376,42 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     return MICLOC_OK;
 }
 
+// ---------------------------------------------------------------------------
+// RZCC overflow (flags bit 0): the streaming encoder of the staged / fused kernels buffers kClusterMax candidates per
+// cluster and follows flat tops of kPlateauMax exact zeros (digital silence: the float32 band-pass output underflows
+// to exact 0).  The staged entry points redo the spikes of such a clip HERE with the unbounded float64 encoder
+// (micloc_rzcc_encode_f64 on the clip's band-pass output) and clear the bit; costs one flag read-back + stream sync.
+// ---------------------------------------------------------------------------
+static int heal_overflow(micloc_snn *c, const void *audio, int dtype, const float *q, float *z_dev, int8_t *spk,
+                         int32_t *flg, long long B, long long T, cudaStream_t st) {
+    const ChainParams &p = c->p;
+    std::vector<int32_t> hf((size_t)B);
+    MICLOC_CUDA(cudaMemcpyAsync(hf.data(), flg, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MICLOC_CUDA(cudaStreamSynchronize(st));
+    const size_t n_c = (size_t)T * p.C2, esz = dtype == MICLOC_I16 ? 2 : 4;
+    for (long long i = 0; i < B; ++i) {
+        if (!(hf[(size_t)i] & 1)) continue;
+        MICLOC_TRY(c->rzd.reserve(n_c * sizeof(double)));
+        const float *z = z_dev ? z_dev + (size_t)i * n_c : nullptr;
+        if (!z) {      // the band-pass output was not kept: once more for this clip
+            MICLOC_TRY(c->rz.reserve(n_c * sizeof(float)));
+            MICLOC_TRY(c->rspk.reserve(n_c));
+            MICLOC_TRY(c->rflag.reserve(sizeof(int32_t)));
+            MICLOC_TRY(launch_chain_any(p, (const char *)audio + (size_t)i * T * p.M * esz, dtype, q + (size_t)i * T * p.M,
+                                        c->d_sos, 1, (float *)c->rz.ptr, (int8_t *)c->rspk.ptr, (int32_t *)c->rflag.ptr, 1, T, st));
+            z = (const float *)c->rz.ptr;
+        }
+        k_f32_to_f64<<<(unsigned)((n_c + 255) / 256), 256, 0, st>>>(z, (double *)c->rzd.ptr, (long long)n_c);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+        MICLOC_TRY(micloc_rzcc_encode_f64((const double *)c->rzd.ptr, 1, T, p.C2, p.w, p.bipolar, spk + (size_t)i * n_c,
+                                          c->device, st));
+        MICLOC_CUDA(cudaMemsetAsync(flg + i, 0, sizeof(int32_t), st));
+        c->refined++;
+    }
+    return MICLOC_OK;
+}
+
 extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T,
                                    float *q_dev, float *z_dev, int8_t *spikes_dev, float *vmem_dev,
                                    float *y_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
@@ -417,6 +459,7 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
     } else {
         MICLOC_TRY(launch_chain_any(p, audio, dtype, q, c->d_sos, 1, z_dev, spk, flg, B, T, st));
     }
+    MICLOC_TRY(heal_overflow(c, audio, dtype, q, z_dev, spk, flg, B, T, st));
     const bool need_vmem = vmem_dev || y_dev || power_dev || doa_dev;
     if (need_vmem) {
         if (segmented) {
@@ -461,6 +504,8 @@ extern "C" int micloc_snn_gram(micloc_snn *c, const void *audio, int dtype, int6
     MICLOC_TRY(launch_stht_any(p, c->d_taps, audio, dtype, (float *)c->q.ptr, B, T, st));
     MICLOC_TRY(launch_chain_any(p, audio, dtype, (float *)c->q.ptr, c->d_sos, 1, nullptr, (int8_t *)c->spikes.ptr,
                                 (int32_t *)c->flags.ptr, B, T, st));
+    MICLOC_TRY(heal_overflow(c, audio, dtype, (const float *)c->q.ptr, nullptr, (int8_t *)c->spikes.ptr, (int32_t *)c->flags.ptr,
+                             B, T, st));
     const long long n = B * p.C2;
     k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const int8_t *)c->spikes.ptr, (float *)c->vmem.ptr, p, B, T);
     dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
@@ -502,6 +547,42 @@ extern "C" int micloc_snn_run(micloc_snn *c, const void *audio, int dtype, int64
 }
 
 // ---------------------------------------------------------------------------
+// The fused kernel only REPORTS an overflowed clip (flags bit 0): micloc_snn_run stays stream-ordered.  micloc_snn_refine
+// is its synchronising companion: it reads the flags back and reruns every flagged clip through the staged kernels,
+// which heal the overflow themselves (heal_overflow).  micloc_snn_run_host calls it on its own.
+// ---------------------------------------------------------------------------
+extern "C" int micloc_snn_refine(micloc_snn *c, const void *audio, int dtype, int64_t B, int64_t T, int8_t *spikes_dev,
+                                 float *power_dev, int32_t *doa_dev, int32_t *flags_dev, int64_t *n_refined, void *stream) {
+    MICLOC_TRY(check_run_args(c, audio, dtype, B, T));
+    if (n_refined) *n_refined = 0;
+    if (!flags_dev) return set_error(MICLOC_ERR_SHAPE, "refine needs the flags of the run");
+    MICLOC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int32_t> hf((size_t)B);
+    MICLOC_CUDA(cudaMemcpyAsync(hf.data(), flags_dev, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MICLOC_CUDA(cudaStreamSynchronize(st));
+    const ChainParams &p = c->p;
+    const size_t esz = dtype == MICLOC_I16 ? 2 : 4;
+    const bool timing = c->timing;
+    c->timing = false;                                   // the rerun is not a timed run of its own
+    long long n = 0;
+    int rc = MICLOC_OK;
+    for (long long i = 0; i < B && rc == MICLOC_OK; ++i) {
+        if (!(hf[(size_t)i] & 1)) continue;
+        rc = micloc_snn_run_taps(c, (const char *)audio + (size_t)i * T * p.M * esz, dtype, 1, T, nullptr, nullptr,
+                                 spikes_dev ? spikes_dev + (size_t)i * T * p.C2 : nullptr, nullptr, nullptr,
+                                 power_dev ? power_dev + (size_t)i * p.G : nullptr, doa_dev ? doa_dev + i : nullptr,
+                                 flags_dev + i, stream);
+        ++n;
+    }
+    c->timing = timing;
+    if (n_refined) *n_refined = n;
+    return rc;
+}
+
+extern "C" int64_t micloc_snn_refined_count(micloc_snn *c) { return c ? c->refined : 0; }
+
+// ---------------------------------------------------------------------------
 // end-to-end with host buffers: two chunks in flight on two private streams
 // ---------------------------------------------------------------------------
 extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dtype, int64_t B, int64_t T,
@@ -520,6 +601,12 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
     }
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
+    if ((size_t)B > c->h_flags_cap) {
+        if (c->h_flags_all) cudaFreeHost(c->h_flags_all);
+        c->h_flags_all = nullptr; c->h_flags_cap = 0;
+        MICLOC_CUDA(cudaHostAlloc((void **)&c->h_flags_all, (size_t)B * sizeof(int32_t), cudaHostAllocDefault));
+        c->h_flags_cap = (size_t)B;
+    }
     for (int i = 0; i < 2; ++i) {
         if (!c->hs[i]) MICLOC_CUDA(cudaStreamCreateWithFlags(&c->hs[i], cudaStreamNonBlocking));
         MICLOC_TRY(c->h_audio[i].reserve((size_t)chunk * clip_in));
@@ -555,9 +642,30 @@ extern "C" int micloc_snn_run_host(micloc_snn *c, const void *audio_host, int dt
         if (flags_host)
             MICLOC_CUDA(cudaMemcpyAsync(flags_host + b0, c->h_flg[slot].ptr, (size_t)nb * sizeof(int32_t),
                                         cudaMemcpyDeviceToHost, st));
+        MICLOC_CUDA(cudaMemcpyAsync(c->h_flags_all + b0, c->h_flg[slot].ptr, (size_t)nb * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));       // the library's own copy (pinned): overflow check below
     }
     MICLOC_CUDA(cudaStreamSynchronize(c->hs[0]));
     MICLOC_CUDA(cudaStreamSynchronize(c->hs[1]));
+    // clips whose RZCC clusters overflowed the streaming encoder are redone one by one through the staged kernels (rare)
+    if (fused) {
+        cudaStream_t st = c->hs[0];
+        const int32_t *fl = (const int32_t *)c->h_flags_all;
+        for (long long i = 0; i < B; ++i) {
+            if (!(fl[i] & 1)) continue;
+            MICLOC_CUDA(cudaMemcpyAsync(c->h_audio[0].ptr, (const char *)audio_host + (size_t)i * clip_in, clip_in,
+                                        cudaMemcpyHostToDevice, st));
+            int8_t *d_spk = spikes_host ? (int8_t *)c->h_spk[0].ptr : nullptr;
+            float *d_pow = power_host ? (float *)c->h_pow[0].ptr : nullptr;
+            MICLOC_TRY(micloc_snn_run_taps(c, c->h_audio[0].ptr, dtype, 1, T, nullptr, nullptr, d_spk, nullptr, nullptr, d_pow,
+                                           (int32_t *)c->h_doa[0].ptr, (int32_t *)c->h_flg[0].ptr, st));
+            if (spikes_host) MICLOC_CUDA(cudaMemcpyAsync(spikes_host + (size_t)i * clip_spk, d_spk, clip_spk, cudaMemcpyDeviceToHost, st));
+            if (power_host) MICLOC_CUDA(cudaMemcpyAsync(power_host + (size_t)i * p.G, d_pow, (size_t)p.G * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (doa_host) MICLOC_CUDA(cudaMemcpyAsync(doa_host + i, c->h_doa[0].ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            if (flags_host) MICLOC_CUDA(cudaMemcpyAsync(flags_host + i, c->h_flg[0].ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            MICLOC_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     return MICLOC_OK;
 }
 

@@ -120,6 +120,12 @@ k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
     }
 }
 
+static __global__ void __launch_bounds__(256)
+k_f32_to_f64(const float *__restrict__ x, double *__restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (double)x[i];
+}
+
 // ---------------------------------------------------------------------------
 // S2' / S3': the same two stages cut into TIME SEGMENTS, for few long clips (BASELINE config 5: one 10 s clip of 64
 // microphones is 128 sequential chains of 480 000 steps -- 128 threads).  Band-pass and alpha kernel forget their

@@ -122,8 +122,12 @@ class SnnEngine:
         return audio.contiguous(), dt
 
     def run(self, audio: torch.Tensor, want_spikes: bool = False, want_power: bool = True,
-            fused: bool = True) -> Dict[str, torch.Tensor]:
-        """audio [B,T,M] on this engine's GPU -> {'doa','power','spikes','flags'} (device tensors)."""
+            fused: bool = True, refine: bool = True) -> Dict[str, torch.Tensor]:
+        """audio [B,T,M] on this engine's GPU -> {'doa','power','spikes','flags'} (device tensors).
+
+        The fused kernel reports clips whose RZCC clusters overflowed its bounded streaming encoder in `flags` bit 0;
+        with `refine` (default) they are redone by the library with the unbounded encoder before this returns, which
+        synchronises the stream.  Pipelined callers pass refine=False and call `refine(audio, out)` once per step."""
         audio, dt = self._check_audio(audio)
         B, T, _ = audio.shape
         dev = self.device
@@ -141,7 +145,23 @@ class SnnEngine:
             rc = self._lib.micloc_snn_run(self._h, _ptr(audio), dt, B, T, _ptr(spikes), _ptr(power), _ptr(doa),
                                           _ptr(flags), 0, _stream_ptr(dev))
         N.check(rc)
-        return {"doa": doa, "power": power, "spikes": spikes, "flags": flags}
+        out = {"doa": doa, "power": power, "spikes": spikes, "flags": flags}
+        if refine and fused:
+            self.refine(audio, out)
+        return out
+
+    def refine(self, audio: torch.Tensor, out: Dict[str, torch.Tensor]) -> int:
+        """micloc_snn_refine on the outputs of a fused `run`: number of clips redone (0 almost always)."""
+        audio, dt = self._check_audio(audio)
+        B, T, _ = audio.shape
+        n = C.c_int64()
+        N.check(self._lib.micloc_snn_refine(self._h, _ptr(audio), dt, B, T, _ptr(out.get("spikes")), _ptr(out.get("power")),
+                                            _ptr(out.get("doa")), _ptr(out["flags"]), C.byref(n), _stream_ptr(self.device)))
+        return n.value
+
+    @property
+    def refined_count(self) -> int:
+        return int(self._lib.micloc_snn_refined_count(self._h))
 
     def run_taps(self, audio: torch.Tensor, want: Sequence[str] = ("q", "z", "spikes", "vmem", "y", "power", "doa")):
         """Staged path with per-stage taps (device tensors)."""

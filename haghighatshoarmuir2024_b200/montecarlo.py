@@ -136,9 +136,11 @@ class SnrSweep:
 
     # ------------------------------------------------------------------
     def run_band(self, band_idx: int, audio: torch.Tensor, want_spikes: bool = False, want_power: bool = True,
-                 hist: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                 hist: Optional[torch.Tensor] = None, refine: bool = True) -> Dict[str, torch.Tensor]:
+        """One band's batch through the fused kernel.  refine=False keeps the call stream-ordered (no read-back of the
+        RZCC overflow flags); the caller then runs `self.engines[band_idx].refine(audio, out)` once per step."""
         eng = self.engines[band_idx]
-        out = eng.run(audio, want_spikes=want_spikes, want_power=want_power, fused=True)
+        out = eng.run(audio, want_spikes=want_spikes, want_power=want_power, fused=True, refine=refine)
         if hist is not None:
             self.histogram(out["doa"], hist)
         return out

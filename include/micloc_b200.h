@@ -41,7 +41,7 @@ typedef enum {
     MICLOC_ERR_CONFIG = -2,      /* reference raises ValueError/AssertionError at construction */
     MICLOC_ERR_CUDA = -3,
     MICLOC_ERR_UNSUPPORTED = -4,
-    MICLOC_ERR_OVERFLOW = -5     /* RZCC cluster buffer overflow in the fused path: rerun staged */
+    MICLOC_ERR_OVERFLOW = -5     /* reserved (RZCC overflow is reported per clip in `flags` and healed by the library) */
 } micloc_status;
 
 typedef enum { MICLOC_F32 = 0, MICLOC_I16 = 1, MICLOC_I32 = 2 /* streams only: wav frames of micloc/record.py */ } micloc_dtype;
@@ -78,11 +78,24 @@ int micloc_snn_set_bf(micloc_snn *ctx, const double *bf_mat, int32_t num_doa);
  *   spikes_dev [B][T][2M] int8 in {-1,0,+1}       (nullable)
  *   power_dev  [B][G] float32 = mean_t y[t,g]^2   (nullable)
  *   doa_dev    [B] int32 = argmax_g power (first maximum) (nullable)
- *   flags_dev  [B] int32, bit0 = RZCC cluster overflow (nullable)
- * `fused` != 0 runs the single fused kernel, 0 the staged kernels (same results). */
+ *   flags_dev  [B] int32, bit0 = RZCC overflow of the fused kernel's bounded streaming encoder (a cluster of more
+ *              than 8 candidates or a flat top of more than 16 exact zeros, e.g. digital silence): the clip's results
+ *              are then not the reference's until micloc_snn_refine has redone it (nullable)
+ * `fused` != 0 runs the single fused kernel, 0 the staged kernels (same results; they heal overflowed clips
+ * themselves with the unbounded float64 encoder, at the price of one stream synchronisation). */
 int micloc_snn_run(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
                    int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
                    int fused, void *stream);
+
+/* Synchronising companion of the fused micloc_snn_run (which stays stream-ordered): reads flags_dev back, reruns every
+ * clip with bit0 set through the staged kernels + the unbounded float64 RZCC encoder (spike_encoder.py:115-137 has no
+ * cluster bound), overwrites that clip's rows of the (nullable) outputs and clears the bit.  Same arguments as the run
+ * it follows; n_refined (nullable) = clips redone.  micloc_snn_run_host does this on its own. */
+int micloc_snn_refine(micloc_snn *ctx, const void *audio_dev, int dtype, int64_t B, int64_t T,
+                      int8_t *spikes_dev, float *power_dev, int32_t *doa_dev, int32_t *flags_dev,
+                      int64_t *n_refined, void *stream);
+/* clips this context has redone with the unbounded encoder since it was created (all entry points) */
+int64_t micloc_snn_refined_count(micloc_snn *ctx);
 
 /* Same with per-stage debug taps (all nullable, all device):
  *   q_dev [B][T][M] f32 (STHT quadrature), z_dev [B][T][2M] f32 (post band-pass,
@@ -94,7 +107,7 @@ int micloc_snn_run_taps(micloc_snn *ctx, const void *audio_dev, int dtype, int64
                         void *stream);
 
 /* End-to-end with HOST buffers: chunks the batch, copies H2D from pinned staging,
- * runs the hot path, copies results D2H.  Outputs nullable as above. */
+ * runs the hot path, copies results D2H, redoes RZCC-overflowed clips (micloc_snn_refine).  Outputs nullable as above. */
 int micloc_snn_run_host(micloc_snn *ctx, const void *audio_host, int dtype, int64_t B, int64_t T,
                         int8_t *spikes_host, float *power_host, int32_t *doa_host,
                         int32_t *flags_host, int fused);

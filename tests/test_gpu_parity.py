@@ -467,3 +467,42 @@ def test_snn_beamformer_unipolar_design_matches_reference():
     bf = beamf.design_from_template((t, g["template"]), g["doa_list"])
     d = np.abs(np.sum(bf * g["bf_mat"], axis=0))
     assert d.min() > 0.995
+
+
+@pytest.mark.parametrize("variant", ["tc", "ffma"])
+def test_rzcc_overflow_is_healed_by_the_library(variant, monkeypatch):
+    """Digital silence: the float32 band-pass output underflows to exact zeros, the running sum gets a flat top longer
+    than the fused kernel's streaming encoder follows (flags bit 0).  micloc_snn_refine / run_host / the staged entry
+    points redo such clips with the unbounded float64 encoder: spikes = find_peaks semantics (oracle RZCC) on the
+    clip's band-pass output, and the flag is cleared."""
+    g = H.load("snn_c1_bipolar")
+    T, B = 24_000, 5
+    x, _ = H.synth_clips(g, B, T, seed=21, snrs_db=(10.0,))
+    x[1, 3000:] = 0
+    x[3, 2000:] = 0
+    eng = engine_for(g, T)
+    xd = to_dev(x)
+    taps = eng.run_taps(xd, want=("z", "spikes", "power", "doa"))
+    torch.cuda.synchronize()
+    assert int(taps["flags"].sum()) == 0 and eng.refined_count >= 2          # healed inside the staged call
+    z = taps["z"].cpu().numpy().astype(np.float64)
+    for b in range(B):
+        want = O.rzcc(z[b], float(eng.spec.robust_width), True)
+        assert np.array_equal(taps["spikes"][b].cpu().numpy(), want), b
+    use_variant(monkeypatch, variant)
+    raw = eng.run(xd, want_spikes=True, fused=True, refine=False)
+    torch.cuda.synchronize()
+    flagged = (raw["flags"].cpu().numpy() & 1).astype(bool)
+    assert flagged[1] and flagged[3] and not flagged[0]
+    n = eng.refine(xd, raw)
+    torch.cuda.synchronize()
+    assert n == int(flagged.sum()) and int(raw["flags"].sum()) == 0
+    for b in np.nonzero(flagged)[0]:
+        assert torch.equal(raw["spikes"][b], taps["spikes"][b])
+        assert H.rel_err(raw["power"][b].cpu().numpy(), taps["power"][b].cpu().numpy()) < 1e-5
+        assert int(raw["doa"][b]) == int(taps["doa"][b])
+    auto = eng.run(xd, want_spikes=True, fused=True)                         # refine=True is the default
+    assert int(auto["flags"].sum()) == 0 and torch.equal(auto["spikes"], raw["spikes"])
+    host = eng.run_host(torch.from_numpy(x).pin_memory(), want_spikes=True, fused=True)
+    assert int(host["flags"].sum()) == 0
+    assert torch.equal(host["spikes"], raw["spikes"].cpu()) and torch.equal(host["doa"], raw["doa"].cpu())
