@@ -335,10 +335,16 @@ def run_gpu(args):
     Be = min(Bb, args.e2e_clips_per_band)                          # bounded: the host copy of the full step would be tens of GB
     d2h = nb * Be * (4 + 4)                                       # doa + flags per clip
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=nb)
+
     def e2e_leg(host):
         h2d = sum(h.numel() for h in host) * host[0].element_size()
         def e2e_step():
-            return [sweep.engines[i].run_host(host[i], want_spikes=False, want_power=False, fused=True) for i in range(nb)]
+            # one host thread per band (ctypes drops the GIL inside the call): the bands are independent contexts with
+            # their own staging streams, so the drain of one band's last chunk overlaps the next band's copies
+            futs = [pool.submit(sweep.engines[i].run_host, host[i], False, False, True) for i in range(nb)]
+            return [f.result() for f in futs]
         for _ in range(max(1, min(args.warmup, 2))):
             res = e2e_step()
         barrier()
@@ -462,7 +468,7 @@ def run_gpu(args):
         "mic_msamples_per_sec": value * T_CLIP * NUM_MIC / 1e6,
         "outputs_in_timed_region": "int8 spikes [B,T,14] + int32 DoA [B] + DoA histogram written to HBM",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "micloc_snn_run_host (pinned host audio in, DoA indices + flags out)",
+                "api": "micloc_snn_run_host (pinned host audio in, DoA indices + flags out), one host thread per band",
                 "wire_format": "int16 PCM [B][T][M] (the reference's recorder format, micloc/record.py:54-75); "
                                "the float32 leg is under `f32`",
                 "clips_per_band_per_step": Be, "pcie_h2d_gbs": e2e_gbs,
@@ -492,6 +498,7 @@ def run_gpu(args):
 # --------------------------------------------------------------------------------------
 def _timed(torch, fn, n=3):
     out = fn()
+    out = fn()                     # twice: the caching allocator needs two generations of the output buffers
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -528,13 +535,19 @@ def run_extras(args, local, fp32_peak, lib):
         B = x.shape[0]
         F = flops_per_mic_sample(len(g["kernel"]), M, g["bf_mat"].shape[1], 0.0, gram=True)
         ach = B * x.shape[1] * M * F / (ms * 1e-3) / 1e12
-        cfg = H.oracle_cfg(g)
-        cfg.nir = O.neuron_kernel(np.arange(x.shape[1]) / FS, float(g["tau"]), float(g["tau"]))
-        xc = x[:n_cmp].cpu().numpy()
-        t0 = time.perf_counter()
-        ref = O.snn_run_batch(cfg, xc, nthreads=min(cores, n_cmp), want_spikes=True)
-        cpu_s = time.perf_counter() - t0
-        doa = out["doa"][:n_cmp].cpu().numpy()
+        parity = cpu_port = None
+        if n_cmp:
+            cfg = H.oracle_cfg(g)
+            cfg.nir = O.neuron_kernel(np.arange(x.shape[1]) / FS, float(g["tau"]), float(g["tau"]))
+            xc = x[:n_cmp].cpu().numpy()
+            t0 = time.perf_counter()
+            ref = O.snn_run_batch(cfg, xc, nthreads=min(cores, n_cmp), want_spikes=True)
+            cpu_s = time.perf_counter() - t0
+            doa = out["doa"][:n_cmp].cpu().numpy()
+            parity = {"clips_compared": n_cmp, "doa_match_rate_vs_cpu_path": float((doa == ref["doa"]).mean()),
+                      "spike_agreement": H.spike_agreement(out["spikes"][:n_cmp].cpu().numpy(), ref["spikes"]),
+                      "power_rel_err": H.rel_err(out["power"][:n_cmp].cpu().numpy(), ref["power"])}
+            cpu_port = {"clips_per_sec": n_cmp / cpu_s, "cores": min(cores, n_cmp)}
         res[name] = {
             "workload": what, "clips": B, "clip_samples": int(x.shape[1]), "num_mic": M, "num_doa": int(g["bf_mat"].shape[1]),
             "path": "fused k_fused_tc (1 launch)" if fused and not eng._fused_unsupported else
@@ -542,10 +555,7 @@ def run_extras(args, local, fp32_peak, lib):
             "ms": ms, "clips_per_sec": B / ms * 1e3, "mic_msamples_per_sec": B * x.shape[1] * M / ms / 1e3,
             "roofline": {"bound": "fp32", "flop_per_mic_sample": F, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak},
-            "parity": {"clips_compared": n_cmp, "doa_match_rate_vs_cpu_path": float((doa == ref["doa"]).mean()),
-                       "spike_agreement": H.spike_agreement(out["spikes"][:n_cmp].cpu().numpy(), ref["spikes"]),
-                       "power_rel_err": H.rel_err(out["power"][:n_cmp].cpu().numpy(), ref["power"])},
-            "cpu_port": {"clips_per_sec": n_cmp / cpu_s, "cores": min(cores, n_cmp)},
+            "parity": parity, "cpu_port": cpu_port,
             "rzcc_overflow_clips": int(out["flags"].sum()),
         }
         eng.close()

@@ -276,13 +276,24 @@ __device__ __forceinline__ void rzcc_sample(RzccState &s, const RzccStoreT<HT, C
     if (nz) { s.r = t; s.sgn = positive ? 1 : 0; }
 }
 
+// The reference's np.cumsum runs in float64 and stops moving once |z| < ulp(sum) / 2: find_peaks then sees a flat top
+// although z still alternates.  That happens in digital silence, where the band-pass output is the filter's decaying
+// tail (below 2^-53 of the sum after ~40 ms; in float32 it then never reaches 0 but settles into a denormal limit
+// cycle whose sign changes would spike forever).  The float32 chains therefore treat such a sample as an exact zero:
+// half an ulp of the float64 sum = 2^(exponent(sum) - 53).
+__device__ __forceinline__ bool rzcc_flat(float z, float cprev) {
+    const float hu = __uint_as_float(__float_as_uint(cprev) & 0x7f800000u) * 1.1102230246251565e-16f;
+    return z == 0.f || fabsf(z) < hu;
+}
+constexpr float kFlatTrigger = 4.5e-16f;      // a segment whose smallest |z| is below this x |sum| takes the per-sample path
+
 // one sample at a time
 template <typename Emit>
 __device__ __forceinline__ void rzcc_detect(RzccState &s, const RzccStore &st, int bipolar, int w, int t, float z,
                                             Emit &&emit) {
     const float cprev = s.csum;
     s.csum = cprev + z;
-    rzcc_sample(s, st, bipolar, w, t, z != 0.f, z > 0.f, cprev, emit);
+    rzcc_sample(s, st, bipolar, w, t, !rzcc_flat(z, cprev), z > 0.f, cprev, emit);
 }
 
 // kSeg samples ts .. ts+nvalid-1 at once.  Bit (31-i) of `neg` / `zero` says that sample ts+i is

@@ -295,10 +295,10 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                     for (int i = 0; i < nvalid; ++i) {
                         if (i == wrap_at) xq -= g.ring_x;
                         const float z = biquad2_step(sos, bq, xq[i * stride]);
+                        zero |= (rzcc_flat(z, csum) ? 1u : 0u) << (31 - i);      // (sum before this sample)
                         csum += z;
                         cs[i * 32] = csum;
                         neg |= (__float_as_uint(z) >> 31) << (31 - i);
-                        zero |= (z == 0.f ? 1u : 0u) << (31 - i);
                     }
                 };
                 if (fast) {
@@ -325,7 +325,9 @@ __device__ __forceinline__ void bandpass_role(const FusedSmem &sm, const ChainPa
                             zmin = fminf(zmin, fabsf(z));
                         }
                     }
-                    if (zmin == 0.f) {                  // redo this lane's segment for its zero mask (same arithmetic)
+                    // a sample that does not move the reference's float64 running sum (exact zeros, the decaying tail in
+                    // digital silence) counts as zero: redo this lane's segment for its zero mask (same arithmetic)
+                    if (zmin <= kFlatTrigger * fmaxf(fabsf(carry), fabsf(csum))) {
                         bq = bq0; csum = carry; neg = 0u;
                         slow_segment(kSeg);
                     }

@@ -539,15 +539,15 @@ __device__ __forceinline__ void bandpass_role(const TcSmem &sm, const ChainParam
                 const float *xo = xe + kTile / 2;
                 const float carry = csum;
                 unsigned int neg = 0u, zero = 0u;
-                // sample by sample with explicit sign / zero masks (ragged segments, exact zeros)
+                // sample by sample with explicit sign / zero masks (ragged segments, zeros)
                 auto slow_segment = [&](int nvalid) {
 #pragma unroll 1
                     for (int i = 0; i < nvalid; ++i) {
                         const float z = biquad2_step(sos, bq, (i & 1) ? xo[i >> 1] : xe[i >> 1]);
+                        zero |= (rzcc_flat(z, csum) ? 1u : 0u) << (31 - i);      // (sum before this sample)
                         csum += z;
                         cs[i * 32] = csum;
                         neg |= (__float_as_uint(z) >> 31) << (31 - i);
-                        zero |= (z == 0.f ? 1u : 0u) << (31 - i);
                     }
                 };
                 if (ts + kSeg <= T) {
@@ -570,7 +570,9 @@ __device__ __forceinline__ void bandpass_role(const TcSmem &sm, const ChainParam
                             zmin = fminf(zmin, fabsf(z));
                         }
                     }
-                    if (zmin == 0.f) {                  // redo this lane's segment for its zero mask (same arithmetic)
+                    // a sample that does not move the reference's float64 running sum (exact zeros, the decaying tail in
+                    // digital silence) counts as zero: redo this lane's segment for its zero mask (same arithmetic)
+                    if (zmin <= kFlatTrigger * fmaxf(fabsf(carry), fabsf(csum))) {
                         bq = bq0; csum = carry; neg = 0u;
                         slow_segment(kSeg);
                     }

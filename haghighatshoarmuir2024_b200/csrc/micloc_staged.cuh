@@ -120,10 +120,12 @@ k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
     }
 }
 
+// band-pass output of one clip -> input of the unbounded float64 encoder (heal_overflow).  Denormals become zeros:
+// in digital silence the float32 filter never decays to 0 but cycles through denormals, whose sign changes are noise.
 static __global__ void __launch_bounds__(256)
 k_f32_to_f64(const float *__restrict__ x, double *__restrict__ y, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = (double)x[i];
+    if (i < n) y[i] = fabsf(x[i]) < 1.17549435e-38f ? 0.0 : (double)x[i];
 }
 
 // ---------------------------------------------------------------------------
