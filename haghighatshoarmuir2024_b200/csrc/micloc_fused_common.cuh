@@ -218,7 +218,19 @@ __device__ __forceinline__ void neuron_role(const SMEM &sm, const ChainParams &p
                         const float tail = fmaf(nLf, nr.q1, nr.q2);
                         const float v = fmaf(-ncT, tail, nc * nr.p2);
                         vq[i] = v;
-                        sseg[(8 * o + i) * C2] = (int8_t)(((P >> i) & 1u) - ((Nn >> i) & 1u));
+                    }
+                    // the 8 samples' spike bytes (+1 / -1 / 0): bit k of a nibble -> byte k by one multiply (0x00204081
+                    // copies the nibble to bit offsets 0, 7, 14, 21), -1 = 0xff = byte x 255; one byte store per sample
+                    {
+                        const unsigned int p0 = ((P & 0xfu) * 0x00204081u) & 0x01010101u, p1 = (((P >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+                        const unsigned int n0 = ((Nn & 0xfu) * 0x00204081u) & 0x01010101u, n1 = (((Nn >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+                        const unsigned int b0 = p0 | (n0 * 255u), b1 = p1 | (n1 * 255u);
+                        int8_t *s8 = sseg + 8 * o * C2;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            s8[i * C2] = (int8_t)(b0 >> (8 * i));
+                            s8[(4 + i) * C2] = (int8_t)(b1 >> (8 * i));
+                        }
                     }
                     // v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 22 significant bits for the tensor-core Gram
                     uint4 h4, l4;

@@ -133,6 +133,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one lane of a converged warp, chosen by the hardware: ptxas then knows that the guarded code runs on a single thread
+// and feeds tcgen05.mma's uniform-register operands with plain R2UR moves instead of an ELECT / BRA.U.ANY loop per MMA
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -258,7 +265,7 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
         const int f0 = kMac * J;
         const IN_T *s = src[slot] + (long long)f0 * M;
         if (al[slot] && f0 + kMac <= T) {
-            if (lane == 0) {
+            if (elect_one()) {
                 fence_proxy_async();
                 mbar_expect_tx(bar_tma, tile_bytes);
                 tma_bulk_g2s(stin_a, s, tile_bytes, bar_tma);
@@ -319,12 +326,13 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 const int par = sidx >= M ? 1 : 0, mic = sidx - par * M;
                 const IN_T *sp = stin + (16 * j - par) * M + mic;
                 float u[8];
-                const int fmax = T - f0;                  // frames of the tile inside the clip (>= kMac for whole tiles)
+                // frames f = 16 j - par + 2 i of the tile; those behind the clip end (f >= T - f0, last tile only) are
+                // zeros: the first nv of the 8 are inside.  f = -1 (j = 0, odd stream) is the carry below.
+                const int left = T - f0 - (16 * j - par);
+                const int nv = left >= 16 ? 8 : (left > 0 ? (left + 1) >> 1 : 0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int f = 16 * j - par + 2 * i;
-                    u[i] = (f >= 0 && f < fmax) ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
-                }
+                for (int i = 1; i < 8; ++i) u[i] = i < nv ? to_f32<IN_T>(sp[2 * i * M]) * s_x : 0.f;
+                u[0] = (nv > 0 && 16 * j - par >= 0) ? to_f32<IN_T>(sp[0]) * s_x : 0.f;
                 if (j == 0 && par == 1) u[0] = J > 0 ? sm.carry[(slot * 2 + ((J + 1) & 1)) * 8 + mic] : 0.f;   // x[128 J - 1]
                 uint4 h4, l4;
                 unsigned int *hp = &h4.x, *lp = &l4.x;
@@ -433,7 +441,7 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
                 const int ks0 = part == 0 ? 0 : (part == 1 ? e0 : (part == 2 ? e1 : e2));
                 const int ks1 = part == 0 ? e0 : (part == 1 ? e1 : (part == 2 ? e2 : g.ksteps));
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t d = tmem_d + (uint32_t)((Jb & 1) * kMmaN);
                     int c = cwin + 2 * ks0;          // chunk of K step ks0
                     if (c >= g.RC) c -= g.RC;
