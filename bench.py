@@ -609,7 +609,7 @@ def run_extras(args, local, fp32_peak, lib):
     net = H.xylo_network(g)
     eng = H.xylo_engine(g, net, device=local)
     xs = torch.from_numpy(H.xylo_synth_clips(g, 16, T, seed=1)).to(f"cuda:{local}")
-    Bx = args.extra_clips
+    Bx = args.extra_xylo_clips
     x = xs.repeat((Bx + 15) // 16, 1, 1)[:Bx].contiguous()
     x[16:] += 1e-3 * torch.randn_like(x[16:])                      # distinct clips; the first 16 stay the oracle's
     ms_exact, out = _timed(torch, lambda: eng.run(x, exact=True, want_spikes_in=True), n=2)
@@ -698,6 +698,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs 1/3/4/5 section of the line")
     ap.add_argument("--extra-clips", type=int, default=1776, help="clips per extra config (1 s, 7 microphones)")
+    ap.add_argument("--extra-xylo-clips", type=int, default=3552,
+                    help="clips of the config-3 extra (3552 = 148 SMs x 24: one full wave of the exact front end's one-warp-per-clip kernel)")
     ap.add_argument("--extra-c5-clips", type=int, default=4, help="10 s 64-microphone clips of the config-5 extra")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -927,7 +927,16 @@ extern "C" int micloc_xylo_run(micloc_xylo *c, const void *audio, int dtype, int
     // the batch goes through in chunks that bound the scratch (float64 intermediates of the exact front end)
     const bool staged_f64 = exact && !chain_f64_supported(c);       // float64 q AND z in HBM (else q only)
     const size_t per_clip = (size_t)T * (staged_f64 ? (size_t)p.M * 8 + (size_t)CT * 8 * 2 + (size_t)CT * 3 : (size_t)p.M * (exact ? 8 : 4) + CT);
-    long long chunk = (long long)(((size_t)6 << 30) / per_clip);
+    // a quarter of the free HBM, at most 24 GB (B200: 180 GB), at least 2 GB: the one-warp-per-clip chain kernel of the
+    // exact front end wants >= 24 clips per SM in flight
+    size_t mem_free = 0, mem_total = 0;
+    size_t budget = (size_t)6 << 30;
+    if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess) {
+        budget = mem_free / 4;
+        if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
+        if (budget < ((size_t)2 << 30)) budget = (size_t)2 << 30;
+    }
+    long long chunk = (long long)(budget / per_clip);
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
     MICLOC_TRY(c->signed_spk.reserve((size_t)chunk * T * CT));

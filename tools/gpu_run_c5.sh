@@ -1,4 +1,10 @@
-#!/bin/bash
-TAG=${1:-c5}
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s -k "time_segmented" --durations=5 > gpurun_out/tests_c5_$TAG.log 2>&1; tail -25 gpurun_out/tests_c5_$TAG.log
+python tools/c5_probe.py 1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c5.csv python tools/c5_probe.py 1 > /dev/null 2>&1
+python - <<PY
+import csv
+rows=list(csv.reader(open('gpurun_out/launches_c5.csv')))
+hi=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]; hdr=rows[hi]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+seq=[(r[ki][:70], float(r[vi].replace(',',''))/1e6) for r in rows[hi+1:] if len(r)>vi]
+n=len(seq)//3
+for k,t in seq[-n:]: print(f"{t:9.3f} ms  {k}")
+PY
