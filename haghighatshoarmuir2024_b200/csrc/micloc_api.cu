@@ -55,7 +55,7 @@ struct micloc_snn {
                                          // micloc_snn_run on the caller's stream, sets 1 and 2 for run_host's two streams
     cudaEvent_t ev_last = nullptr;       // recorded behind the last launch of micloc_snn_run / run_taps / gram: run_host's
                                          // private streams wait for it before they touch the shared scratch
-    DevBuf q, spikes, vmem, gram, flags, part;
+    DevBuf q, spikes, vmem, gram, flags, part, chunkbuf;
     DevBuf rz, rzd, rspk, rflag;            // one clip's worth of scratch of the overflow path (heal_overflow)
     long long refined = 0;                  // clips redone with the unbounded encoder so far
     int32_t *h_flags_all = nullptr;         // pinned host copy of a run_host batch's flags
@@ -83,9 +83,11 @@ static bool plan_segments(const micloc_snn *c, long long B, long long T, int nb,
     // band-pass transient below 1e-9 of full scale, the decision latency of the RZCC encoder on top
     int warm = (int)std::ceil(std::log(1e-9) / std::log(c->pole_radius)) + 2 * rzcc_lag(p.w);
     warm = (warm + 31) & ~31;
-    long long seg = 4ll * warm;                                  // 25 % redundant work at most
-    const long long want = (65536 + chains - 1) / chains;        // segments per chain that fill the GPU
-    if (T / seg > want) seg = (T + want - 1) / want;
+    // The chains are latency-bound (one dependent recurrence per thread): what counts is threads in flight, not work.
+    // Aim at 16 warps per SM; a segment is never shorter than its own warm-up (2.1 x the sequential work at worst).
+    const long long want = (512ll * c->sm_count + chains - 1) / chains;      // segments per chain that fill the GPU
+    long long seg = (T + want - 1) / want;
+    if (seg < warm) seg = warm;
     seg = (seg + 31) & ~31ll;
     if (seg * 2 > T) return false;
     sp.seg_len = (int)seg; sp.warm = warm; sp.tail = rzcc_lag(p.w) + kSeg;
@@ -212,7 +214,7 @@ extern "C" int micloc_snn_destroy(micloc_snn *c) {
     if (!c) return MICLOC_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_taps); cudaFree(c->d_sos); cudaFree(c->d_W); cudaFree(c->d_Wd); cudaFree(c->d_sm_slots);
-    c->q.release(); c->spikes.release(); c->vmem.release(); c->gram.release(); c->flags.release(); c->part.release();
+    c->q.release(); c->spikes.release(); c->vmem.release(); c->gram.release(); c->flags.release(); c->part.release(); c->chunkbuf.release();
     c->rz.release(); c->rzd.release(); c->rspk.release(); c->rflag.release();
     if (c->h_flags_all) cudaFreeHost(c->h_flags_all);
     for (int i = 0; i < 2; ++i) {
@@ -353,7 +355,19 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     const ChainParams &p = c->p;
     MICLOC_TRY(c->gram.reserve((size_t)B * p.C2 * p.C2 * sizeof(double)));
     dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
-    if ((long long)gg.x * gg.y < 2ll * c->sm_count && T >= 65536 && !getenv("MICLOC_NO_SEGMENTS")) {
+    const bool few_long = (long long)gg.x * gg.y < 2ll * c->sm_count && T >= 65536 && !getenv("MICLOC_NO_SEGMENTS");
+    if (few_long && p.C2 >= 32) {
+        // few long clips of a wide array (BASELINE config 5): the Gram matrix as a tiled float32 product over time slabs
+        const int nblk = (p.C2 + kGtTile - 1) / kGtTile, nblocks = nblk * (nblk + 1) / 2;
+        const long long slab_len = kGtFlush;                                 // float32 sums of 1024 samples, float64 across slabs
+        const long long nslab = (T + slab_len - 1) / slab_len;
+        if (nslab > 65535) return set_error(MICLOC_ERR_UNSUPPORTED, "clip too long for the tiled Gram kernel");
+        MICLOC_TRY(c->part.reserve((size_t)nslab * B * p.C2 * p.C2 * sizeof(double)));
+        k_gram_tiled<<<dim3((unsigned)B, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(vmem, (double *)c->part.ptr, p.C2, B, T, 0, slab_len);
+        const long long ne = B * p.C2 * p.C2;
+        k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, (int)nslab);
+        count_launch(1);
+    } else if (few_long) {
         // few long clips: time slabs so that the sum fills the GPU
         int nslab = (int)((4ll * c->sm_count + (long long)gg.x * gg.y - 1) / ((long long)gg.x * gg.y));
         if (nslab > 64) nslab = 64;
@@ -369,9 +383,27 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     }
     const size_t smem = (size_t)p.C2 * p.C2 * sizeof(double);
     MICLOC_CUDA(cudaFuncSetAttribute(k_power_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_power_argmax<<<(unsigned)B, 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
-                                                   1.0 / (double)T);
+    // few clips: slices of the DoA grid on separate CTAs (one CTA per clip would run G x C2^2 float64 FMAs on one SM)
+    int nchunk = 1;
+    if (B < c->sm_count && (long long)p.G * p.C2 * p.C2 >= (1ll << 20)) {
+        nchunk = (int)((c->sm_count + B - 1) / B);
+        const int max_chunk = (p.G + 31) / 32;
+        if (nchunk > max_chunk) nchunk = max_chunk;
+        if (nchunk < 1) nchunk = 1;
+    }
+    double *cv = nullptr; int *ci = nullptr;
+    if (nchunk > 1) {
+        MICLOC_TRY(c->chunkbuf.reserve((size_t)B * nchunk * (sizeof(double) + sizeof(int))));
+        cv = (double *)c->chunkbuf.ptr;
+        ci = (int *)(cv + (size_t)B * nchunk);
+    }
+    k_power_argmax<<<dim3((unsigned)B, (unsigned)nchunk), 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
+                                                                          1.0 / (double)T, nchunk, cv, ci);
     count_launch(2);
+    if (nchunk > 1 && doa) {
+        k_argmax_chunks<<<(unsigned)((B + 31) / 32), 32, 0, st>>>(cv, ci, doa, B, nchunk);
+        count_launch(1);
+    }
     MICLOC_CUDA(cudaGetLastError());
     return MICLOC_OK;
 }

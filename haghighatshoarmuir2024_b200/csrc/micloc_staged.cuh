@@ -187,14 +187,16 @@ k_chain_seg(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
     };
     bool unsynced = false;
     int zrun = 0;
-    float xc[4], xn[4];
+    // (few chains per SM -- a handful of warps: nothing but this thread's own loads in flight hides the HBM latency)
+    constexpr int kPf = 4;
+    float xc[kPf], xn[kPf];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xc[u] = fetch(t_begin + u);
-    for (long long t4 = t_begin; t4 < t_stop; t4 += 4) {
+    for (int u = 0; u < kPf; ++u) xc[u] = fetch(t_begin + u);
+    for (long long t4 = t_begin; t4 < t_stop; t4 += kPf) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xn[u] = fetch(t4 + 4 + u);       // next inputs on their way while these 4 steps run
+        for (int u = 0; u < kPf; ++u) xn[u] = fetch(t4 + kPf + u);   // next inputs on their way while these steps run
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kPf; ++u) {
             const long long t = t4 + u;
             if (t < t_stop) {
                 if (t == start && seg > 0) {
@@ -215,7 +217,7 @@ k_chain_seg(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xc[u] = xn[u];
+        for (int u = 0; u < kPf; ++u) xc[u] = xn[u];
     }
     // a cluster that is still open behind the tail and holds a candidate of this segment was not decided
     if (t_stop < T && ((rz.n1 > 0 && cl_pos[kClusterMax] < end) || (rz.n0 > 0 && cl_pos[0] < end))) unsynced = true;
@@ -277,6 +279,80 @@ k_gram_slab(const float *__restrict__ vmem, double *__restrict__ part, int C2, l
     for (long long t = t0; t < t1; ++t) acc = fma((double)v[t * C2 + i], (double)v[t * C2 + j], acc);
     part[((long long)blockIdx.z * B + b) * C2 * C2 + i * C2 + j] = acc;
 }
+// The same partial sums for WIDE arrays as a tiled float32 product (config 5: 128 channels, C = V^T V is a real GEMM,
+// 7.9 G multiply-adds per 10 s clip; one thread per matrix element looping over time ran 14 ms).  A CTA owns one
+// 128 x 128 block (bi <= bj) of the Gram matrix over its time slab: rows of the membrane tile go through shared
+// memory 32 samples at a time, every thread keeps an 8 x 8 register tile (rows 4 ty.., 64 + 4 ty..; columns 4 tx..,
+// 64 + 4 tx..: conflict-free 128-bit reads).  A slab is kGtFlush samples: the float32 rounding of a 1024-term sum is
+// ~1e-6 relative, below the chain's own float32 error; the slabs are summed in float64 by k_gram_reduce.
+constexpr int kGtTile = 128, kGtK = 32, kGtFlush = 1024;
+static __global__ void __launch_bounds__(256, 1)
+k_gram_tiled(const float *__restrict__ vmem, double *__restrict__ part, int C2, long long B, long long T, long long t_start,
+             long long slab_len) {
+    __shared__ __align__(16) float As[kGtK][kGtTile + 4];
+    __shared__ __align__(16) float Bs[kGtK][kGtTile + 4];
+    const long long b = blockIdx.x;
+    const int nblk = (C2 + kGtTile - 1) / kGtTile;
+    int y = blockIdx.y, bi = 0;
+    while (y >= nblk - bi) { y -= nblk - bi; ++bi; }
+    const int bj = bi + y;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const long long t0 = t_start + (long long)blockIdx.z * slab_len, t1 = min(T, t0 + slab_len);
+    const float *v = vmem + b * T * C2;
+    const bool vec = (C2 & 3) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    for (long long t = t0; t < t1; t += kGtK) {
+        for (int e = threadIdx.x; e < kGtK * (kGtTile / 4); e += 256) {
+            const int r = e / (kGtTile / 4), c4 = e % (kGtTile / 4);
+            const long long tt = t + r;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (side == 1 && bj == bi) break;
+                const int col = (side ? bj : bi) * kGtTile + 4 * c4;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tt < t1) {
+                    const float *src = v + tt * C2 + col;
+                    if (vec && col + 3 < C2) val = *reinterpret_cast<const float4 *>(src);
+                    else {
+                        if (col < C2) val.x = src[0];
+                        if (col + 1 < C2) val.y = src[1];
+                        if (col + 2 < C2) val.z = src[2];
+                        if (col + 3 < C2) val.w = src[3];
+                    }
+                }
+                *reinterpret_cast<float4 *>(side ? &Bs[r][4 * c4] : &As[r][4 * c4]) = val;
+            }
+        }
+        __syncthreads();
+        const float (*Bp)[kGtTile + 4] = bj == bi ? As : Bs;
+#pragma unroll 4
+        for (int r = 0; r < kGtK; ++r) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[r][4 * ty]), a1 = *reinterpret_cast<const float4 *>(&As[r][64 + 4 * ty]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bp[r][4 * tx]), b1 = *reinterpret_cast<const float4 *>(&Bp[r][64 + 4 * tx]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gi = bi * kGtTile + (i < 4 ? 4 * ty + i : 64 + 4 * ty + i - 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gj = bj * kGtTile + (j < 4 ? 4 * tx + j : 64 + 4 * tx + j - 4);
+            if (gi < C2 && gj < C2 && gi <= gj)
+                part[(((long long)blockIdx.z * B + b) * C2 + gi) * C2 + gj] = (double)acc[i][j];
+        }
+    }
+}
 static __global__ void __launch_bounds__(256)
 k_gram_reduce(const double *__restrict__ part, double *__restrict__ gram, int C2, long long B, int nslab) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,16 +371,20 @@ k_gram_reduce(const double *__restrict__ part, double *__restrict__ gram, int C2
 // ---------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256)
 k_power_argmax(const double *__restrict__ gram, const double *__restrict__ Wd, float *__restrict__ power,
-               int32_t *__restrict__ doa, int C2, int G, double inv_T) {
+               int32_t *__restrict__ doa, int C2, int G, double inv_T, int nchunk, double *__restrict__ chunk_v,
+               int *__restrict__ chunk_i) {
     extern __shared__ __align__(16) double sm_d[];
     double *Cs = sm_d;
     __shared__ double red_v[256];
     __shared__ int red_i[256];
     const long long b = blockIdx.x;
+    // few clips and a wide array (BASELINE config 5): blockIdx.y takes a slice of the DoA grid, k_argmax_chunks finishes
+    const int gper = (G + nchunk - 1) / nchunk;
+    const int g_lo = blockIdx.y * gper, g_hi = min(G, g_lo + gper);
     for (int e = threadIdx.x; e < C2 * C2; e += blockDim.x) Cs[e] = gram[b * C2 * C2 + e];
     __syncthreads();
     double best = -1.0; int besti = 0x7fffffff;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    for (int g = g_lo + threadIdx.x; g < g_hi; g += blockDim.x) {
         double acc = 0.0;
         for (int i = 0; i < C2; ++i) {
             double r = 0.0;
@@ -326,7 +406,23 @@ k_power_argmax(const double *__restrict__ gram, const double *__restrict__ Wd, f
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && doa) doa[b] = red_i[0];
+    if (threadIdx.x == 0) {
+        if (nchunk == 1) { if (doa) doa[b] = red_i[0]; }
+        else { chunk_v[b * nchunk + blockIdx.y] = red_v[0]; chunk_i[b * nchunk + blockIdx.y] = red_i[0]; }
+    }
+}
+// first maximum over the DoA slices of k_power_argmax (ascending slices: a later slice only wins with a larger value)
+static __global__ void __launch_bounds__(32)
+k_argmax_chunks(const double *__restrict__ chunk_v, const int *__restrict__ chunk_i, int32_t *__restrict__ doa,
+                long long B, int nchunk) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double best = -1.0; int besti = 0x7fffffff;
+    for (int c = 0; c < nchunk; ++c) {
+        const double v = chunk_v[b * nchunk + c]; const int i = chunk_i[b * nchunk + c];
+        if (v > best || (v == best && i < besti)) { best = v; besti = i; }
+    }
+    doa[b] = besti;
 }
 
 // ---------------------------------------------------------------------------

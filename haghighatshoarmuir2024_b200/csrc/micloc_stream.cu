@@ -259,7 +259,7 @@ static int stream_finalise(micloc_stream *s, long long F_new, int8_t *spikes_dev
         k_gram<<<gg, 256, 0, st>>>(s->vmem, s->gram, p.C2, m, 0);
         const size_t smem = (size_t)p.C2 * p.C2 * sizeof(double);
         MICLOC_CUDA(cudaFuncSetAttribute(k_power_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_power_argmax<<<1, 256, smem, st>>>(s->gram, (const double *)s->prm.bf_f64_dev, power_dev, doa_dev, p.C2, p.G, 1.0 / (double)m);
+        k_power_argmax<<<1, 256, smem, st>>>(s->gram, (const double *)s->prm.bf_f64_dev, power_dev, doa_dev, p.C2, p.G, 1.0 / (double)m, 1, nullptr, nullptr);
         count_launch(2);
     }
     if (env_dev || doa_t_dev) {
