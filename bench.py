@@ -604,6 +604,33 @@ def run_extras(args, local, fp32_peak, lib):
         res[key]["one_clip_ms"] = one_ms
         del x
 
+    # design time: SNNBeamformer.design_from_template on the G = 449 grid of configs[1] -- per-DoA front
+    # end + neuron filter + covariance batched on the GPU (micloc_snn_gram), the 449 small eigen-problems on the host
+    try:
+        import contextlib
+        import io
+        from haghighatshoarmuir2024_b200.array_geometry import CenterCircularArray
+        from haghighatshoarmuir2024_b200.snn_beamformer import SNNBeamformer
+        d2, bands2 = load_workload()
+        band = bands2[0]
+        beamf = SNNBeamformer(CenterCircularArray(radius=4.5e-2, num_mic=NUM_MIC), float(d2["kernel_duration"]), band,
+                              [float(d2["tau_0"])] * 2, bipolar_spikes=True, fs=FS, device=local)
+        tt = np.arange(0, 0.25, 1 / FS)
+        tmpl = (tt, np.sin(2 * np.pi * float(np.mean(band)) * tt))
+        doa_list = np.linspace(-np.pi, np.pi, 449)
+        with contextlib.redirect_stdout(io.StringIO()):
+            beamf.design_from_template(tmpl, doa_list)
+            t0 = time.perf_counter()
+            bf = beamf.design_from_template(tmpl, doa_list)
+            dt_design = time.perf_counter() - t0
+        res["design_from_template"] = {
+            "workload": "SNNBeamformer.design_from_template, 7-mic array, 0.25 s sine template, G=449 (micloc/snn_beamformer.py:82-211)",
+            "seconds": dt_design, "doa_per_sec": 449 / dt_design, "bf_shape": list(bf.shape),
+            "note": "front end + neuron filter + covariance of all DoAs in one batch on the GPU (staged kernels, float64 Gram); "
+                    "the per-DoA SVD / constrained eigenvector stays on the host (numpy)"}
+    except Exception as e:
+        res["design_from_template"] = {"error": f"{type(e).__name__}: {e}"}
+
     # configs[2]: Xylo integer chain, bit-exact float64 front end + integer LIF network
     g = H.load("xylo_c3_bipolar")
     net = H.xylo_network(g)
