@@ -425,6 +425,15 @@ def run_gpu(args):
                 traffic = float(tj["dram_bytes_per_clip"]) * Bb          # bytes per launch of Bb clips
         except Exception:
             pass
+    # what the tensor cores execute for the STHT share (k_fused_tc): per tile of 128 stream samples x 32 columns a dense
+    # 128 x 368 Toeplitz product in three fp16 pieces -- 2 x 3 x 128 x 368 x 32 FLOP for 2 clips x 256 frames x M microphones
+    tensor_peak, tensor_src = 2250.0, "nominal dense fp16"
+    try:
+        tensor_peak, tensor_src = float(json.load(open(peaks_file))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        pass
+    mma_flop_per_mic_sample = 2.0 * 3 * 128 * 368 * 32 / (2 * 256 * NUM_MIC)
+    tensor_tflops = mic_samples_per_launch * mma_flop_per_mic_sample / (avg_launch_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp32", "kernel": "k_fused" if os.environ.get("MICLOC_FUSED_FIR", "")[:1] == "f" else "k_fused_tc",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -440,6 +449,10 @@ def run_gpu(args):
         "launch_timing": ("3 band launches per step overlap on 3 streams: avg_launch_ms = step device time / 3; "
                           "kernel_share_of_step sums the overlapping per-launch event durations (> 1 when they overlap)"
                           if side else "CUDA events around every launch on its stream, inside the library"),
+        "tensor_view": {"achieved": tensor_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tensor_peak,
+                        "executed_flop_per_mic_sample": mma_flop_per_mic_sample, "peak_source": tensor_src,
+                        "note": "fp16 tcgen05.mma FLOPs k_fused_tc executes for the STHT (dense Toeplitz tiles incl. their zeros, "
+                                "hi/lo split x3): 5.3 x the 480 algorithmic FLOPs; not the bound"},
         "hbm_view": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                      "peak_source": hbm_src + " (MEASURED_PEAKS.json hbm_gbs)" if hbm_src == "measured" else "fallback 6650",
                      "bytes_per_mic_sample": in_bytes + 2},
