@@ -24,14 +24,18 @@
 //               of an instruction: 1 KB.  (A first version had the samples as the A operand, a Hankel matrix read
 //               through overlapping core matrices: correct, but 4.5 KB of shared-memory reads per instruction starved
 //               the serial warps -- profiles/README.md.)
-//   in          The producer warp streams 128-frame audio tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
-//               into a staging buffer; the four serial warps convert it into the hi/lo rings at the top of a step;
-//               the producer issues the MMAs of a tile once its four audio tiles are in.
+//   in          Front-end warp 0 streams 128-frame audio tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier)
+//               into a staging buffer; the four front-end warps convert it into the hi/lo rings at the top of a step;
+//               warp 3 issues the K steps of an MMA tile as their samples arrive, a quarter per step.
 //   out         A step's 32 stream samples are one 32-lane quarter of the accumulator: the warp owning that quarter
 //               moves them into the step's q rows (tcgen05.ld); all four warps rebuild the in-phase samples
 //               x[t - K/2] (np.roll: the first K/2 come from the clip tail) from the rings.
 //
-// One CTA holds two independent clip-pair groups of five warps (four serial roles + producer).
+// One CTA holds two independent clip-pair groups of eight warps: four serial roles (band-pass, RZCC, neuron, Gram) and
+// four front-end warps (warp q owns tensor-memory lane quarter q; warp 0 also issues the TMA copies, warp 1 scans the
+// next clip pair's largest magnitude, warp 3 issues the MMAs through one elected lane).  The same role of both groups
+// sits on the same SM sub-partition (warp id mod 4): a sub-partition then runs ~20 KB of code (one serial role + the
+// front end), which is what its instruction cache holds -- other pairings measured 3-7 % slower.
 #include <cstdlib>
 
 #include "micloc_fused_common.cuh"

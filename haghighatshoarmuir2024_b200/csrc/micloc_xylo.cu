@@ -388,6 +388,27 @@ __device__ __forceinline__ int xylo_step(int &isyn, int &vmem, int in, int ds, i
     return ns;
 }
 
+// The same step for the tensor-core-input kernel, which is bound by the integer ALU pipe (half rate): no clamps when the
+// host has proved them idle (SAT_ISYN / SAT_V), no bias add without a bias, and the common single spike as two
+// predicated ops.  Identical results.
+template <bool SAT_ISYN, bool SAT_V, bool HAS_BIAS>
+__device__ __forceinline__ void xylo_step_lean(int &isyn, int &vmem, int &count, int in, int ds, int dm, int bs, int th,
+                                               int max_spikes, int &ns_out) {
+    isyn = xylo_decay(isyn, ds) + in;
+    if (SAT_ISYN) isyn = xylo_sat16(isyn);
+    int v = xylo_decay(vmem, dm) + isyn;
+    if (HAS_BIAS) v += bs;
+    if (SAT_V) v = xylo_sat16(v);
+    int ns = 0;
+    if (v >= th) { v -= th; ns = 1; }                  // predicated
+    if (v >= th) {                                     // rare: several spikes in one step
+        while (v >= th && ns < max_spikes) { v -= th; ++ns; }
+    }
+    count += ns;
+    vmem = v;
+    ns_out = ns;
+}
+
 // named barriers (ids 1..4): full[buf] = masks of a tile are ready, empty[buf] = they have been consumed
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -538,6 +559,194 @@ k_xylo_lif(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in, con
     if (live && counts) counts[b * N + n] = count;
 }
 
+
+// ---------------------------------------------------------------------------
+// The same network with the weighted input on the tensor cores.  The input current of a step, sum_i spike_i[t] w[i][n],
+// IS a matrix product (binary spikes [T][N_in] x int8 weights [N_in][N]).  Every neuron warp computes it for its own 32
+// neurons, exactly, with int8 mma.sync.m16n8k32 (A = weights of 16 neurons x 32 inputs, held in registers for the
+// whole clip; B = 8 time steps x 32 inputs from the tile's binary spike rows; int32 accumulators): 6 MMAs per tile of
+// 24 steps.  The accumulator layout spreads a neuron's steps over four lanes, so the sums pass through a warp-private
+// int16 [neuron][step] buffer in shared memory (48-byte rows: the 32-bit stores and the 128-bit loads are both
+// conflict-free) and a neuron thread fetches the inputs of 8 steps with one load.  Per step that is ~2 instructions
+// instead of the ~12 of the event loop above (bit scan + address + load + add per event), at identical integer
+// results.  The producer warp only turns the signed spike bytes of the next tile into binary rows.
+// Needs N_in <= 32 and |sum| < 2^15 (checked by the host); otherwise the event-loop kernel runs.
+// ---------------------------------------------------------------------------
+constexpr int kMmaTile = 24;     // time steps per tile: 3 MMA column blocks
+#ifndef MICLOC_LIF_MMA_MINB
+#define MICLOC_LIF_MMA_MINB 2
+#endif
+
+__device__ __forceinline__ void mma_s8_16x8x32(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
+}
+
+constexpr int kTrPitch = 28;      // int32 words per neuron row of the hand-over buffer: 24 steps + 4 (conflict-free 128-bit reads)
+template <bool SIGNED_IN, bool SAT_ISYN, bool SAT_V, bool HAS_BIAS, bool RASTER>
+__global__ void __launch_bounds__(512, MICLOC_LIF_MMA_MINB)
+k_xylo_lif_mma(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in, const int8_t *__restrict__ w8, int w_shift,
+               const int16_t *__restrict__ thr, const int8_t *__restrict__ dash_syn, const int8_t *__restrict__ dash_mem,
+               const int16_t *__restrict__ bias, int max_spikes, int N, int npb, long long T,
+               uint8_t *__restrict__ raster, int32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint8_t *Sb = sm_raw;                                                                // [2][kMmaTile][32] binary spikes
+    int *tr_all = reinterpret_cast<int *>(sm_raw + 2 * kMmaTile * 32);                   // [neuron warps][32][kTrPitch]
+    const int row = SIGNED_IN ? CI : N_in;
+
+    const long long b = blockIdx.x;
+    const int n0 = blockIdx.y * npb;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int n_cons = nthreads - 32;
+    const int ntiles = (int)((T + kMmaTile - 1) / kMmaTile);
+    for (int e = tid; e < 2 * kMmaTile * 32; e += nthreads) Sb[e] = 0;       // columns beyond the inputs stay zero
+    __syncthreads();
+
+    if (tid >= n_cons) {
+        // ---------------- producer warp: signed spike bytes -> binary rows ----------------
+        // lane = time step of the tile; a row (<= 32 bytes, even length) travels as 16-bit words, prefetched one tile ahead
+        const int lane = tid - n_cons;
+        const int8_t *src = spikes + b * T * row;
+        constexpr int kPreW = 16;
+        unsigned short pre[kPreW];
+        auto prefetch = [&](int k) {
+            const long long t = (long long)k * kMmaTile + lane;
+            const bool valid = k < ntiles && lane < kMmaTile && t < T;
+            const unsigned short *gp = reinterpret_cast<const unsigned short *>(src + t * row);
+#pragma unroll
+            for (int j = 0; j < kPreW; ++j) pre[j] = (valid && 2 * j < row) ? __ldg(gp + j) : (unsigned short)0;
+        };
+        prefetch(0);
+        for (int k = 0; k < ntiles; ++k) {
+            if (k >= 2) bar_sync_named(3 + (k & 1), nthreads);       // rows k&1 have been read (tile k-2)
+            if (lane < kMmaTile) {
+                uint8_t *S = Sb + ((k & 1) * kMmaTile + lane) * 32;
+#pragma unroll
+                for (int j = 0; j < kPreW; ++j) {
+                    if (2 * j < row) {
+                        const int v0 = (int)(signed char)(pre[j] & 0xff), v1 = (int)(signed char)(pre[j] >> 8);   // zero behind the clip end
+                        if (SIGNED_IN) {
+                            *reinterpret_cast<unsigned short *>(S + 2 * j) = (unsigned short)((v0 > 0 ? 1 : 0) | (v1 > 0 ? 0x100 : 0));
+                            if (bipolar) { S[CI + 2 * j] = v0 < 0 ? 1 : 0; S[CI + 2 * j + 1] = v1 < 0 ? 1 : 0; }
+                        } else {
+                            *reinterpret_cast<unsigned short *>(S + 2 * j) = (unsigned short)((v0 != 0 ? 1 : 0) | (v1 != 0 ? 0x100 : 0));
+                        }
+                    }
+                }
+            }
+            __threadfence_block();
+            bar_arrive_named(1 + (k & 1), nthreads);                 // rows of tile k are ready
+            prefetch(k + 1);                                         // next tile's bytes on their way
+        }
+        return;
+    }
+
+    // ---------------- neuron warps ----------------
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int n = n0 + tid;
+    const bool live = tid < npb && n < N;
+    int isyn = 0, vmem = 0, count = 0;
+    const int th = live ? thr[n] : 0x3fffffff;
+    const int th2 = 2 * th;
+    const int ds = live ? dash_syn[n] : 0, dm = live ? dash_mem[n] : 0;
+    const int bs = (live && bias) ? bias[n] : 0;
+    uint8_t *rp = (RASTER && live) ? raster + b * T * N + n : nullptr;
+    int *tr = tr_all + (size_t)warp * 32 * kTrPitch;
+    // A fragments of this warp's two blocks of 16 neurons: a0 = (neuron g, inputs 4 tq ..), a1 = (neuron g + 8, same),
+    // a2 / a3 = inputs 16 + 4 tq ..
+    unsigned af[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int nl = 32 * warp + 16 * r + g + 8 * (q & 1);   // neuron inside this CTA's chunk
+            unsigned v = 0u;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 16 * (q >> 1) + 4 * tq + e;
+                const int wv = (i < N_in && nl < npb && n0 + nl < N) ? (int)w8[(long long)i * N + n0 + nl] : 0;
+                v |= ((unsigned)wv & 0xffu) << (8 * e);
+            }
+            af[r][q] = v;
+        }
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int len = (int)min((long long)kMmaTile, T - (long long)k * kMmaTile);
+        bar_sync_named(1 + (k & 1), nthreads);                       // wait for the binary rows of tile k
+        const uint8_t *S = Sb + (k & 1) * kMmaTile * 32;
+        unsigned bf[kMmaTile / 8][2];
+#pragma unroll
+        for (int sb = 0; sb < kMmaTile / 8; ++sb) {
+            bf[sb][0] = *reinterpret_cast<const unsigned *>(S + (8 * sb + g) * 32 + 4 * tq);
+            bf[sb][1] = *reinterpret_cast<const unsigned *>(S + (8 * sb + g) * 32 + 16 + 4 * tq);
+        }
+        if (k + 2 < ntiles) bar_arrive_named(3 + (k & 1), nthreads); // rows k&1 may be refilled (tile k+2)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int sb = 0; sb < kMmaTile / 8; ++sb) {
+                int d[4];
+                mma_s8_16x8x32(d, af[r], bf[sb][0], bf[sb][1]);
+                // d0, d1 = (neuron g, steps 2 tq, 2 tq + 1); d2, d3 = neuron g + 8
+                *reinterpret_cast<int2 *>(tr + (16 * r + g) * kTrPitch + 8 * sb + 2 * tq) = make_int2(d[0] << w_shift, d[1] << w_shift);
+                *reinterpret_cast<int2 *>(tr + (16 * r + g + 8) * kTrPitch + 8 * sb + 2 * tq) = make_int2(d[2] << w_shift, d[3] << w_shift);
+            }
+        __syncwarp();
+        if (live) {
+            const int *wt = tr + lane * kTrPitch;
+#pragma unroll 1
+            for (int s0 = 0; s0 < len; s0 += 8) {
+                const int4 p0 = *reinterpret_cast<const int4 *>(wt + s0), p1 = *reinterpret_cast<const int4 *>(wt + s0 + 4);
+                const int in[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                if (s0 + 8 <= len) {
+                    // eight steps with at most ONE spike each (the common case: two predicated ops per step, no branch);
+                    // a step that would fire again (V >= 2 threshold, rare) only raises a flag, and the group is then
+                    // redone from its saved state by the exact multi-spike loop
+                    const int isyn0 = isyn, vmem0 = vmem, count0 = count;
+                    bool again = false;
+                    unsigned fired = 0u;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        isyn = xylo_decay(isyn, ds) + in[u];
+                        if (SAT_ISYN) isyn = xylo_sat16(isyn);
+                        int v = xylo_decay(vmem, dm) + isyn;
+                        if (HAS_BIAS) v += bs;
+                        if (SAT_V) v = xylo_sat16(v);
+                        if (v >= th) { v -= th; ++count; if (RASTER) fired |= 1u << u; }
+                        again |= v >= th;
+                        vmem = v;
+                    }
+                    if (again) {
+                        isyn = isyn0; vmem = vmem0; count = count0;
+#pragma unroll 1
+                        for (int u = 0; u < 8; ++u) {
+                            int ns;
+                            xylo_step_lean<SAT_ISYN, SAT_V, HAS_BIAS>(isyn, vmem, count, in[u], ds, dm, bs, th, max_spikes, ns);
+                            if (RASTER) { *rp = (uint8_t)ns; rp += N; }
+                        }
+                    } else if (RASTER) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { *rp = (uint8_t)((fired >> u) & 1u); rp += N; }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int u = 0; u < 8; ++u)
+                        if (s0 + u < len) {
+                            int ns;
+                            xylo_step_lean<SAT_ISYN, SAT_V, HAS_BIAS>(isyn, vmem, count, in[u], ds, dm, bs, th, max_spikes, ns);
+                            if (RASTER) { *rp = (uint8_t)ns; rp += N; }
+                        }
+                }
+            }
+        }
+        __syncwarp();                                                // the next tile overwrites this warp's buffer
+    }
+    if (live && counts) counts[b * N + n] = count;
+}
+
 // One CTA per clip: S[g] = sum_f counts[f*G + g]; doa = first argmax S; doa_peak = first argmax of the
 // 'full' box-car sums of S, minus win/2, modulo G (micloc/utils.py:84-121 on integers).
 __global__ void __launch_bounds__(128)
@@ -617,6 +826,7 @@ struct micloc_xylo {
     int F = 1, N = 0, G = 0, N_in = 0, CT = 0, nba = 0, max_spikes = 31;
     bool has_rec = false;
     bool sat_isyn = true;           // I_syn can reach the int16 limits: keep the clamps
+    bool sat_v = true;              // V_mem can reach the int16 limits
     float *d_taps = nullptr;        // float32 compacted STHT taps (fast front end)
     float *d_band_sos = nullptr;    // [F][kMaxSections][5]
     double *d_h = nullptr;          // [K] float64 STHT kernel (exact front end)
@@ -625,6 +835,9 @@ struct micloc_xylo {
     long long n_fallback = 0;       // clips the fast exact front end handed to the unbounded kernels so far
     double *d_ba_b = nullptr, *d_ba_a = nullptr;   // [F][nba]
     int16_t *d_w = nullptr;         // [N_in][N] input weights, shift applied
+    int8_t *d_w8 = nullptr;         // [N_in][N] input weights as given (tensor-core input path)
+    int w_shift = 0;
+    bool lif_mma = false;           // k_xylo_lif_mma applies (N_in <= 32, weighted sums fit int16)
     int16_t *d_thr = nullptr, *d_bias = nullptr;
     int8_t *d_ds = nullptr, *d_dm = nullptr;
     DevBuf q, qd, zd, signed_spk, counts, flags;
@@ -642,7 +855,7 @@ extern "C" int micloc_xylo_destroy(micloc_xylo *c) {
     if (!c) return MICLOC_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_taps); cudaFree(c->d_band_sos); cudaFree(c->d_h); cudaFree(c->d_g); cudaFree(c->d_ba_b); cudaFree(c->d_ba_a);
-    cudaFree(c->d_w); cudaFree(c->d_thr); cudaFree(c->d_bias); cudaFree(c->d_ds); cudaFree(c->d_dm);
+    cudaFree(c->d_w); cudaFree(c->d_w8); cudaFree(c->d_thr); cudaFree(c->d_bias); cudaFree(c->d_ds); cudaFree(c->d_dm);
     cudaFree(c->d_Wd1); cudaFree(c->d_sm_slots);
     c->q.release(); c->qd.release(); c->zd.release(); c->signed_spk.release(); c->counts.release(); c->flags.release();
     delete c;
@@ -728,12 +941,26 @@ extern "C" int micloc_xylo_create(const micloc_xylo_config *cfg, int device, mic
         std::vector<int16_t> w16((size_t)N_in * N);
         for (size_t i = 0; i < w16.size(); ++i) w16[i] = (int16_t)((int)cfg->w_in[i] << cfg->weight_shift_in);
         rc = upload(&c->d_w, w16.data(), w16.size());
+        if (!rc) rc = upload(&c->d_w8, cfg->w_in, (size_t)N_in * N);
+        c->w_shift = cfg->weight_shift_in;
+        // tensor-core input path (k_xylo_lif_mma): 32 input columns per MMA, int16 hand-over of the weighted sum
+        c->lif_mma = N_in <= 32 && cfg->weight_shift_in >= 0 && (((long long)N_in * 128) << cfg->weight_shift_in) <= 32767;
         // |I_syn| <= 2^dash_syn * (sum_i |w_i| + 1) by induction over the decay recurrence
         c->sat_isyn = false;
         for (int n = 0; n < N && !c->sat_isyn; ++n) {
             long long sabs = 1;
             for (int i = 0; i < N_in; ++i) sabs += w16[(size_t)i * N + n] < 0 ? -w16[(size_t)i * N + n] : w16[(size_t)i * N + n];
             if ((sabs << cfg->dash_syn[n]) > 32767) c->sat_isyn = true;
+        }
+        // |V_mem| <= 2^dash_mem * (I + |bias| + 1) with I the bound on |I_syn|: one decay step removes at least
+        // |V| / 2^dash_mem - 1, the spikes only move a positive V towards zero
+        c->sat_v = c->sat_isyn;
+        for (int n = 0; n < N && !c->sat_v; ++n) {
+            long long sabs = 1;
+            for (int i = 0; i < N_in; ++i) sabs += w16[(size_t)i * N + n] < 0 ? -w16[(size_t)i * N + n] : w16[(size_t)i * N + n];
+            const long long ib = sabs << cfg->dash_syn[n];
+            const long long bb = cfg->bias ? (cfg->bias[n] < 0 ? -(long long)cfg->bias[n] : (long long)cfg->bias[n]) : 0;
+            if (((ib + bb + 1) << cfg->dash_mem[n]) > 32767) c->sat_v = true;
         }
     }
     if (!rc) rc = upload(&c->d_thr, cfg->threshold, (size_t)N);
@@ -778,6 +1005,26 @@ static int launch_lif(micloc_xylo *c, const int8_t *spikes, long long B, long lo
     const int nchunks = (N + 479) / 480;                       // <= 480 neurons (15 warps) per CTA
     const int npb = (N + nchunks - 1) / nchunks;
     const int threads = ((npb + 31) & ~31) + 32;             // neuron warps + the producer warp
+    const int row_in = SIGNED_IN ? c->CT : c->N_in;
+    if (c->lif_mma && row_in <= 32 && (row_in & 1) == 0 && ((uintptr_t)spikes & 1) == 0 && !getenv("MICLOC_XYLO_LIF_ADDS")) {
+        const size_t smem_m = (size_t)2 * kMmaTile * 32 + (size_t)((threads - 32) / 32) * 32 * kTrPitch * 4 + 16;
+        dim3 grid_m((unsigned)B, (unsigned)nchunks);
+        void (*kern)(const int8_t *, int, int, int, const int8_t *, int, const int16_t *, const int8_t *, const int8_t *,
+                     const int16_t *, int, int, int, long long, uint8_t *, int32_t *) = nullptr;
+        const bool hb = c->d_bias != nullptr;
+#define MICLOC_MMA_PICK(SI, SV, HB)                                                                          \
+        kern = raster ? k_xylo_lif_mma<SIGNED_IN, SI, SV, HB, true> : k_xylo_lif_mma<SIGNED_IN, SI, SV, HB, false>
+        if (c->sat_isyn) { if (hb) MICLOC_MMA_PICK(true, true, true); else MICLOC_MMA_PICK(true, true, false); }
+        else if (c->sat_v) { if (hb) MICLOC_MMA_PICK(false, true, true); else MICLOC_MMA_PICK(false, true, false); }
+        else { if (hb) MICLOC_MMA_PICK(false, false, true); else MICLOC_MMA_PICK(false, false, false); }
+#undef MICLOC_MMA_PICK
+        MICLOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+        kern<<<grid_m, threads, smem_m, st>>>(spikes, c->CT, c->p.bipolar, c->N_in, c->d_w8, c->w_shift, c->d_thr, c->d_ds, c->d_dm,
+                                              c->d_bias, c->max_spikes, N, npb, T, raster, counts);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+        return MICLOC_OK;
+    }
     const int W = (c->N_in + 31) / 32;
     const int npb_pad = (npb + 7) & ~7;
     const int row = SIGNED_IN ? c->CT : c->N_in;

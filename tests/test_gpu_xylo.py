@@ -223,3 +223,30 @@ def test_demo_dropin_methods():
     rate = demo.extract_rate(raster)
     assert rate.shape == (len(g["doa_list"]),)
     assert demo.estimate_doa_from_rate(rate, "peak") == g["doa_list"][np.argmax(rate)]
+
+
+@pytest.mark.parametrize("scale,bias", [(1, False), (8, False), (1, True)])
+def test_tensor_core_input_kernel_equals_event_loop_kernel_and_oracle(scale, bias, monkeypatch):
+    """k_xylo_lif_mma (weighted input by int8 MMA, clamps dropped where the host proves them idle) against the
+    event-loop kernel and the oracle: small weights (no clamp can trigger: SAT_ISYN = SAT_V = false), the reference's
+    weights, with and without a bias; dense and sparse input, a ragged clip length."""
+    rng = np.random.default_rng(5 + scale)
+    g = H.load("xylo_c3_bipolar")
+    net = H.xylo_network(g)
+    n = net.w_in.shape[1]
+    net.w_in = np.clip(net.w_in.astype(np.int32) // scale, -127, 127).astype(np.int8)
+    net.threshold = np.full(n, max(int(net.threshold[0]) // scale, 2), dtype=np.int16)
+    if bias:
+        net.bias = rng.integers(-2, 3, size=n).astype(np.int16)
+    eng = H.xylo_engine(g, net)
+    cfg = H.xylo_oracle_cfg(g, net)
+    for T, density in ((1000, 0.04), (253, 0.5)):
+        s = (rng.random((3, T, net.w_in.shape[0])) < density).astype(np.int8)
+        monkeypatch.delenv("MICLOC_XYLO_LIF_ADDS", raising=False)
+        mma = eng.process(dev(s), want_raster=True)
+        monkeypatch.setenv("MICLOC_XYLO_LIF_ADDS", "1")
+        adds = eng.process(dev(s), want_raster=True)
+        assert torch.equal(mma["raster"], adds["raster"]) and torch.equal(mma["counts"], adds["counts"])
+        raster, counts = O.xylo_lif(cfg, s[0])
+        assert np.array_equal(mma["raster"][0].cpu().numpy(), raster)
+        assert np.array_equal(mma["counts"][0].cpu().numpy(), counts)

@@ -1,0 +1,3 @@
+python tools/xylo_bench.py 3552 2>&1 | tail -5
+MICLOC_B200_LIB=$PWD/tools/libmicloc_b200_vX3.so python -m pytest tests/test_gpu_xylo.py -m gpu -q -x 2>&1 | tail -2
+MICLOC_B200_LIB=$PWD/tools/libmicloc_b200_vX3.so python tools/xylo_bench.py 3552 2>&1 | tail -5
