@@ -583,6 +583,11 @@ __device__ __forceinline__ void mma_s8_16x8x32(int (&d)[4], const unsigned (&a)[
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0));
 }
 
+__device__ __forceinline__ int imad_pipe(int a, int b, int c) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 constexpr int kTrPitch = 28;      // int32 words per neuron row of the hand-over buffer: 24 steps + 4 (conflict-free 128-bit reads)
 template <bool SIGNED_IN, bool SAT_ISYN, bool SAT_V, bool HAS_BIAS, bool RASTER>
 __global__ void __launch_bounds__(512, MICLOC_LIF_MMA_MINB)
@@ -655,6 +660,7 @@ k_xylo_lif_mma(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in,
     const int bs = (live && bias) ? bias[n] : 0;
     uint8_t *rp = (RASTER && live) ? raster + b * T * N + n : nullptr;
     int *tr = tr_all + (size_t)warp * 32 * kTrPitch;
+    const int one = (w_shift >> 31) + 1, neg_one = -one;      // 1 and -1 (w_shift >= 0), but not to the compiler
     // A fragments of this warp's two blocks of 16 neurons: a0 = (neuron g, inputs 4 tq ..), a1 = (neuron g + 8, same),
     // a2 / a3 = inputs 16 + 4 tq ..
     unsigned af[2][4];
@@ -710,9 +716,11 @@ k_xylo_lif_mma(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in,
                     unsigned fired = 0u;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        isyn = xylo_decay(isyn, ds) + in[u];
+                        // (the adds as IMADs by a register that holds 1 / -1: they issue on the FMA pipe, which idles, instead
+                        //  of the half-rate integer ALU pipe that bounds this loop)
+                        isyn = imad_pipe(in[u], one, imad_pipe(max(isyn >> ds, min(isyn, 1)), neg_one, isyn));
                         if (SAT_ISYN) isyn = xylo_sat16(isyn);
-                        int v = xylo_decay(vmem, dm) + isyn;
+                        int v = imad_pipe(isyn, one, imad_pipe(max(vmem >> dm, min(vmem, 1)), neg_one, vmem));
                         if (HAS_BIAS) v += bs;
                         if (SAT_V) v = xylo_sat16(v);
                         if (v >= th) { v -= th; ++count; if (RASTER) fired |= 1u << u; }
