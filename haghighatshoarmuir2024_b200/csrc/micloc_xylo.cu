@@ -723,7 +723,7 @@ k_xylo_lif_mma(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in,
                         int v = imad_pipe(isyn, one, imad_pipe(max(vmem >> dm, min(vmem, 1)), neg_one, vmem));
                         if (HAS_BIAS) v += bs;
                         if (SAT_V) v = xylo_sat16(v);
-                        if (v >= th) { v -= th; ++count; if (RASTER) fired |= 1u << u; }
+                        if (v >= th) { v = imad_pipe(th, neg_one, v); count = imad_pipe(one, one, count); if (RASTER) fired |= 1u << u; }
                         again |= v >= th;
                         vmem = v;
                     }
