@@ -356,17 +356,29 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     MICLOC_TRY(c->gram.reserve((size_t)B * p.C2 * p.C2 * sizeof(double)));
     dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
     const bool few_long = (long long)gg.x * gg.y < 2ll * c->sm_count && T >= 65536 && !getenv("MICLOC_NO_SEGMENTS");
-    if (few_long && p.C2 >= 32) {
-        // few long clips of a wide array (BASELINE config 5): the Gram matrix as a tiled float32 product over time slabs
+    if (p.C2 >= 32 && T >= 256 && !getenv("MICLOC_NO_SEGMENTS")) {
+        // wide arrays (BASELINE config 5: 128 channels): the Gram matrix is a real GEMM -- a tiled float32 product over
+        // time slabs, summed in float64; clips go through in groups that bound the slab buffer to 1 GB
         const int nblk = (p.C2 + kGtTile - 1) / kGtTile, nblocks = nblk * (nblk + 1) / 2;
         const long long slab_len = kGtFlush;                                 // float32 sums of 1024 samples, float64 across slabs
         const long long nslab = (T + slab_len - 1) / slab_len;
         if (nslab > 65535) return set_error(MICLOC_ERR_UNSUPPORTED, "clip too long for the tiled Gram kernel");
-        MICLOC_TRY(c->part.reserve((size_t)nslab * B * p.C2 * p.C2 * sizeof(double)));
-        k_gram_tiled<<<dim3((unsigned)B, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(vmem, (double *)c->part.ptr, p.C2, B, T, 0, slab_len);
-        const long long ne = B * p.C2 * p.C2;
-        k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, (int)nslab);
-        count_launch(1);
+        const size_t per_clip = (size_t)nslab * p.C2 * p.C2 * sizeof(double);
+        long long bgrp = (long long)(((size_t)1 << 30) / per_clip);
+        if (bgrp < 1) bgrp = 1;
+        if (bgrp > B) bgrp = B;
+        if (bgrp > 65535) bgrp = 65535;
+        MICLOC_TRY(c->part.reserve((size_t)bgrp * per_clip));
+        for (long long b0 = 0; b0 < B; b0 += bgrp) {
+            const long long nb = B - b0 < bgrp ? B - b0 : bgrp;
+            k_gram_tiled<<<dim3((unsigned)nb, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(
+                vmem + (size_t)b0 * T * p.C2, (double *)c->part.ptr, p.C2, nb, T, 0, slab_len);
+            const long long ne = nb * p.C2 * p.C2;
+            k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr,
+                                                                       (double *)c->gram.ptr + (size_t)b0 * p.C2 * p.C2, p.C2, nb, (int)nslab);
+            count_launch(2);
+        }
+        count_launch(-1);
     } else if (few_long) {
         // few long clips: time slabs so that the sum fills the GPU
         int nslab = (int)((4ll * c->sm_count + (long long)gg.x * gg.y - 1) / ((long long)gg.x * gg.y));
