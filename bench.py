@@ -318,6 +318,20 @@ def run_gpu(args):
         m_, n_ = e.last_kernel_ms()
         kern_ms += m_; kern_n += n_
         e.enable_timing(False)
+    # cross-check of the launch time with one launch at a time (no overlap between the bands): the library's CUDA events
+    # around every k_fused_tc launch on its stream, two passes over the three bands, outside the timed region
+    solo_ms, solo_n = 0.0, 0
+    for e in sweep.engines:
+        e.enable_timing(True)
+    for _ in range(2):
+        for i in range(nb):
+            o_ = sweep.run_band(i, audio[i], want_spikes=True, want_power=False, hist=None, refine=False)
+            torch.cuda.synchronize()
+            del o_
+    for e in sweep.engines:
+        m_, n_ = e.last_kernel_ms()
+        solo_ms += m_; solo_n += n_
+        e.enable_timing(False)
     tm = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -446,8 +460,11 @@ def run_gpu(args):
                 "Toeplitz tiles), so the FP32 pipe itself carries only the 94 non-STHT FLOPs per mic-sample",
         "avg_launch_ms": avg_launch_ms, "launches_timed": kern_n, "mic_samples_per_launch": mic_samples_per_launch,
         "kernel_share_of_step": kern_ms / ms,
+        "solo_launch_ms": solo_ms / max(solo_n, 1), "solo_launches_timed": solo_n,
+        "solo_frac": (mic_samples_per_launch * F_gram / (solo_ms / max(solo_n, 1) * 1e-3) / 1e12) / fp32_peak,
         "launch_timing": ("3 band launches per step overlap on 3 streams: avg_launch_ms = step device time / 3; "
-                          "kernel_share_of_step sums the overlapping per-launch event durations (> 1 when they overlap)"
+                          "kernel_share_of_step sums the overlapping per-launch event durations (> 1 when they overlap); "
+                          "solo_launch_ms = CUDA events around single launches with nothing else running (their tails do not overlap)"
                           if side else "CUDA events around every launch on its stream, inside the library"),
         "tensor_view": {"achieved": tensor_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tensor_tflops / tensor_peak,
                         "executed_flop_per_mic_sample": mma_flop_per_mic_sample, "peak_source": tensor_src,
