@@ -378,7 +378,6 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
                                                                        (double *)c->gram.ptr + (size_t)b0 * p.C2 * p.C2, p.C2, nb, (int)nslab);
             count_launch(2);
         }
-        count_launch(-1);
     } else if (few_long) {
         // few long clips: time slabs so that the sum fills the GPU
         int nslab = (int)((4ll * c->sm_count + (long long)gg.x * gg.y - 1) / ((long long)gg.x * gg.y));
@@ -389,9 +388,10 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
         k_gram_slab<<<gg, 256, 0, st>>>(vmem, (double *)c->part.ptr, p.C2, B, T, 0, slab_len);
         const long long ne = B * p.C2 * p.C2;
         k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, nslab);
-        count_launch(1);
+        count_launch(2);
     } else {
         k_gram<<<gg, 256, 0, st>>>(vmem, (double *)c->gram.ptr, p.C2, T, 0);
+        count_launch(1);
     }
     const size_t smem = (size_t)p.C2 * p.C2 * sizeof(double);
     MICLOC_CUDA(cudaFuncSetAttribute(k_power_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -411,7 +411,7 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
     }
     k_power_argmax<<<dim3((unsigned)B, (unsigned)nchunk), 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
                                                                           1.0 / (double)T, nchunk, cv, ci);
-    count_launch(2);
+    count_launch(1);
     if (nchunk > 1 && doa) {
         k_argmax_chunks<<<(unsigned)((B + 31) / 32), 32, 0, st>>>(cv, ci, doa, B, nchunk);
         count_launch(1);
