@@ -481,8 +481,8 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         cfgs = oracle_cfgs(d, bands)
-        n_cpu = args.cpu_clips_per_band if args.cpu_clips_per_band > 0 else cores
-        n_cpu = min(n_cpu, Bb)
+        n_cpu = args.cpu_clips_per_band if args.cpu_clips_per_band > 0 else 4 * cores      # ~4 s of wall time on all cores
+        n_cpu = min(n_cpu, Bb, Be)
         xs = [host[i][:n_cpu].numpy() for i in range(nb)]
         n, s, ref = cpu_pass(cfgs, xs, cores)
         cpu = {"value": n / s, "unit": UNIT, "cores": cores, "kind": "port",
@@ -676,10 +676,10 @@ def run_extras(args, local, fp32_peak, lib):
     ms_lif, _ = _timed(torch, lambda: eng.process(spikes, want_raster=False), n=2)
     del spikes
     ms_fast, outf = _timed(torch, lambda: eng.run(x, exact=False), n=2)
-    n_cmp = 8
+    n_cmp = 64
     t0 = time.perf_counter()
     ocfg = H.xylo_oracle_cfg(g, net)
-    ref = O.xylo_run_batch(ocfg, xs[:n_cmp].cpu().numpy(), FS, nthreads=min(cores, n_cmp))
+    ref = O.xylo_run_batch(ocfg, x[:n_cmp].cpu().numpy(), FS, nthreads=min(cores, n_cmp))
     cpu_s = time.perf_counter() - t0
     ref["spikes_in"] = np.stack([O.xylo_encode(ocfg, xs[i].cpu().numpy())[0] for i in range(2)])
     v = ctypes.c_double()
