@@ -369,12 +369,23 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
         if (bgrp > B) bgrp = B;
         if (bgrp > 65535) bgrp = 65535;
         MICLOC_TRY(c->part.reserve((size_t)bgrp * per_clip));
+        // tensor-core form (fp16 hi + lo of the membrane values x 2^12): needs |v| <= sum |h| < 15 to stay in fp16 range
+        double habs = 0.0, an = 1.0;
+        for (int n = 0; n < p.nL; ++n) { habs += (double)p.nc * n * an; an *= (double)p.na; }
+        const bool tc = p.C2 >= 64 && habs < 15.0 && !getenv("MICLOC_GRAM_FP32");
         for (long long b0 = 0; b0 < B; b0 += bgrp) {
             const long long nb = B - b0 < bgrp ? B - b0 : bgrp;
-            k_gram_tiled<<<dim3((unsigned)nb, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(
-                vmem + (size_t)b0 * T * p.C2, (double *)c->part.ptr, p.C2, nb, T, 0, slab_len);
+            if (tc && nblk == 1)
+                k_gram_tc<true><<<dim3((unsigned)nb, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(
+                    vmem + (size_t)b0 * T * p.C2, (double *)c->part.ptr, p.C2, nb, T, 0, slab_len);
+            else if (tc)
+                k_gram_tc<false><<<dim3((unsigned)nb, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(
+                    vmem + (size_t)b0 * T * p.C2, (double *)c->part.ptr, p.C2, nb, T, 0, slab_len);
+            else
+                k_gram_tiled<<<dim3((unsigned)nb, (unsigned)nblocks, (unsigned)nslab), 256, 0, st>>>(
+                    vmem + (size_t)b0 * T * p.C2, (double *)c->part.ptr, p.C2, nb, T, 0, slab_len);
             const long long ne = nb * p.C2 * p.C2;
-            k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr,
+            k_gram_reduce<<<(unsigned)((ne + 31) / 32), 256, 0, st>>>((const double *)c->part.ptr,
                                                                        (double *)c->gram.ptr + (size_t)b0 * p.C2 * p.C2, p.C2, nb, (int)nslab);
             count_launch(2);
         }
@@ -387,7 +398,7 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
         gg.z = (unsigned)nslab;
         k_gram_slab<<<gg, 256, 0, st>>>(vmem, (double *)c->part.ptr, p.C2, B, T, 0, slab_len);
         const long long ne = B * p.C2 * p.C2;
-        k_gram_reduce<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, nslab);
+        k_gram_reduce<<<(unsigned)((ne + 31) / 32), 256, 0, st>>>((const double *)c->part.ptr, (double *)c->gram.ptr, p.C2, B, nslab);
         count_launch(2);
     } else {
         k_gram<<<gg, 256, 0, st>>>(vmem, (double *)c->gram.ptr, p.C2, T, 0);
@@ -409,8 +420,16 @@ static int run_power(micloc_snn *c, const float *vmem, long long B, long long T,
         cv = (double *)c->chunkbuf.ptr;
         ci = (int *)(cv + (size_t)B * nchunk);
     }
-    k_power_argmax<<<dim3((unsigned)B, (unsigned)nchunk), 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
-                                                                          1.0 / (double)T, nchunk, cv, ci);
+    const size_t smem_w = smem + ((size_t)p.C2 * 32 + (size_t)kPwSlices * 32) * sizeof(double);
+    if (p.C2 >= 32 && smem_w <= 200 * 1024 && !getenv("MICLOC_POWER_NARROW")) {
+        // wide arrays: a warp per slice of Gram rows x 32 DoAs (one thread per DoA leaves most of the CTA idle)
+        MICLOC_CUDA(cudaFuncSetAttribute(k_power_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        k_power_wide<<<dim3((unsigned)B, (unsigned)nchunk), 32 * kPwSlices, smem_w, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa,
+                                                                                          p.C2, p.G, 1.0 / (double)T, nchunk, cv, ci);
+    } else {
+        k_power_argmax<<<dim3((unsigned)B, (unsigned)nchunk), 256, smem, st>>>((const double *)c->gram.ptr, c->d_Wd, power, doa, p.C2, p.G,
+                                                                              1.0 / (double)T, nchunk, cv, ci);
+    }
     count_launch(1);
     if (nchunk > 1 && doa) {
         k_argmax_chunks<<<(unsigned)((B + 31) / 32), 32, 0, st>>>(cv, ci, doa, B, nchunk);

@@ -205,6 +205,9 @@ __device__ __forceinline__ void fir_role(const FusedSmem &sm, const ChainParams 
             }
             c0 += kTile; if (c0 >= g.ring_x) c0 -= g.ring_x;
         }
+        // (the zero-padded first tap block of tile k reads one sample into tile k+1, times a zero tap: the window reads of
+        //  every lane come before the stores below -- compute-sanitizer racecheck)
+        __syncwarp();
         if (filling) {
 #pragma unroll
             for (int m = 0; m < kRows; ++m)

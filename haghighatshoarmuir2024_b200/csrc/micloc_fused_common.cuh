@@ -38,7 +38,12 @@ __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long lon
 
 // The eight warps of one clip-pair group meet here once per pipeline step (the roles run different code);
 // every group of a CTA owns one named barrier.
-__device__ __forceinline__ void tile_barrier(int id, int nthreads = kThreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// (bar.sync is barrier.sync.aligned: the warp has to arrive converged -- compute-sanitizer synccheck found the RZCC warp
+//  still split by its candidate branches here -- hence the __syncwarp)
+__device__ __forceinline__ void tile_barrier(int id, int nthreads = kThreads) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // Called by every serial role at the top of pipeline step k, before its own work: the tensor-core kernel
 // (micloc_fused_tc.cu) moves the finished STHT tile out of tensor memory there; the FFMA kernel passes this no-op.

@@ -4,6 +4,7 @@
 // the Xylo front end, and the cross-check of the fused kernel.
 #pragma once
 #include "micloc_device.cuh"
+#include <cuda_fp16.h>
 
 namespace micloc {
 
@@ -353,16 +354,175 @@ k_gram_tiled(const float *__restrict__ vmem, double *__restrict__ part, int C2, 
         }
     }
 }
+// The same 128 x 128 block on the TENSOR CORES: the membrane tile (x 2^12) is split into fp16 hi + lo (22 significant
+// bits, as the fused kernel's Gram role does), staged [sample][channel] in shared memory, and both operands of
+// C += V^T V are read from it with ldmatrix.trans (A[m][k] = V[k][m], B[k][n] = V[k][n]: the same transposed 8 x 8
+// pieces).  Three mma.sync.m16n8k16 per tile and k step (hi.hi, hi.lo, lo.hi), float32 accumulators over the slab of
+// kGtFlush samples, float64 across slabs (k_gram_reduce).  8 warps, warp tile 64 x 32; the next 32 samples travel from
+// HBM to registers while the current ones are multiplied.
+constexpr int kGcK = 32;                 // samples per stage: two k steps of 16
+constexpr int kGcPitch = kGtTile + 8;    // halves per shared-memory row: 272 B, eight ldmatrix rows hit eight bank groups
+constexpr float kGcScale = 4096.f;       // |v| x 2^12 < 65504: the host checks the neuron kernel's absolute sum (< 15)
+__device__ __forceinline__ void ldsm_x4_trans(unsigned (&r)[4], const void *p) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma_gram_k16(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool DIAG_ONLY>      // every block is a diagonal block (C2 <= 128): one staged operand, half the prefetch registers
+static __global__ void __launch_bounds__(256, 2)
+k_gram_tc(const float *__restrict__ vmem, double *__restrict__ part, int C2, long long B, long long T, long long t_start,
+          long long slab_len) {
+    __shared__ __align__(16) __half S[DIAG_ONLY ? 1 : 2][2][kGcK][kGcPitch];   // [row block | column block][hi | lo][sample][channel]
+    const long long b = blockIdx.x;
+    const int nblk = (C2 + kGtTile - 1) / kGtTile;
+    int y = blockIdx.y, bi = 0;
+    while (y >= nblk - bi) { y -= nblk - bi; ++bi; }
+    const int bj = bi + y;
+    const bool diag = DIAG_ONLY || bi == bj;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    const long long t0 = t_start + (long long)blockIdx.z * slab_len, t1 = min(T, t0 + slab_len);
+    const float *v = vmem + b * T * C2;
+    const bool vec = (C2 & 3) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+    // staging: thread -> sample r = e / 32, channels 4 (e % 32) .. + 3, e = tid + 256 q
+    constexpr int kSides = DIAG_ONLY ? 1 : 2;
+    float4 pre[kSides][4];
+    auto fetch = [&](long long t) {
+#pragma unroll
+        for (int side = 0; side < kSides; ++side) {
+            if (side == 1 && diag) break;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = tid + 256 * q;
+                const long long tt = t + (e >> 5);
+                const int col = (side ? bj : bi) * kGtTile + 4 * (e & 31);
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tt < t1) {
+                    const float *src = v + tt * C2 + col;
+                    if (vec && col + 3 < C2) val = __ldg(reinterpret_cast<const float4 *>(src));
+                    else {
+                        if (col < C2) val.x = src[0];
+                        if (col + 1 < C2) val.y = src[1];
+                        if (col + 2 < C2) val.z = src[2];
+                        if (col + 3 < C2) val.w = src[3];
+                    }
+                }
+                pre[side][q] = val;
+            }
+        }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int side = 0; side < kSides; ++side) {
+            if (side == 1 && diag) break;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = tid + 256 * q;
+                const float4 val = pre[side][q];
+                const float s0 = val.x * kGcScale, s1 = val.y * kGcScale, s2 = val.z * kGcScale, s3 = val.w * kGcScale;
+                const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const unsigned *>(&h01); hv.y = *reinterpret_cast<const unsigned *>(&h23);
+                lv.x = *reinterpret_cast<const unsigned *>(&l01); lv.y = *reinterpret_cast<const unsigned *>(&l23);
+                *reinterpret_cast<uint2 *>(&S[side][0][e >> 5][4 * (e & 31)]) = hv;
+                *reinterpret_cast<uint2 *>(&S[side][1][e >> 5][4 * (e & 31)]) = lv;
+            }
+        }
+    };
+    const int sb = diag ? 0 : 1;
+    // ldmatrix row of this lane: A pieces (samples +8 in matrices 2, 3; channels +8 in matrices 1, 3), B pieces
+    // (samples +8 in matrices 1, 3; channels +8 in matrices 2, 3: two column blocks of 8 per load)
+    const int a_row = (lane & 7) + 8 * (lane >> 4), a_col = wm * 64 + 8 * ((lane >> 3) & 1);
+    const int b_row = (lane & 7) + 8 * ((lane >> 3) & 1), b_col = wn * 32 + 8 * (lane >> 4);
+    fetch(t0);
+    for (long long t = t0; t < t1; t += kGcK) {
+        stash();
+        __syncthreads();
+        if (t + kGcK < t1) fetch(t + kGcK);
+#pragma unroll
+        for (int ks = 0; ks < kGcK / 16; ++ks) {
+            const int k0 = 16 * ks;
+            unsigned ah[4][4], bh[4][2], x[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) ldsm_x4_trans(ah[mb], &S[0][0][k0 + a_row][a_col + 16 * mb]);
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                ldsm_x4_trans(x, &S[sb][0][k0 + b_row][b_col + 16 * n2]);
+                bh[2 * n2][0] = x[0]; bh[2 * n2][1] = x[1]; bh[2 * n2 + 1][0] = x[2]; bh[2 * n2 + 1][1] = x[3];
+            }
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) mma_gram_k16(acc[mb][nb], ah[mb], bh[nb][0], bh[nb][1]);
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {                              // hi . lo
+                ldsm_x4_trans(x, &S[sb][1][k0 + b_row][b_col + 16 * n2]);
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) {
+                    mma_gram_k16(acc[mb][2 * n2], ah[mb], x[0], x[1]);
+                    mma_gram_k16(acc[mb][2 * n2 + 1], ah[mb], x[2], x[3]);
+                }
+            }
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) {                              // lo . hi
+                ldsm_x4_trans(x, &S[0][1][k0 + a_row][a_col + 16 * mb]);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) mma_gram_k16(acc[mb][nb], x, bh[nb][0], bh[nb][1]);
+            }
+        }
+        __syncthreads();
+    }
+    const int g = lane >> 2, tq = lane & 3;
+    const double unscale = 1.0 / ((double)kGcScale * (double)kGcScale);
+    double *out = part + ((long long)blockIdx.z * B + b) * C2 * C2;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gi = bi * kGtTile + wm * 64 + mb * 16 + g + 8 * (e >> 1);
+                const int gj = bj * kGtTile + wn * 32 + nb * 8 + 2 * tq + (e & 1);
+                if (gi < C2 && gj < C2 && gi <= gj) out[(long long)gi * C2 + gj] = (double)acc[mb][nb][e] * unscale;
+            }
+}
+// part[slab][b][i][j] (upper triangle) -> gram[b][i][j], both halves.  A block owns 32 consecutive elements; its eight
+// warps add up interleaved slab groups (coalesced 256-byte rows of `part`), the eight partial sums are added in group
+// order: a fixed order, so the result does not depend on scheduling.
 static __global__ void __launch_bounds__(256)
 k_gram_reduce(const double *__restrict__ part, double *__restrict__ gram, int C2, long long B, int nslab) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * C2 * C2) return;
+    __shared__ double red[8][32];
+    const int ex = threadIdx.x & 31, sg = threadIdx.x >> 5;
+    const long long e = (long long)blockIdx.x * 32 + ex;
+    const bool in = e < B * C2 * C2;
     const int j = (int)(e % C2), i = (int)((e / C2) % C2);
     const long long b = e / ((long long)C2 * C2);
-    const int lo = i < j ? i : j, hi = i < j ? j : i;
     double acc = 0.0;
-    for (int s = 0; s < nslab; ++s) acc += part[((long long)s * B + b) * C2 * C2 + lo * C2 + hi];
-    gram[e] = acc;
+    if (in && i <= j)
+        for (int s = sg; s < nslab; s += 8) acc += part[((long long)s * B + b) * C2 * C2 + i * C2 + j];
+    red[sg][ex] = acc;
+    __syncthreads();
+    if (sg == 0 && in && i <= j) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][ex];
+        gram[e] = t;
+        gram[(b * C2 + j) * C2 + i] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -409,6 +569,82 @@ k_power_argmax(const double *__restrict__ gram, const double *__restrict__ Wd, f
     if (threadIdx.x == 0) {
         if (nchunk == 1) { if (doa) doa[b] = red_i[0]; }
         else { chunk_v[b * nchunk + blockIdx.y] = red_v[0]; chunk_i[b * nchunk + blockIdx.y] = red_i[0]; }
+    }
+}
+// The same for WIDE arrays (config 5: C2 = 128, G = 512, a handful of clips): one thread per DoA would leave 32 threads
+// of a CTA running 16 384 dependent float64 FMAs each (0.5 ms).  Here a warp owns one slice of the Gram rows for 32
+// DoAs (lane = DoA, 4 rows in flight = 4 independent sums), the steering weights of the 32 DoAs sit in shared memory,
+// and the kPwSlices partial sums of a DoA are added in slice order (a fixed order: deterministic).
+constexpr int kPwSlices = 8;
+static __global__ void __launch_bounds__(32 * kPwSlices)
+k_power_wide(const double *__restrict__ gram, const double *__restrict__ Wd, float *__restrict__ power,
+             int32_t *__restrict__ doa, int C2, int G, double inv_T, int nchunk, double *__restrict__ chunk_v,
+             int *__restrict__ chunk_i) {
+    extern __shared__ __align__(16) double sm_d[];
+    double *Cs = sm_d;                       // [C2][C2]
+    double *Ws = Cs + (size_t)C2 * C2;       // [C2][32]
+    double *Ps = Ws + (size_t)C2 * 32;       // [kPwSlices][32]
+    const long long b = blockIdx.x;
+    const int gper = (((G + nchunk - 1) / nchunk) + 31) & ~31;
+    const int g_lo = blockIdx.y * gper, g_hi = min(G, g_lo + gper);
+    const int gl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int rows = (C2 + kPwSlices - 1) / kPwSlices;
+    const int i0 = min(C2, sl * rows), i1 = min(C2, i0 + rows);
+    for (int e = threadIdx.x; e < C2 * C2; e += blockDim.x) Cs[e] = gram[b * C2 * C2 + e];
+    double best = -1.0; int besti = 0x7fffffff;
+    for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
+        __syncthreads();                     // Cs loaded; the previous pass is done with Ws / Ps
+        for (int e = threadIdx.x; e < C2 * 32; e += blockDim.x) {
+            const int gg = g0 + (e & 31);
+            Ws[e] = gg < g_hi ? Wd[(long long)(e >> 5) * G + gg] : 0.0;
+        }
+        __syncthreads();
+        double part = 0.0;
+        int i = i0;
+        for (; i + 4 <= i1; i += 4) {
+            const double *c0 = Cs + (size_t)i * C2;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+            for (int j = 0; j < C2; ++j) {
+                const double w = Ws[j * 32 + gl];
+                r0 = fma(c0[j], w, r0);
+                r1 = fma(c0[C2 + j], w, r1);
+                r2 = fma(c0[2 * C2 + j], w, r2);
+                r3 = fma(c0[3 * C2 + j], w, r3);
+            }
+            part = fma(Ws[i * 32 + gl], r0, part);
+            part = fma(Ws[(i + 1) * 32 + gl], r1, part);
+            part = fma(Ws[(i + 2) * 32 + gl], r2, part);
+            part = fma(Ws[(i + 3) * 32 + gl], r3, part);
+        }
+        for (; i < i1; ++i) {
+            const double *c0 = Cs + (size_t)i * C2;
+            double r = 0.0;
+            for (int j = 0; j < C2; ++j) r = fma(c0[j], Ws[j * 32 + gl], r);
+            part = fma(Ws[i * 32 + gl], r, part);
+        }
+        Ps[sl * 32 + gl] = part;
+        __syncthreads();
+        if (sl == 0 && g0 + gl < g_hi) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < kPwSlices; ++s) acc += Ps[s * 32 + gl];
+            acc *= inv_T;
+            if (power) power[b * G + g0 + gl] = (float)acc;
+            if (acc > best) { best = acc; besti = g0 + gl; }     // ascending g per lane: first maximum kept
+        }
+    }
+    if (sl == 0) {
+        // first maximum over the 32 lanes: larger value wins, equal values keep the lower index
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, s);
+            const int oi = __shfl_down_sync(0xffffffffu, besti, s);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (gl == 0) {
+            if (nchunk == 1) { if (doa) doa[b] = besti; }
+            else { chunk_v[b * nchunk + blockIdx.y] = best; chunk_i[b * nchunk + blockIdx.y] = besti; }
+        }
     }
 }
 // first maximum over the DoA slices of k_power_argmax (ascending slices: a later slice only wins with a larger value)

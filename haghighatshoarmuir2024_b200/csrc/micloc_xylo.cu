@@ -410,8 +410,9 @@ __device__ __forceinline__ void xylo_step_lean(int &isyn, int &vmem, int &count,
 }
 
 // named barriers (ids 1..4): full[buf] = masks of a tile are ready, empty[buf] = they have been consumed
-__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// (aligned barriers: the warp arrives converged)
+__device__ __forceinline__ void bar_sync_named(int id, int count) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Warp-specialised: the LAST warp of the CTA is the producer, it stages the raw spike bytes of tile
 // k+1 and turns them into per-step event masks while the neuron warps run tile k (two mask buffers,
