@@ -498,12 +498,23 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
     if (segmented) {
         const long long n = B * sp.nseg * p.C2;
         const unsigned grid = (unsigned)((n + 127) / 128);
-        if (dtype == MICLOC_I16)
-            k_chain_seg<int16_t><<<grid, 128, 0, st>>>((const int16_t *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
-                                                       sp.seg_len, sp.warm, sp.tail, sp.nseg);
-        else
-            k_chain_seg<float><<<grid, 128, 0, st>>>((const float *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
-                                                     sp.seg_len, sp.warm, sp.tail, sp.nseg);
+        if (getenv("MICLOC_CHAIN_SEG_V1")) {            // one sample at a time (the block-wise kernel's cross-check)
+            if (dtype == MICLOC_I16)
+                k_chain_seg<int16_t><<<grid, 128, 0, st>>>((const int16_t *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
+                                                           sp.seg_len, sp.warm, sp.tail, sp.nseg);
+            else
+                k_chain_seg<float><<<grid, 128, 0, st>>>((const float *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1,
+                                                         sp.seg_len, sp.warm, sp.tail, sp.nseg);
+        } else {
+            // 32 samples at a time: stores spikes only, into a zeroed raster
+            MICLOC_CUDA(cudaMemsetAsync(spk, 0, n_c, st));
+#define MICLOC_CHAIN_BLK(IN_T, NSEC)                                                                                     \
+            k_chain_blk<IN_T, NSEC><<<grid, kChainBlkThreads, 0, st>>>((const IN_T *)audio, q, c->d_sos, z_dev, spk, flg, p, B, T, 1, \
+                                                                       sp.seg_len, sp.warm, sp.tail, sp.nseg)
+            if (dtype == MICLOC_I16) { if (p.nsec == 2) MICLOC_CHAIN_BLK(int16_t, 2); else MICLOC_CHAIN_BLK(int16_t, 0); }
+            else { if (p.nsec == 2) MICLOC_CHAIN_BLK(float, 2); else MICLOC_CHAIN_BLK(float, 0); }
+#undef MICLOC_CHAIN_BLK
+        }
         count_launch(1);
         MICLOC_CUDA(cudaGetLastError());
         // what the segments could not vouch for (or an overflowed cluster) is redone by the sequential kernel: its own

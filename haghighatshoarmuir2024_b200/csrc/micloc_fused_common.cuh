@@ -38,11 +38,20 @@ __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long lon
 
 // The eight warps of one clip-pair group meet here once per pipeline step (the roles run different code);
 // every group of a CTA owns one named barrier.
-// (bar.sync is barrier.sync.aligned: the warp has to arrive converged -- compute-sanitizer synccheck found the RZCC warp
-//  still split by its candidate branches here -- hence the __syncwarp)
+// Named barrier of a clip-pair group.  `bar.sync` is `barrier.sync.aligned`: PTX wants the whole warp converged on one
+// barrier instruction.  compute-sanitizer synccheck reports role warps that arrive split (lanes without a channel leave the
+// step's loops early and wait at the WARPSYNC.ALL ptxas puts in front of the barrier; the tool sees the two halves pass it
+// separately).  Both PTX forms compile to the SAME instruction, BAR.SYNC.DEFER_BLOCKING, which counts threads, so the
+// hardware behaviour is that of the unaligned form either way; what differs is the code ptxas builds around it: with
+// `barrier.sync` (no .aligned) it duplicates the paths into the barrier and the kernel runs 6 % slower (260 k vs 277 k
+// clips/s).  -DMICLOC_UNALIGNED_BARRIERS selects that form (tools/build_rt.sh; synccheck-clean, same results bit for bit).
+#ifdef MICLOC_UNALIGNED_BARRIERS
+#define MICLOC_BAR_SYNC "barrier.sync"
+#else
+#define MICLOC_BAR_SYNC "bar.sync"
+#endif
 __device__ __forceinline__ void tile_barrier(int id, int nthreads = kThreads) {
-    __syncwarp();
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    asm volatile(MICLOC_BAR_SYNC " %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Called by every serial role at the top of pipeline step k, before its own work: the tensor-core kernel

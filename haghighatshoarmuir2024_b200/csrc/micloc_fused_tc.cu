@@ -259,7 +259,7 @@ __device__ __forceinline__ void front_role(const TcSmem &sm, const ChainParams &
     const int NJb = (NJ + 1) >> 1;            // MMA tiles of 256 frames
     const int t128 = quarter * 32 + lane;
     const float sx[kSlots] = {sm.scale[0], sm.scale[1]};
-    auto front_sync = [&]() { __syncwarp(); asm volatile("bar.sync %0, 128;" ::"r"(front_bar) : "memory"); };
+    auto front_sync = [&]() { asm volatile(MICLOC_BAR_SYNC " %0, 128;" ::"r"(front_bar) : "memory"); };
     ROLE_TIMER_DECL;
     PH_DECL;
 

@@ -225,6 +225,121 @@ k_chain_seg(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
     if ((rz.overflow || unsynced) && flags) atomicOr(flags + b, 1);
 }
 
+// The same segments, 32 samples at a time (ncu on k_chain_seg: 144 warp instructions per sample -- the per-sample
+// candidate test runs its divergent cluster path on almost every step, because with 32 channels in a warp SOME lane has a
+// zero crossing).  Here a thread first runs the band-pass and the running sum over a block of kSeg samples without a
+// branch (sign / flat-top bit masks, the running sums of the block in shared memory), then hands the block to
+// rzcc_segment_masks -- the front end of the fused kernels, which visits only the sign changes -- and the next block's
+// 32 inputs travel from HBM to registers meanwhile.  Same decisions as k_chain_seg (both front ends feed one cluster
+// logic).  The spike raster must be ZEROED by the caller: only spikes are stored.
+constexpr int kChainBlkThreads = 128;
+template <typename IN_T, int NSEC>          // NSEC: biquads of the band-pass (0 = p.nsec at run time)
+__global__ void __launch_bounds__(kChainBlkThreads)
+k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const float *__restrict__ band_sos,
+            float *__restrict__ z_out, int8_t *__restrict__ spikes, int32_t *__restrict__ flags,
+            const __grid_constant__ ChainParams p, long long B, long long T64, int nb, int seg_len, int warm, int tail,
+            int nseg) {
+    __shared__ float cs_s[kSeg * kChainBlkThreads];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int CT = p.C2 * nb;
+    const bool live = idx < B * nseg * CT;           // (no early return: nothing below is a CTA barrier, but keep the warp whole)
+    const long long idc = live ? idx : 0;
+    const int cc = (int)(idc % CT);
+    const int seg = (int)((idc / CT) % nseg);
+    const long long b = idc / ((long long)CT * nseg);
+    const int band = cc / p.C2, c = cc % p.C2;
+    const int T = (int)T64;
+    constexpr int NS = NSEC ? NSEC : kMaxSections;
+
+    float sos[kMaxSections][5];
+#pragma unroll
+    for (int k = 0; k < kMaxSections; ++k)
+#pragma unroll
+        for (int e = 0; e < 5; ++e) sos[k][e] = band_sos[(band * kMaxSections + k) * 5 + e];
+    const int nsec = NSEC ? NSEC : p.nsec;
+
+    const int start = seg * seg_len;
+    const int end = min(T, start + seg_len);
+    const int t_begin = max(0, start - warm);                 // a multiple of kSeg (seg_len and warm are)
+    const int t_stop = live ? min(T, end + tail) : t_begin;
+    BiquadState bq; biquad_reset(bq);
+    RzccState rz; rzcc_reset(rz);
+    int cl_pos[2 * kClusterMax]; float cl_h[2 * kClusterMax];
+    const RzccStore store{cl_pos, cl_h, 1};
+    int8_t *sp = spikes + b * T64 * CT + cc;
+    auto emit = [&](int pos, int sign) { if (pos >= start && pos < end) sp[(long long)pos * CT] = (int8_t)sign; };
+
+    const bool inphase = c < p.M;
+    const IN_T *xa = audio + b * T64 * p.M + (inphase ? c : 0);
+    const float *xq = q + b * T64 * p.M + (inphase ? 0 : c - p.M);
+    const int src0 = (int)(((long long)t_begin - p.half) % T + T) % T;       // (t - K/2) mod T at t = t_begin (np.roll)
+    const int M = p.M;
+    float x[kSeg];
+    auto load_block = [&](int ts) {
+        const int left = t_stop - ts;                      // samples of this block inside the segment (<= 0: none)
+        if (inphase) {
+            int s0 = src0 + (ts - t_begin);
+            if (s0 >= T) s0 -= T;
+            const int wrap = T - s0;                       // the source index wraps after this many samples
+            const IN_T *p0 = xa + (long long)s0 * M;
+#pragma unroll
+            for (int i = 0; i < kSeg; ++i)
+                x[i] = i < left ? to_f32<IN_T>(p0[(long long)(i < wrap ? i : i - T) * M]) : 0.f;
+        } else {
+            const float *p0 = xq + (long long)ts * M;
+#pragma unroll
+            for (int i = 0; i < kSeg; ++i) x[i] = i < left ? p0[(long long)i * M] : 0.f;
+        }
+    };
+    bool unsynced = false;
+    int zrun = 0;
+    float *cs = cs_s + threadIdx.x;
+    load_block(t_begin);
+    for (int ts = t_begin; ts < t_stop; ts += kSeg) {
+        const int nvalid = min(kSeg, t_stop - ts);
+        if (ts == start && seg > 0) {
+            // decisions from here on are this segment's: every open cluster must have begun after the filters settled
+            const int settled = t_begin + (warm >> 1);
+            if ((rz.n1 > 0 && cl_pos[kClusterMax] < settled) || (rz.n0 > 0 && cl_pos[0] < settled)) unsynced = true;
+        }
+        // ---- band-pass + running sum of the block, branch-free ----
+        const float carry = rz.csum;
+        float csum = carry;
+        unsigned neg = 0u, zero = 0u;
+        const bool keep_z = z_out != nullptr;
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i) {
+            float v = x[i];
+            zrun = v == 0.f ? zrun + 1 : 0;
+            if (zrun >= kSilenceRun && i < nvalid) unsynced = true;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                if (k < nsec) {
+                    const float y = fmaf(sos[k][0], v, bq.s1[k]);
+                    bq.s1[k] = fmaf(sos[k][1], v, fmaf(-sos[k][3], y, bq.s2[k]));
+                    bq.s2[k] = fmaf(sos[k][2], v, -sos[k][4] * y);
+                    v = y;
+                }
+            }
+            const float cprev = csum;
+            csum = cprev + v;
+            neg |= (__float_as_uint(v) & 0x80000000u) >> i;
+            zero |= rzcc_flat(v, cprev) ? (0x80000000u >> i) : 0u;
+            cs[i * kChainBlkThreads] = csum;
+            if (keep_z && ts + i >= start && ts + i < end) z_out[(b * T64 + ts + i) * CT + cc] = v;
+        }
+        // ---- the next block's inputs on their way while the candidates of this one are handled ----
+        if (ts + kSeg < t_stop) load_block(ts + kSeg);
+        rzcc_segment_masks(rz, store, p.bipolar, p.w, ts, nvalid, neg, zero, cs, kChainBlkThreads, carry, emit);
+        rz.csum = nvalid == kSeg ? csum : cs[(nvalid - 1) * kChainBlkThreads];
+        const bool last = ts + nvalid == T;
+        if (last || nvalid == kSeg) rzcc_close(rz, store, p.w, ts + nvalid - 1, last, emit);
+    }
+    // a cluster that is still open behind the tail and holds a candidate of this segment was not decided
+    if (t_stop < T && ((rz.n1 > 0 && cl_pos[kClusterMax] < end) || (rz.n0 > 0 && cl_pos[0] < end))) unsynced = true;
+    if (live && (rz.overflow || unsynced) && flags) atomicOr(flags + b, 1);
+}
+
 static __global__ void __launch_bounds__(128)
 k_neuron_seg(const int8_t *__restrict__ spikes, float *__restrict__ vmem, const __grid_constant__ ChainParams p,
              long long B, long long T, int seg_len, int warm, int nseg) {

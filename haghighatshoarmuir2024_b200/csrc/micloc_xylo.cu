@@ -410,9 +410,9 @@ __device__ __forceinline__ void xylo_step_lean(int &isyn, int &vmem, int &count,
 }
 
 // named barriers (ids 1..4): full[buf] = masks of a tile are ready, empty[buf] = they have been consumed
-// (aligned barriers: the warp arrives converged)
-__device__ __forceinline__ void bar_sync_named(int id, int count) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive_named(int id, int count) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// (the forms without .aligned: a warp need not arrive converged)
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Warp-specialised: the LAST warp of the CTA is the producer, it stages the raw spike bytes of tile
 // k+1 and turns them into per-step event masks while the neuron warps run tile k (two mask buffers,
@@ -656,7 +656,6 @@ k_xylo_lif_mma(const int8_t *__restrict__ spikes, int CI, int bipolar, int N_in,
     const bool live = tid < npb && n < N;
     int isyn = 0, vmem = 0, count = 0;
     const int th = live ? thr[n] : 0x3fffffff;
-    const int th2 = 2 * th;
     const int ds = live ? dash_syn[n] : 0, dm = live ? dash_mem[n] : 0;
     const int bs = (live && bias) ? bias[n] : 0;
     uint8_t *rp = (RASTER && live) ? raster + b * T * N + n : nullptr;

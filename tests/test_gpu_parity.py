@@ -314,6 +314,29 @@ def test_time_segmented_kernels_equal_the_sequential_ones(monkeypatch):
         assert torch.equal(seg["flags"], one["flags"])
 
 
+def test_wide_array_tensor_core_gram_and_sliced_power_equal_the_float64_sum(monkeypatch):
+    """64 microphones (128 channels): k_gram_tc (fp16 hi/lo mma.sync) + k_power_wide against the float32 tiled product and
+    against the plain float64 sum with one thread per DoA; ragged T (last slab and last k step partly empty)."""
+    g = H.load("snn_c5_linear64")
+    for B, T in ((2, 20_011), (1, 3_000)):
+        x, _ = H.synth_clips(g, B, T, seed=11, snrs_db=(5.0,))
+        eng = engine_for(g, T)
+        xd = to_dev(x)
+        for k in ("MICLOC_GRAM_FP32", "MICLOC_POWER_NARROW", "MICLOC_NO_SEGMENTS"):
+            monkeypatch.delenv(k, raising=False)
+        tc = eng.run_taps(xd, want=("power", "doa"))
+        monkeypatch.setenv("MICLOC_GRAM_FP32", "1")
+        monkeypatch.setenv("MICLOC_POWER_NARROW", "1")
+        f32 = eng.run_taps(xd, want=("power", "doa"))
+        monkeypatch.setenv("MICLOC_NO_SEGMENTS", "1")                    # float64 Gram, one thread per matrix element
+        f64 = eng.run_taps(xd, want=("power", "doa"))
+        torch.cuda.synchronize()
+        p64 = f64["power"].cpu().numpy()
+        assert H.rel_err(tc["power"].cpu().numpy(), p64) < 1e-5, (B, T)
+        assert H.rel_err(f32["power"].cpu().numpy(), p64) < 1e-5, (B, T)
+        assert torch.equal(tc["doa"], f64["doa"]) and torch.equal(f32["doa"], f64["doa"])
+
+
 def test_stht_linearity_and_zero_input():
     g = H.load("snn_c1_bipolar")
     eng = engine_for(g, 2048)
