@@ -139,6 +139,7 @@ int micloc::setup_stht(ChainParams &p, const double *h, int K, float **d_taps) {
     p.K = K; p.half = K / 2;
     p.tap_stride = stride; p.tap_first = first; p.n_taps = npad;
     p.span = first + stride * (npad - 1);
+    p.tap_max = (float)mx;
     MICLOC_CUDA(cudaMalloc(d_taps, npad * sizeof(float)));
     MICLOC_CUDA(cudaMemcpy(*d_taps, taps.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
     return MICLOC_OK;
@@ -303,6 +304,18 @@ extern "C" int micloc_snn_last_kernel_ms(micloc_snn *c, float *ms, int32_t *n_ke
 template <typename IN_T>
 static int launch_stht(const ChainParams &p, const float *d_taps, const IN_T *audio, float *q,
                        long long B, long long T, cudaStream_t st) {
+    if (p.tap_stride == 2 && p.M > 8 && p.tap_max * kStTapScale < 60000.f && stht_tc_smem(p.n_taps) <= 112 * 1024 &&
+        T < (1ll << 30) && !getenv("MICLOC_STHT_FP32")) {
+        // wide arrays: polyphase Toeplitz product on the tensor cores
+        const int ntiles_tc = (int)((T + 32 * kStMB - 1) / (32 * kStMB));
+        const size_t smem_tc = stht_tc_smem(p.n_taps);
+        MICLOC_CUDA(cudaFuncSetAttribute(k_stht_tc<IN_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        k_stht_tc<IN_T><<<dim3((unsigned)(B * ntiles_tc), (unsigned)((p.M + kStMics - 1) / kStMics)), kStThreads, smem_tc, st>>>(
+            audio, q, d_taps, p, T, ntiles_tc);
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+        return MICLOC_OK;
+    }
     const int TT = 512;
     const int MG = p.M < 8 ? p.M : 8;
     const int ntiles = (int)((T + TT - 1) / TT);

@@ -27,6 +27,7 @@ struct ChainParams {
     int tap_first;    // index k0 of the first kept tap
     int n_taps;       // kept taps, padded with zeros to a multiple of kFirJB
     int span;         // largest look-back = tap_first + tap_stride*(n_taps-1)
+    float tap_max;    // largest |tap| (the tensor-core STHT keeps taps x 2^14 in fp16)
     int nsec;         // biquad sections
     float sos[kMaxSections][5];  // b0 b1 b2 a1 a2
     int w;            // RZCC distance (>=1)

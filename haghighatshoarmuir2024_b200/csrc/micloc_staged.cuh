@@ -615,6 +615,232 @@ k_gram_tc(const float *__restrict__ vmem, double *__restrict__ part, int C2, lon
                 if (gi < C2 && gj < C2 && gi <= gj) out[(long long)gi * C2 + gj] = (double)acc[mb][nb][e] * unscale;
             }
 }
+// ---------------------------------------------------------------------------
+// S1 on the TENSOR CORES, for wide arrays (M > 8: the fused kernels do not apply and k_stht's FP32 FIR is 27-50 % of a
+// config-5 clip).  Polyphase: the Hilbert kernel keeps every other tap, so the outputs of one time parity are a DENSE
+// n_taps-tap FIR of the input samples of one parity:  Q[2u + pi] = sum_j g[j] xs[u - j - c],  xs[v] = x[2v + rho].
+// Per CTA: U = 16 MB outputs of each parity x 32 microphones.  D[a][n] = sum_e A[a][e] B[e][n] with B[e][n] = xs[vb + e]
+// of microphone n (the staged window, fp16 hi + lo of x * 2^k, k from the window's largest magnitude; int16 input is
+// exact) and A[a][e] = g[a - e + L] the Toeplitz matrix of the taps (x 2^14, fp16 hi + lo).  A is never stored: the
+// mma.sync fragment of the 16 x 16 block (mb, ks) depends on mb - ks only, so ND = n_taps/16 + 1 fragments per split
+// piece sit in shared memory (one LDS.128 per fragment and lane) and a warp that owns two consecutive row blocks gets
+// the second block's fragment by keeping the first one's for one more k step.  B fragments come from the [sample][mic]
+// tile by ldmatrix.trans (16-byte chunks XOR-swizzled by the row: stores and matrix loads both conflict-free).  Three
+// products per tile (hi.hi, hi.lo, lo.hi), float32 accumulation: ~1e-6 relative against float64 (bar 1e-4).
+// ---------------------------------------------------------------------------
+constexpr int kStMB = 8;                    // row blocks of 16 outputs per parity and CTA (U = 128): two per warp
+constexpr int kStThreads = 32 * kStMB;      // 2 parities x kStMB/2 pairs = kStMB warps
+constexpr int kStMics = 32;                 // microphones per CTA
+constexpr float kStTapScale = 16384.f;
+__host__ __device__ inline int stht_tc_nd(int n_taps) { return (n_taps + 14) / 16 + 1; }
+__host__ __device__ inline int stht_tc_window(int n_taps) { return 16 * (kStMB + stht_tc_nd(n_taps) - 1); }
+__host__ __device__ inline size_t stht_tc_smem(int n_taps) {
+    return (size_t)2 * 2 * stht_tc_window(n_taps) * 64 + (size_t)stht_tc_nd(n_taps) * 2 * 512 + 16;
+}
+template <typename IN_T>
+__global__ void __launch_bounds__(kStThreads, 2)
+k_stht_tc(const IN_T *__restrict__ audio, float *__restrict__ q, const float *__restrict__ taps,
+          const __grid_constant__ ChainParams p, long long T64, int ntiles) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int ND = stht_tc_nd(p.n_taps), W = stht_tc_window(p.n_taps), L = 16 * (ND - 1);
+    unsigned char *Xs = st_smem;                                            // [rho][hi | lo][W][64 B]
+    uint4 *Fs = reinterpret_cast<uint4 *>(st_smem + (size_t)4 * W * 64);      // [ND][hi | lo][32 lanes]
+    unsigned int *amax_s = reinterpret_cast<unsigned int *>(st_smem + (size_t)4 * W * 64 + (size_t)ND * 1024);
+    const int T = (int)T64, M = p.M;
+    const long long b = blockIdx.x / ntiles;
+    const int u0 = (int)(blockIdx.x % ntiles) * (16 * kStMB);
+    const int m0 = blockIdx.y * kStMics;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const IN_T *clip = audio + b * T64 * M;
+    // input parity rho serves output parity pi = (rho + tap_first) & 1; first staged stream sample vb = u0 - c - L
+    const int tf = p.tap_first;
+    auto vbase = [&](int rho) { const int pi = (rho + tf) & 1; return u0 - ((tf + rho - pi) >> 1) - L; };
+
+    if (tid == 0) *amax_s = 0u;
+    // ---- Toeplitz fragments of the taps ----
+    for (int e = tid; e < ND * 32; e += kStThreads) {
+        const int d = e >> 5, ln = e & 31, g = ln >> 2, tq = ln & 3;
+        unsigned hv[4], lv[4];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const int r = g + 8 * (qd & 1), c0 = 2 * tq + 8 * (qd >> 1);
+            unsigned short hh[2], ll[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 16 * d + r - (c0 + u);
+                const float gs = (j >= 0 && j < p.n_taps) ? taps[j] * kStTapScale : 0.f;
+                const __half hi = __float2half_rn(gs);
+                hh[u] = __half_as_ushort(hi);
+                ll[u] = __half_as_ushort(__float2half_rn(gs - __half2float(hi)));
+            }
+            hv[qd] = (unsigned)hh[0] | ((unsigned)hh[1] << 16);
+            lv[qd] = (unsigned)ll[0] | ((unsigned)ll[1] << 16);
+        }
+        Fs[(d * 2 + 0) * 32 + ln] = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+        Fs[(d * 2 + 1) * 32 + ln] = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+    }
+    __syncthreads();
+    // ---- window: four microphones of one sample row per thread (one 16-byte load); all of a thread's loads are in
+    //      flight at once and stay in registers across the scan for the largest magnitude (float32 input) ----
+    const int nvec = 2 * W * (kStMics / 4);
+    const bool vec_ok = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(clip) & 15) == 0;
+    auto load4 = [&](int idx) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < nvec) {
+            const int row = idx >> 3, c4 = idx & 7;
+            const int rho = row >= W ? 1 : 0, e = row - rho * W;
+            const long long i = 2ll * (vbase(rho) + e) + rho;
+            const int m = m0 + 4 * c4;
+            if (i >= 0 && i < T && m < M) {
+                const IN_T *src = clip + i * M + m;
+                if (vec_ok) {                                   // (M % 4 == 0: the four microphones exist)
+                    if (sizeof(IN_T) == 4) v = __ldg(reinterpret_cast<const float4 *>(src));
+                    else {
+                        const short4 s4 = __ldg(reinterpret_cast<const short4 *>(src));
+                        v = make_float4((float)s4.x, (float)s4.y, (float)s4.z, (float)s4.w);
+                    }
+                } else {
+                    v.x = to_f32<IN_T>(src[0]);
+                    if (m + 1 < M) v.y = to_f32<IN_T>(src[1]);
+                    if (m + 2 < M) v.z = to_f32<IN_T>(src[2]);
+                    if (m + 3 < M) v.w = to_f32<IN_T>(src[3]);
+                }
+            }
+        }
+        return v;
+    };
+    auto amax4 = [](float mx, const float4 &v) {
+        return fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    };
+    float scale = 1.f, unscale = 1.f / kStTapScale;
+    auto set_scale = [&]() {
+        if (sizeof(IN_T) == 4) {
+            const unsigned am = *amax_s;
+            int ex = (int)((am >> 23) & 0xffu) - 127;              // floor(log2(amax)); x * 2^(14 - ex) < 2^15
+            if (am == 0u) ex = 14;
+            ex = ex < -90 ? -90 : (ex > 100 ? 100 : ex);
+            scale = __uint_as_float((unsigned)(127 + 14 - ex) << 23);
+            unscale = __uint_as_float((unsigned)(127 + ex - 28) << 23);
+        }
+    };
+    auto publish_amax = [&](float mx) {
+        unsigned mb = __float_as_uint(mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned ot = __shfl_xor_sync(0xffffffffu, mb, o); mb = ot > mb ? ot : mb; }
+        if (lane == 0) atomicMax(amax_s, mb);
+    };
+    auto stash4 = [&](int idx, const float4 &v) {
+        if (idx >= nvec) return;
+        const int row = idx >> 3, c4 = idx & 7;
+        const int rho = row >= W ? 1 : 0, e = row - rho * W;
+        const float s0 = v.x * scale, s1 = v.y * scale, s2 = v.z * scale, s3 = v.w * scale;
+        const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const unsigned *>(&h01); hv.y = *reinterpret_cast<const unsigned *>(&h23);
+        lv.x = *reinterpret_cast<const unsigned *>(&l01); lv.y = *reinterpret_cast<const unsigned *>(&l23);
+        unsigned char *rowp = Xs + ((size_t)(rho * 2) * W + e) * 64 + 16 * ((c4 >> 1) ^ ((e >> 1) & 3)) + 8 * (c4 & 1);
+        *reinterpret_cast<uint2 *>(rowp) = hv;
+        *reinterpret_cast<uint2 *>(rowp + (size_t)W * 64) = lv;
+    };
+    constexpr int kStHold = 24;                                  // 16-byte pieces a thread keeps: W <= 384 (n_taps <= 264)
+    if (nvec <= kStHold * kStThreads) {
+        float4 hold[kStHold];
+#pragma unroll
+        for (int k = 0; k < kStHold; ++k) hold[k] = load4(tid + kStThreads * k);
+        if (sizeof(IN_T) == 4) {
+            float mx = 0.f;
+#pragma unroll
+            for (int k = 0; k < kStHold; ++k) mx = amax4(mx, hold[k]);
+            publish_amax(mx);
+            __syncthreads();
+            set_scale();
+        }
+#pragma unroll
+        for (int k = 0; k < kStHold; ++k) stash4(tid + kStThreads * k, hold[k]);
+    } else {
+        // long kernels: two passes over the window (the second one hits L2)
+        if (sizeof(IN_T) == 4) {
+            float mx = 0.f;
+#pragma unroll 4
+            for (int idx = tid; idx < nvec; idx += kStThreads) mx = amax4(mx, load4(idx));
+            publish_amax(mx);
+            __syncthreads();
+            set_scale();
+        }
+#pragma unroll 4
+        for (int idx = tid; idx < nvec; idx += kStThreads) stash4(idx, load4(idx));
+    }
+    __syncthreads();
+
+    // ---- this warp: output parity pi, row blocks mb0 and mb0 + 1 ----
+    const int pi = warp / (kStMB / 2), mb0 = 2 * (warp % (kStMB / 2));
+    const int rho = (pi + tf) & 1;                       // (rho + tf) & 1 == pi
+    const unsigned char *Xh = Xs + (size_t)(rho * 2) * W * 64, *Xl = Xh + (size_t)W * 64;
+    const int mg = min(kStMics, M - m0), nblk = (mg + 7) >> 3;     // column blocks of 8 microphones in use
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    unsigned fa_h[4] = {0u, 0u, 0u, 0u}, fa_l[4] = {0u, 0u, 0u, 0u}, fb_h[4], fb_l[4];
+    const int b_row = (lane & 7) + 8 * ((lane >> 3) & 1), b_chunk = lane >> 4;
+    for (int ks = mb0; ks <= mb0 + ND; ++ks) {
+        const int dA = mb0 - ks + ND - 1;                // fragment of block mb0; block mb0 + 1 uses dA + 1 = last step's
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { fb_h[i] = fa_h[i]; fb_l[i] = fa_l[i]; }
+        const bool useA = dA >= 0, useB = ks > mb0;
+        if (useA) {
+            const uint4 h4 = Fs[(dA * 2 + 0) * 32 + lane], l4 = Fs[(dA * 2 + 1) * 32 + lane];
+            fa_h[0] = h4.x; fa_h[1] = h4.y; fa_h[2] = h4.z; fa_h[3] = h4.w;
+            fa_l[0] = l4.x; fa_l[1] = l4.y; fa_l[2] = l4.z; fa_l[3] = l4.w;
+        }
+        const int e = 16 * ks + b_row;
+        const int sw = (e >> 1) & 3;
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            if (2 * np >= nblk) break;
+            unsigned bh[4], bl[4];
+            const size_t off = (size_t)e * 64 + 16 * ((2 * np + b_chunk) ^ sw);
+            ldsm_x4_trans(bh, Xh + off);
+            ldsm_x4_trans(bl, Xl + off);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int nb = 2 * np + h;
+                if (useA) {
+                    mma_gram_k16(acc[0][nb], fa_h, bh[2 * h], bh[2 * h + 1]);
+                    mma_gram_k16(acc[0][nb], fa_h, bl[2 * h], bl[2 * h + 1]);
+                    mma_gram_k16(acc[0][nb], fa_l, bh[2 * h], bh[2 * h + 1]);
+                }
+                if (useB) {
+                    mma_gram_k16(acc[1][nb], fb_h, bh[2 * h], bh[2 * h + 1]);
+                    mma_gram_k16(acc[1][nb], fb_h, bl[2 * h], bl[2 * h + 1]);
+                    mma_gram_k16(acc[1][nb], fb_l, bh[2 * h], bh[2 * h + 1]);
+                }
+            }
+        }
+    }
+    // ---- out: row a of block mb -> time 2 (u0 + 16 mb + a) + pi, columns = microphones ----
+    const int g = lane >> 2, tq = lane & 3;
+    float *qc = q + b * T64 * M;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const long long t = 2ll * (u0 + 16 * (mb0 + i) + g + 8 * hr) + pi;
+                const int m = m0 + 8 * nb + 2 * tq;
+                if (t < T) {
+                    if (m < M) qc[t * M + m] = acc[i][nb][2 * hr] * unscale;
+                    if (m + 1 < M) qc[t * M + m + 1] = acc[i][nb][2 * hr + 1] * unscale;
+                }
+            }
+}
+
 // part[slab][b][i][j] (upper triangle) -> gram[b][i][j], both halves.  A block owns 32 consecutive elements; its eight
 // warps add up interleaved slab groups (coalesced 256-byte rows of `part`), the eight partial sums are added in group
 // order: a fixed order, so the result does not depend on scheduling.

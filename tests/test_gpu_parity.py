@@ -337,6 +337,34 @@ def test_wide_array_tensor_core_gram_and_sliced_power_equal_the_float64_sum(monk
         assert torch.equal(tc["doa"], f64["doa"]) and torch.equal(f32["doa"], f64["doa"])
 
 
+@pytest.mark.parametrize("name", ["snn_c5_linear64", "snn_linear16"])
+def test_wide_array_tensor_core_stht_equals_the_fp32_fir(name, monkeypatch):
+    """M > 8: k_stht_tc (polyphase Toeplitz product, fp16 hi/lo mma.sync) against the float32 FIR kernel and the
+    float64 oracle; float32 and int16 clips, ragged T (partial tiles, odd length), loud and quiet clips in one batch."""
+    g = H.load(name)
+    M = g["x"].shape[1]
+    for T, int16 in ((5_001, False), (777, False), (4_096, True)):
+        x, _ = H.synth_clips(g, 3, T, seed=T)
+        x[1] *= 1e-3                                                     # per-tile scaling: a quiet clip next to a loud one
+        x[2, : T // 2] = 0
+        if int16:
+            x = np.round(x / np.abs(x).max() * 30000).astype(np.int16)
+        eng = engine_for(g, max(T, 1024))
+        xd = to_dev(x)
+        monkeypatch.delenv("MICLOC_STHT_FP32", raising=False)
+        q_tc = eng.run_taps(xd, want=("q",))["q"].cpu().numpy()
+        monkeypatch.setenv("MICLOC_STHT_FP32", "1")
+        q_32 = eng.run_taps(xd, want=("q",))["q"].cpu().numpy()
+        monkeypatch.delenv("MICLOC_STHT_FP32", raising=False)
+        h = np.asarray(g["kernel"], np.float64)
+        for bi in range(3):
+            ref = np.stack([np.convolve(x[bi, :, m].astype(np.float64), h)[:T] for m in (0, M // 2, M - 1)], axis=1)
+            got = q_tc[bi][:, [0, M // 2, M - 1]]
+            assert H.rel_err(got, ref) < 1e-5, (T, int16, bi)
+            assert H.rel_err(q_32[bi][:, [0, M // 2, M - 1]], ref) < 1e-5
+        assert np.isfinite(q_tc).all()
+
+
 def test_stht_linearity_and_zero_input():
     g = H.load("snn_c1_bipolar")
     eng = engine_for(g, 2048)
