@@ -234,7 +234,7 @@ k_chain_seg(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
 // logic).  The spike raster must be ZEROED by the caller: only spikes are stored.
 constexpr int kChainBlkThreads = 128;
 template <typename IN_T, int NSEC>          // NSEC: biquads of the band-pass (0 = p.nsec at run time)
-__global__ void __launch_bounds__(kChainBlkThreads)
+__global__ void __launch_bounds__(kChainBlkThreads, 3)
 k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const float *__restrict__ band_sos,
             float *__restrict__ z_out, int8_t *__restrict__ spikes, int32_t *__restrict__ flags,
             const __grid_constant__ ChainParams p, long long B, long long T64, int nb, int seg_len, int warm, int tail,
@@ -281,18 +281,27 @@ k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
             int s0 = src0 + (ts - t_begin);
             if (s0 >= T) s0 -= T;
             const int wrap = T - s0;                       // the source index wraps after this many samples
-            const IN_T *p0 = xa + (long long)s0 * M;
+            const IN_T *pp = xa + (long long)s0 * M;
+            if (left >= kSeg && wrap >= kSeg) {            // (almost always: one pointer, one stride)
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i)
-                x[i] = i < left ? to_f32<IN_T>(p0[(long long)(i < wrap ? i : i - T) * M]) : 0.f;
+                for (int i = 0; i < kSeg; ++i) { x[i] = to_f32<IN_T>(*pp); pp += M; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kSeg; ++i)
+                    x[i] = i < left ? to_f32<IN_T>(pp[(long long)(i < wrap ? i : i - T) * M]) : 0.f;
+            }
         } else {
-            const float *p0 = xq + (long long)ts * M;
+            const float *pp = xq + (long long)ts * M;
+            if (left >= kSeg) {
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) x[i] = i < left ? p0[(long long)i * M] : 0.f;
+                for (int i = 0; i < kSeg; ++i) { x[i] = *pp; pp += M; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kSeg; ++i) x[i] = i < left ? pp[(long long)i * M] : 0.f;
+            }
         }
     };
     bool unsynced = false;
-    int zrun = 0;
     float *cs = cs_s + threadIdx.x;
     load_block(t_begin);
     for (int ts = t_begin; ts < t_stop; ts += kSeg) {
@@ -305,13 +314,13 @@ k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
         // ---- band-pass + running sum of the block, branch-free ----
         const float carry = rz.csum;
         float csum = carry;
-        unsigned neg = 0u, zero = 0u;
-        const bool keep_z = z_out != nullptr;
+        unsigned neg = 0u, zero = 0u, any = 0u;
+        const bool keep_z = z_out != nullptr && ts >= start && ts < end;     // (start is a multiple of kSeg)
+        float *zo = keep_z ? z_out + (b * T64 + ts) * CT + cc : nullptr;
 #pragma unroll
         for (int i = 0; i < kSeg; ++i) {
             float v = x[i];
-            zrun = v == 0.f ? zrun + 1 : 0;
-            if (zrun >= kSilenceRun && i < nvalid) unsynced = true;
+            any |= __float_as_uint(v);
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if (k < nsec) {
@@ -326,8 +335,10 @@ k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
             neg |= (__float_as_uint(v) & 0x80000000u) >> i;
             zero |= rzcc_flat(v, cprev) ? (0x80000000u >> i) : 0u;
             cs[i * kChainBlkThreads] = csum;
-            if (keep_z && ts + i >= start && ts + i < end) z_out[(b * T64 + ts + i) * CT + cc] = v;
+            if (keep_z && ts + i < end) zo[(long long)i * CT] = v;
         }
+        // digital silence: a run of kSilenceRun exactly-zero inputs (k_chain_seg's test) contains a whole block of zeros
+        if ((any << 1) == 0u && nvalid == kSeg) unsynced = true;
         // ---- the next block's inputs on their way while the candidates of this one are handled ----
         if (ts + kSeg < t_stop) load_block(ts + kSeg);
         rzcc_segment_masks(rz, store, p.bipolar, p.w, ts, nvalid, neg, zero, cs, kChainBlkThreads, carry, emit);
@@ -352,11 +363,38 @@ k_neuron_seg(const int8_t *__restrict__ spikes, float *__restrict__ vmem, const 
     float *vm = vmem + b * T * p.C2 + c;
     const long long start = (long long)seg * seg_len, end = min(T, start + seg_len);
     NeuronState n; neuron_reset(n);
-    for (long long t = max(0ll, start - warm); t < end; ++t) {
-        const float s = (float)sp[t * p.C2];
-        const float sd = t >= p.nL ? (float)sp[(t - p.nL) * p.C2] : 0.f;
-        const float v = neuron_step(p, n, s, sd);
-        if (t >= start) vm[t * p.C2] = v;
+    // (few threads per SM: a step that waits for its own two spike bytes runs at one memory latency per sample -- the
+    //  bytes of the next kNeuBlk steps are requested before the current kNeuBlk steps are computed)
+    constexpr int kNeuBlk = 8;
+    const int C2 = p.C2, nL = p.nL;
+    const int t_first = (int)max(0ll, start - warm), t_end = (int)end;
+    const int last = t_end - 1;
+    int nx_s[kNeuBlk], nx_d[kNeuBlk];
+    auto request = [&](int t0) {
+        // clamped addresses (always inside the clip); what lies outside [0, end) is masked when it is used
+        const int8_t *ps = sp + (long long)min(t0, last) * C2;
+        const int room = last - min(t0, last);
+#pragma unroll
+        for (int u = 0; u < kNeuBlk; ++u) nx_s[u] = ps[(long long)min(u, room) * C2];
+        const int td = t0 - nL;
+#pragma unroll
+        for (int u = 0; u < kNeuBlk; ++u) nx_d[u] = sp[(long long)min(max(td + u, 0), last) * C2];
+    };
+    request(t_first);
+    for (int t0 = t_first; t0 < t_end; t0 += kNeuBlk) {
+        float cs[kNeuBlk], cd[kNeuBlk];
+#pragma unroll
+        for (int u = 0; u < kNeuBlk; ++u) {
+            cs[u] = t0 + u < t_end ? (float)nx_s[u] : 0.f;
+            cd[u] = (t0 + u < t_end && t0 + u >= nL) ? (float)nx_d[u] : 0.f;
+        }
+        request(t0 + kNeuBlk);
+#pragma unroll
+        for (int u = 0; u < kNeuBlk; ++u) {
+            const int t = t0 + u;
+            const float v = neuron_step(p, n, cs[u], cd[u]);
+            if (t >= start && t < t_end) vm[(long long)t * C2] = v;
+        }
     }
 }
 
