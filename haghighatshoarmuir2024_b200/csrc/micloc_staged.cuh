@@ -365,7 +365,7 @@ k_neuron_seg(const int8_t *__restrict__ spikes, float *__restrict__ vmem, const 
     NeuronState n; neuron_reset(n);
     // (few threads per SM: a step that waits for its own two spike bytes runs at one memory latency per sample -- the
     //  bytes of the next kNeuBlk steps are requested before the current kNeuBlk steps are computed)
-    constexpr int kNeuBlk = 8;
+    constexpr int kNeuBlk = 16;
     const int C2 = p.C2, nL = p.nL;
     const int t_first = (int)max(0ll, start - warm), t_end = (int)end;
     const int last = t_end - 1;
