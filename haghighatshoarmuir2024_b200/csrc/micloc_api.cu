@@ -345,6 +345,23 @@ int micloc::launch_chain_any(const ChainParams &p, const void *audio, int dtype,
                              long long B, long long T, cudaStream_t st) {
     const long long n = B * p.C2 * nb;
     const unsigned grid = (unsigned)((n + 127) / 128);
+    if (p.M > 8 && T < (1ll << 30) && !getenv("MICLOC_CHAIN_SEG_V1")) {
+        // wide arrays: the block-wise kernel with one segment per chain (32 channels of a warp make the per-sample
+        // kernel run its divergent candidate path on every step); it stores spikes only, into a zeroed raster.
+        // (Arrays of up to 8 microphones keep k_chain: the FFMA fused kernel is tested bit for bit against it.)
+        MICLOC_CUDA(cudaMemsetAsync(spikes, 0, (size_t)n * T, st));
+        const int seg_len = (int)((T + kSeg - 1) & ~(long long)(kSeg - 1));
+        const unsigned gb = (unsigned)((n + kChainBlkThreads - 1) / kChainBlkThreads);
+#define MICLOC_CHAIN_BLK1(IN_T, NSEC)                                                                                 \
+        k_chain_blk<IN_T, NSEC><<<gb, kChainBlkThreads, 0, st>>>((const IN_T *)audio, q, band_sos, z, spikes, flags, p, B, T, nb, \
+                                                                 seg_len, 0, 0, 1)
+        if (dtype == MICLOC_I16) { if (p.nsec == 2) MICLOC_CHAIN_BLK1(int16_t, 2); else MICLOC_CHAIN_BLK1(int16_t, 0); }
+        else { if (p.nsec == 2) MICLOC_CHAIN_BLK1(float, 2); else MICLOC_CHAIN_BLK1(float, 0); }
+#undef MICLOC_CHAIN_BLK1
+        count_launch(1);
+        MICLOC_CUDA(cudaGetLastError());
+        return MICLOC_OK;
+    }
     if (dtype == MICLOC_I16)
         k_chain<int16_t><<<grid, 128, 0, st>>>((const int16_t *)audio, q, band_sos, z, spikes, flags, p, B, T, nb);
     else

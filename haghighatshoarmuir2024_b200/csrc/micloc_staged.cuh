@@ -338,7 +338,7 @@ k_chain_blk(const IN_T *__restrict__ audio, const float *__restrict__ q, const f
             if (keep_z && ts + i < end) zo[(long long)i * CT] = v;
         }
         // digital silence: a run of kSilenceRun exactly-zero inputs (k_chain_seg's test) contains a whole block of zeros
-        if ((any << 1) == 0u && nvalid == kSeg) unsynced = true;
+        if ((any << 1) == 0u && nvalid == kSeg && nseg > 1) unsynced = true;
         // ---- the next block's inputs on their way while the candidates of this one are handled ----
         if (ts + kSeg < t_stop) load_block(ts + kSeg);
         rzcc_segment_masks(rz, store, p.bipolar, p.w, ts, nvalid, neg, zero, cs, kChainBlkThreads, carry, emit);
