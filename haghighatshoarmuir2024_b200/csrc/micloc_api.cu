@@ -571,7 +571,7 @@ extern "C" int micloc_snn_run_taps(micloc_snn *c, const void *audio, int dtype, 
             k_neuron_seg<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T, sp.seg_len_neuron, sp.nwarm, sp.nseg_neuron);
         } else {
             const long long n = B * p.C2;
-            k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T);
+            k_neuron_seg<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(spk, vm, p, B, T, (int)T, 0, 1);   // one segment: the sequential recurrence, spike bytes requested ahead
         }
         count_launch(1);
         MICLOC_CUDA(cudaGetLastError());
@@ -611,7 +611,7 @@ extern "C" int micloc_snn_gram(micloc_snn *c, const void *audio, int dtype, int6
     MICLOC_TRY(heal_overflow(c, audio, dtype, (const float *)c->q.ptr, nullptr, (int8_t *)c->spikes.ptr, (int32_t *)c->flags.ptr,
                              B, T, st));
     const long long n = B * p.C2;
-    k_neuron<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const int8_t *)c->spikes.ptr, (float *)c->vmem.ptr, p, B, T);
+    k_neuron_seg<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const int8_t *)c->spikes.ptr, (float *)c->vmem.ptr, p, B, T, (int)T, 0, 1);
     dim3 gg((unsigned)B, (unsigned)((p.C2 * p.C2 + 255) / 256));
     k_gram<<<gg, 256, 0, st>>>((const float *)c->vmem.ptr, gram_dev, p.C2, T, t_start);
     count_launch(2);

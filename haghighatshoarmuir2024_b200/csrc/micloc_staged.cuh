@@ -101,25 +101,9 @@ k_chain(const IN_T *__restrict__ audio, const float *__restrict__ q, const float
 }
 
 // ---------------------------------------------------------------------------
-// S3: neuron filter   vmem[b][t][c] = sum_{n<L} h[n] * spikes[b][t-n][c]
-//     (snn_beamformer.py:364)
+// S3: neuron filter   vmem[b][t][c] = sum_{n<L} h[n] * spikes[b][t-n][c]   (snn_beamformer.py:364)
+//     is k_neuron_seg below (one segment per chain = the sequential recurrence).
 // ---------------------------------------------------------------------------
-static __global__ void __launch_bounds__(128)
-k_neuron(const int8_t *__restrict__ spikes, float *__restrict__ vmem,
-         const __grid_constant__ ChainParams p, long long B, long long T) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * p.C2) return;
-    const long long b = idx / p.C2;
-    const int c = (int)(idx % p.C2);
-    const int8_t *sp = spikes + b * T * p.C2 + c;
-    float *vm = vmem + b * T * p.C2 + c;
-    NeuronState n; neuron_reset(n);
-    for (long long t = 0; t < T; ++t) {
-        const float s = (float)sp[t * p.C2];
-        const float sd = t >= p.nL ? (float)sp[(t - p.nL) * p.C2] : 0.f;
-        vm[t * p.C2] = neuron_step(p, n, s, sd);
-    }
-}
 
 // band-pass output of one clip -> input of the unbounded float64 encoder (heal_overflow).  Denormals become zeros:
 // in digital silence the float32 filter never decays to 0 but cycles through denormals, whose sign changes are noise.
