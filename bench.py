@@ -581,7 +581,7 @@ def run_extras(args, local, fp32_peak, lib):
         res[name] = {
             "workload": what, "clips": B, "clip_samples": int(x.shape[1]), "num_mic": M, "num_doa": int(g["bf_mat"].shape[1]),
             "path": "fused k_fused_tc (1 launch)" if fused and not eng._fused_unsupported else
-                    f"staged, time-segmented kernels ({launches} launches)",
+                    f"staged kernels: tensor-core STHT / Gram for wide arrays, time-segmented chains for long clips ({launches} launches)",
             "ms": ms, "clips_per_sec": B / ms * 1e3, "mic_msamples_per_sec": B * x.shape[1] * M / ms / 1e3,
             "roofline": {"bound": "fp32", "flop_per_mic_sample": F, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak},
@@ -633,6 +633,14 @@ def run_extras(args, local, fp32_peak, lib):
         one_ms, _ = _timed(torch, lambda: SnnEngineCache.run(g, x[:1], local))
         res[key]["one_clip_ms"] = one_ms
         del x
+        if name == "snn_c5_linear64":
+            # the same array as a Monte-Carlo batch: many one-second clips (unsegmented chains, tensor-core STHT / Gram)
+            nb5 = 256
+            xb = synthesize_clips(g["r_vec"], g["theta_vec"], FS, T, rng.uniform(0.3, 2.8, nb5), snr_lin=np.full(nb5, 10.0),
+                                  sine_freq=f0, mode=0, seed=74, device=local)
+            fp32_entry("c5_linear64_batch", g, xb, 0, fused=False,
+                       what=f"{nb5} x 1 s clips on the 64-mic linear array of configs[4], G=512")
+            del xb
 
     # design time: SNNBeamformer.design_from_template on the G = 449 grid of configs[1] -- per-DoA front
     # end + neuron filter + covariance batched on the GPU (micloc_snn_gram), the 449 small eigen-problems on the host
