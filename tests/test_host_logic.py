@@ -112,3 +112,48 @@ def test_doa_histogram_groups():
     h = D.doa_histogram(doa, 4, grp, 2)
     assert h.tolist() == [[1, 0, 0, 1], [1, 1, 0, 1]]
     assert D.doa_histogram(doa, 4).tolist() == [[2, 1, 0, 2]]
+
+
+@pytest.mark.parametrize("tap_first,n_taps,T", [(1, 240, 1500), (3, 24, 700), (0, 8, 300), (1, 17, 401)])
+def test_polyphase_toeplitz_block_algebra_of_the_tensor_core_stht(tap_first, n_taps, T):
+    """The index algebra of k_stht_tc (csrc/micloc_staged.cuh), restated in numpy: a stride-2 FIR as two dense FIRs over
+    the input parities, each a product of 16 x 16 Toeplitz blocks that depend on (row block - k step) only:
+        Q[2u + pi] = sum_j g[j] xs[u - j - c],  xs[v] = x[2v + rho],  pi = (rho + tap_first) & 1,  c = (tap_first + rho - pi) / 2,
+        tile: D[a][n] = sum_e A[a][e] B[e][n],  A[a][e] = g[a - e + L],  L = 16 (ND - 1),  ND = (n_taps + 14) // 16 + 1,
+        block (mb, ks): tap index j = 16 d + r - c',  d = mb - ks + ND - 1  (0 <= d < ND, else the block is zero).
+    Checked against np.convolve with the zero-stuffed kernel (zero initial state: lfilter's)."""
+    rng = np.random.default_rng(n_taps)
+    g = rng.standard_normal(n_taps)
+    x = rng.standard_normal(T)
+    h = np.zeros(tap_first + 2 * (n_taps - 1) + 1)
+    h[tap_first::2] = g
+    ref = np.convolve(x, h)[:T]
+
+    MB = 8                                            # row blocks per parity and tile (kStMB)
+    U = 16 * MB
+    ND = (n_taps + 14) // 16 + 1
+    L = 16 * (ND - 1)
+    W = 16 * (MB + ND - 1)
+    frag = np.zeros((ND, 16, 16))                     # the ND distinct blocks (kernel: per-lane register fragments)
+    for d in range(ND):
+        for r in range(16):
+            for c in range(16):
+                j = 16 * d + r - c
+                if 0 <= j < n_taps:
+                    frag[d, r, c] = g[j]
+    out = np.zeros(T)
+    for u0 in range(0, (T + 1) // 2 + U, U):
+        for rho in (0, 1):
+            pi = (rho + tap_first) & 1
+            c = (tap_first + rho - pi) // 2
+            vb = u0 - c - L
+            idx = 2 * (vb + np.arange(W)) + rho        # staged window of the input parity rho
+            win = np.where((idx >= 0) & (idx < T), x[np.clip(idx, 0, T - 1)], 0.0)
+            for mb in range(MB):
+                acc = np.zeros(16)
+                for ks in range(mb, mb + ND):          # the ND k steps whose block is not zero
+                    acc += frag[mb - ks + ND - 1] @ win[16 * ks: 16 * ks + 16]
+                t = 2 * (u0 + 16 * mb + np.arange(16)) + pi
+                ok = t < T
+                out[t[ok]] = acc[ok]
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
