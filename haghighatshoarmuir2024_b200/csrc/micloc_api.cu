@@ -84,8 +84,11 @@ static bool plan_segments(const micloc_snn *c, long long B, long long T, int nb,
     int warm = (int)std::ceil(std::log(1e-9) / std::log(c->pole_radius)) + 2 * rzcc_lag(p.w);
     warm = (warm + 31) & ~31;
     // The chains are latency-bound (one dependent recurrence per thread): what counts is threads in flight, not work.
-    // Aim at 16 warps per SM; a segment is never shorter than its own warm-up (2.1 x the sequential work at worst).
-    const long long want = (512ll * c->sm_count + chains - 1) / chains;      // segments per chain that fill the GPU
+    // Aim at ONE full wave of the block-wise chain kernel -- 3 CTAs of 128 threads per SM (its register budget) -- and
+    // never more: a few CTAs beyond the wave would run alone for a whole segment.  A segment is never shorter than its
+    // own warm-up (2.1 x the sequential work at worst).
+    long long want = (3ll * kChainBlkThreads * c->sm_count) / chains;        // segments per chain that fill the GPU
+    if (want < 1) want = 1;
     long long seg = (T + want - 1) / want;
     if (seg < warm) seg = warm;
     seg = (seg + 31) & ~31ll;
